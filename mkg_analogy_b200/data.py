@@ -1,0 +1,162 @@
+"""Seeded synthetic MARS-shaped batches.
+
+Host-side logic only.  The batch schema is the one the reference collator produces
+(MarT/data/data_module.py:48-182) and `TransformerLitModel.training_step` consumes
+(MarT/lit_models/transformer.py:59-109): input_ids / attention_mask / token_type_ids (B, L) int64,
+pixel_values (B, 2, 3, S, S) fp32, sep_idx (B, 6), label, rel_idx (B, 2), q_head_idx, a_head_idx, pre_type.
+"""
+from dataclasses import dataclass
+
+import torch
+
+CLS, SEP, MASK, PAD = 101, 102, 103, 0
+
+
+@dataclass(frozen=True)
+class VocabLayout:
+    """Token-id layout after the reference adds its special tokens (data_module.py:195-206, transformer.py:41-54):
+    [0, word_vocab) word pieces, then entities, then relations, then "[R]" as the last id."""
+    word_vocab: int = 30522
+    n_entities: int = 11292
+    n_relations: int = 192
+    n_analogy_entities: int = 2063
+    n_analogy_relations: int = 27
+    filler_lo: int = 1000
+    filler_hi: int = 30000
+
+    @property
+    def entity_id_st(self):
+        return self.word_vocab
+
+    @property
+    def entity_id_ed(self):
+        return self.word_vocab + self.n_entities
+
+    @property
+    def relation_id_st(self):
+        return self.entity_id_ed
+
+    @property
+    def relation_id_ed(self):
+        return self.entity_id_ed + self.n_relations
+
+    @property
+    def r_token(self):
+        return self.relation_id_ed
+
+    @property
+    def vocab(self):
+        return self.relation_id_ed + 1
+
+    def analogy_entity_ids(self, seed=7):
+        g = torch.Generator().manual_seed(seed)
+        perm = torch.randperm(self.n_entities, generator=g)[: self.n_analogy_entities]
+        return (perm.sort().values + self.entity_id_st).tolist()
+
+    def analogy_relation_ids(self, seed=7):
+        g = torch.Generator().manual_seed(seed + 1)
+        perm = torch.randperm(self.n_relations, generator=g)[: self.n_analogy_relations]
+        return (perm.sort().values + self.relation_id_st).tolist()
+
+
+MARS_VOCAB = VocabLayout()
+TINY_VOCAB = VocabLayout(word_vocab=500, n_entities=150, n_relations=40, n_analogy_entities=60,
+                         n_analogy_relations=9, filler_lo=110, filler_hi=500)
+
+
+def _composition(total, parts, g):
+    """Random non-negative integers summing to `total`."""
+    if total <= 0:
+        return [0] * parts
+    cuts = torch.randint(0, total + 1, (parts - 1,), generator=g).sort().values.tolist()
+    edges = [0] + cuts + [total]
+    return [edges[i + 1] - edges[i] for i in range(parts)]
+
+
+def make_finetune_batch(B, L, image_size=224, vocab: VocabLayout = MARS_VOCAB, seed=1234, pad=True, min_len=24):
+    """One fine-tune batch.  Prompt structure per sample (positions):
+    [CLS] e_h ... [SEP]0 ... [R] ... [SEP]1 e_t ... [SEP]2 e_q ... [SEP]3 ... [R] ... [SEP]4 ... [MASK] ... [SEP]5 [PAD]*
+    s = sep_idx[:, 2] is the split used by the adaptive attention scaling (modeling_unimo.py:342-349)."""
+    g = torch.Generator().manual_seed(seed)
+    assert L >= 14
+    min_len = max(14, min(min_len, L))
+    ids = torch.zeros(B, L, dtype=torch.long)
+    att = torch.zeros(B, L, dtype=torch.long)
+    tt = torch.zeros(B, L, dtype=torch.long)
+    sep_idx = torch.zeros(B, 6, dtype=torch.long)
+    rel_idx = torch.zeros(B, 2, dtype=torch.long)
+    q_head = torch.ones(B, dtype=torch.long)
+    a_head = torch.zeros(B, dtype=torch.long)
+    for b in range(B):
+        n = int(torch.randint(min_len, L + 1, (1,), generator=g)) if pad else L
+        s_hi = min(40, n - 8)
+        s_lo = min(max(6, 8), s_hi)
+        s = int(torch.randint(s_lo, s_hi + 1, (1,), generator=g))
+        a, bb, c = _composition(s - 6, 3, g)
+        d, e, f = _composition(n - 7 - s, 3, g)
+        row = torch.randint(vocab.filler_lo, vocab.filler_hi, (n,), generator=g)
+        ent = torch.randint(vocab.entity_id_st, vocab.entity_id_ed, (3,), generator=g)
+        row[0] = CLS
+        row[1] = ent[0]
+        sep0 = 2 + a
+        sep1 = sep0 + 2 + bb
+        sep2 = sep1 + 2 + c
+        sep3 = sep2 + 2 + d
+        sep4 = sep3 + 2 + e
+        sep5 = sep4 + 2 + f
+        assert sep2 == s and sep5 == n - 1, (sep2, s, sep5, n)
+        for k, p in enumerate((sep0, sep1, sep2, sep3, sep4, sep5)):
+            row[p] = SEP
+            sep_idx[b, k] = p
+        r0 = sep0 + 1 + int(torch.randint(0, bb + 1, (1,), generator=g))
+        r1 = sep3 + 1 + int(torch.randint(0, e + 1, (1,), generator=g))
+        row[r0] = vocab.r_token
+        row[r1] = vocab.r_token
+        rel_idx[b, 0], rel_idx[b, 1] = r0, r1
+        row[sep1 + 1] = ent[1]
+        row[s + 1] = ent[2]
+        a_head[b] = s + 1
+        mpos = sep4 + 1 + int(torch.randint(0, f + 1, (1,), generator=g))
+        row[mpos] = MASK
+        ids[b, :n] = row
+        att[b, :n] = 1
+        tt[b, s + 1:n] = 1
+    px = torch.randn(B, 2, 3, image_size, image_size, generator=g)
+    mode = torch.rand(B, generator=g)
+    px[mode < 0.4, 1] = 0.0   # "[PAD] image" = zeros (data_module.py:134-142); MARS mode-0 share is 40 %
+    label = torch.randint(0, vocab.n_analogy_entities, (B,), generator=g)
+    return {
+        "input_ids": ids, "attention_mask": att, "token_type_ids": tt, "pixel_values": px, "sep_idx": sep_idx,
+        "label": label, "rel_idx": rel_idx, "q_head_idx": q_head, "a_head_idx": a_head,
+        "rel_label": torch.randint(0, vocab.n_analogy_relations, (B,), generator=g),
+        "pre_type": torch.zeros(B, dtype=torch.long),
+    }
+
+
+def make_pretrain_batch(B, L, image_size=224, vocab: VocabLayout = MARS_VOCAB, seed=4321, min_len=12):
+    """Pre-train batch (transformer.py:72-90): no sep_idx; pre_type 1 = entity prediction over
+    [entity_id_st, entity_id_ed), 2 = relation prediction over [relation_id_st, relation_id_ed)."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.zeros(B, L, dtype=torch.long)
+    att = torch.zeros(B, L, dtype=torch.long)
+    tt = torch.zeros(B, L, dtype=torch.long)
+    pre_type = torch.randint(1, 3, (B,), generator=g)
+    label = torch.zeros(B, dtype=torch.long)
+    for b in range(B):
+        n = int(torch.randint(min(min_len, L), L + 1, (1,), generator=g))
+        row = torch.randint(vocab.filler_lo, vocab.filler_hi, (n,), generator=g)
+        row[0] = CLS
+        row[1] = int(torch.randint(vocab.entity_id_st, vocab.entity_id_ed, (1,), generator=g))
+        row[n - 1] = SEP
+        mpos = int(torch.randint(2, n - 1, (1,), generator=g))
+        row[mpos] = MASK
+        ids[b, :n] = row
+        att[b, :n] = 1
+        if pre_type[b] == 2:
+            label[b] = int(torch.randint(0, vocab.n_relations, (1,), generator=g))
+        else:
+            label[b] = int(torch.randint(0, vocab.n_entities, (1,), generator=g))
+    px = torch.randn(B, 2, 3, image_size, image_size, generator=g)
+    px[torch.rand(B, generator=g) < 0.4, 1] = 0.0
+    return {"input_ids": ids, "attention_mask": att, "token_type_ids": tt, "pixel_values": px,
+            "label": label, "pre_type": pre_type}
