@@ -1,0 +1,95 @@
+"""The oracle restatement (oracle/mkgformer_oracle.py) against golden outputs of the REFERENCE itself
+(tests/golden/*.pt, produced by oracle/make_golden.py in the build container). fp32 on CPU; tolerance:
+abs 2e-5 on logits/hidden (different but equivalent op order), rel 2e-4 on gradients."""
+import os
+
+import pytest
+import torch
+
+from mkg_analogy_b200.config import MKGformerConfig, init_params
+from mkg_analogy_b200.data import TINY_VOCAB, make_finetune_batch, make_pretrain_batch
+from oracle import mkgformer_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    g = torch.load(os.path.join(GOLD, "mkgformer_tiny.pt"), weights_only=False)
+    cfg = MKGformerConfig(**g["cfg"])
+    params = init_params(cfg, g["seed_w"])
+    batch = make_finetune_batch(g["B"], g["L"], cfg.image_size, TINY_VOCAB, seed=g["seed_b"], min_len=16)
+    chk = float(sum(t.double().abs().sum().item() for t in params.values()))
+    assert abs(chk - g["param_checksum"]) < 1e-6 * g["param_checksum"], "seeded weights drifted from the fixture"
+    bchk = float(sum(t.double().abs().sum().item() for t in (batch["input_ids"], batch["pixel_values"], batch["sep_idx"])))
+    assert abs(bchk - g["batch_checksum"]) < 1e-6 * g["batch_checksum"], "seeded batch drifted from the fixture"
+    return g, cfg, params, batch
+
+
+def test_forward_logits_and_hidden(tiny):
+    g, cfg, P, batch = tiny
+    with torch.no_grad():
+        logits, z = O.forward(P, cfg, batch, full_logits=True)
+    mpos = O.mask_positions(batch["input_ids"])
+    B = z.shape[0]
+    assert torch.allclose(z, g["ft_trans"], atol=2e-5, rtol=1e-4)
+    assert torch.allclose(logits[torch.arange(B), mpos], g["ft_mask_logits_full"], atol=2e-5, rtol=1e-4)
+    assert torch.allclose(logits[0], g["ft_logits_row0"], atol=2e-5, rtol=1e-4)
+
+
+def test_finetune_loss_grads_ranks(tiny):
+    g, cfg, P, batch = tiny
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    loss, x, _ = O.finetune_loss(Pg, cfg, batch, TINY_VOCAB.analogy_entity_ids(), alpha=0.43, label_smoothing=0.1)
+    assert abs(loss.item() - g["ft_loss"].item()) < 1e-5
+    loss.backward()
+    for name, ref_norm in g["ft_grad_norm"].items():
+        if name.startswith("cls.predictions.decoder"):
+            continue
+        gr = Pg[name].grad
+        if ref_norm is None:
+            assert gr is None or gr.abs().max().item() == 0.0, f"{name} must have no gradient"
+            continue
+        assert gr is not None, name
+        assert abs(gr.norm().item() - ref_norm) <= 2e-4 * ref_norm + 1e-7, (name, gr.norm().item(), ref_norm)
+    for name, ref in g["ft_grad_full"].items():
+        gr = Pg[name].grad
+        if name.endswith("patch_embedding.weight"):
+            gr = gr[:8]
+        assert torch.allclose(gr, ref, atol=1e-6, rtol=2e-4), name
+    ranks = O.ranks_of_gold(x.detach(), batch["label"])
+    assert torch.equal(ranks, g["ft_ranks"])
+
+
+def test_pretrain_loss_and_grad_norms(tiny):
+    g, cfg, P, _ = tiny
+    pb = make_pretrain_batch(g["B"], g["L"], cfg.image_size, TINY_VOCAB, seed=g["seed_b"] + 1)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    loss = O.pretrain_loss(Pg, cfg, pb, (TINY_VOCAB.entity_id_st, TINY_VOCAB.entity_id_ed),
+                           (TINY_VOCAB.relation_id_st, TINY_VOCAB.relation_id_ed), label_smoothing=0.1)
+    assert abs(loss.item() - g["pt_loss"].item()) < 1e-5
+    loss.backward()
+    for name, ref_norm in g["pt_grad_norm"].items():
+        if name.startswith("cls.predictions.decoder"):
+            continue
+        gr = Pg[name].grad
+        if ref_norm is None:
+            assert gr is None or gr.abs().max().item() == 0.0, name
+        else:
+            assert abs(gr.norm().item() - ref_norm) <= 2e-4 * ref_norm + 1e-7, name
+
+
+def test_label_smooth_ce_known_answers():
+    g = torch.load(os.path.join(GOLD, "ls_ce.pt"), weights_only=False)
+    for tag, c in g.items():
+        x = c["x"].clone().requires_grad_(True)
+        loss = O.label_smooth_ce(x, c["y"], 0.1)
+        (gx,) = torch.autograd.grad(loss, x)
+        assert torch.allclose(loss, c["loss"], atol=1e-6, rtol=1e-6), tag
+        assert torch.allclose(gx, c["grad"], atol=1e-7, rtol=1e-5), tag
+        # closed form of SURVEY.md App. A: dx = ((sum q) softmax(x) - q) / n_valid
+        C = x.shape[1]
+        valid = c["y"] != -100
+        q = torch.full_like(x, 0.1 / C).scatter_(1, c["y"].clamp(min=0)[:, None], 0.9)
+        closed = ((1 - 0.1 / C) * torch.softmax(x, 1) - q) * valid[:, None] / valid.sum()
+        assert torch.allclose(closed.detach(), c["grad"], atol=1e-7, rtol=1e-5), tag

@@ -1,0 +1,57 @@
+"""Pins the oracle restatement against the reference code executed live from /root/reference (build container
+only; skipped on the GPU box). Covers a second seed / shape than the committed golden fixture, and the AdamW
+restatement against torch.optim.AdamW with the reference's parameter grouping (lit_models/transformer.py:224-241)."""
+import pytest
+import torch
+
+from mkg_analogy_b200.config import MKGformerConfig, init_params
+from mkg_analogy_b200.data import TINY_VOCAB, make_finetune_batch
+from oracle import mkgformer_oracle as O
+from oracle import reference_loader as RL
+
+pytestmark = pytest.mark.reference
+
+
+def test_forward_matches_reference_other_seed():
+    cfg = MKGformerConfig(hidden=128, layers=9, heads=2, intermediate=256, vocab=TINY_VOCAB.vocab, max_position=64,
+                          image_size=64, patch=32)
+    P = init_params(cfg, 3)
+    model = RL.build_reference_model(cfg, P)
+    batch = make_finetune_batch(3, 32, cfg.image_size, TINY_VOCAB, seed=99, min_len=20)
+    with torch.no_grad():
+        mo = model(**{k: batch[k] for k in ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "sep_idx")},
+                   return_dict=True)
+        logits, z = O.forward(P, cfg, batch)
+    assert torch.allclose(logits, mo[0].logits, atol=2e-5, rtol=1e-4)
+    assert torch.allclose(z, mo[1], atol=2e-5, rtol=1e-4)
+
+
+def test_state_dict_contract_matches_reference():
+    from mkg_analogy_b200.config import TINY, param_shapes
+    model = RL.build_reference_model(TINY)
+    ref = {k: tuple(v.shape) for k, v in model.named_parameters()}
+    mine = param_shapes(TINY)
+    assert set(ref) == set(mine), (set(ref) ^ set(mine))
+    for k in ref:
+        assert tuple(mine[k]) == ref[k], k
+
+
+def test_adamw_restatement_matches_torch():
+    g = torch.Generator().manual_seed(0)
+    names = ["a.weight", "a.bias", "x.LayerNorm.weight", "v.layer_norm1.weight"]
+    params = {n: torch.randn(5, 3, generator=g) for n in names}
+    grads = {n: torch.randn(5, 3, generator=g) for n in names}
+    tp = {n: torch.nn.Parameter(p.clone()) for n, p in params.items()}
+    no_decay = ["bias", "LayerNorm.weight"]
+    opt = torch.optim.AdamW([
+        {"params": [p for n, p in tp.items() if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
+        {"params": [p for n, p in tp.items() if any(nd in n for nd in no_decay)], "weight_decay": 0.0}],
+        lr=5e-5, eps=1e-8)
+    state = {}
+    for step in (1, 2, 3):
+        for n in names:
+            tp[n].grad = grads[n].clone() * step
+        opt.step()
+        O.adamw_step(params, {n: grads[n] * step for n in names}, state, step, 5e-5)
+    for n in names:
+        assert torch.allclose(params[n], tp[n].detach(), atol=1e-7, rtol=1e-6), n
