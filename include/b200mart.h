@@ -44,7 +44,7 @@ int32_t b200mart_version(void);
  * modeling_unimo.py:221-226,:283-287 (CLIP), :327-334,:388,:458-462,:475 (BERT), :972-976,:958 (head).
  *   a_mn/b_mn: 0 = operand stored [rows][K] (K contiguous); 1 = stored [K][rows].
  *   (A2,B2,K2): optional second operand pair extending the contraction (K must be a multiple of 64).
- *   epilogue order: *alpha, +bias[n], store out_preact, act (1 gelu-erf, 2 quick-gelu),
+ *   epilogue order: *alpha, +bias[n] (+bias2[n]), store out_preact, act (1 gelu-erf, 2 quick-gelu),
  *                   *act'(dact_src) (dact 1/2), +residual, store out_f32 (or atomically accumulate) / out_bf16.
  */
 typedef struct b200mart_gemm_desc {
@@ -56,6 +56,7 @@ typedef struct b200mart_gemm_desc {
     const void* B2; int64_t ldb2;
     float alpha;
     const float* bias;
+    const float* bias2;            /* optional second bias (bias of the second operand pair) */
     void* out_preact; int64_t ldp; /* bf16 */
     int32_t act;
     const void* dact_src; int64_t ldx; int32_t dact;
@@ -68,6 +69,161 @@ typedef struct b200mart_gemm_desc {
 } b200mart_gemm_desc;
 
 int32_t b200mart_gemm_bf16(const b200mart_gemm_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MKGformer model handle.  Shapes follow the reference's two HF configs (BertConfig for the text
+ * stream, CLIPVisionConfig for the vision stream; MarT/main.py:76-86); fuse_from is the layer index 8
+ * hard-coded at MarT/models/modeling_unimo.py:616,627.
+ */
+typedef struct b200mart_model_desc {
+    int32_t hidden, layers, heads, intermediate;
+    int32_t vocab, max_position, type_vocab;
+    int32_t image_size, patch;
+    int32_t fuse_from;
+    float text_eps, vision_eps;
+} b200mart_model_desc;
+
+typedef struct b200mart_handle b200mart_handle;
+
+int32_t b200mart_create(const b200mart_model_desc* desc, b200mart_handle** out);
+void b200mart_destroy(b200mart_handle* h);
+
+/* Parameter storage.  All parameters of the reference module (state_dict contract of SURVEY.md §8a,
+ * modeling_unimo.py:100-186,:189-287,:290-478,:661-673,:942-976) live in ONE flat fp32 buffer owned by the
+ * caller (so that torch nn.Parameters can be views of it), mirrored by a flat bf16 buffer of the same
+ * layout (tensor-core operands) and a flat fp32 gradient buffer.  The library fixes the layout
+ * (q/k/v projection weights and biases of a layer are adjacent so that they form one [3H, H] operand). */
+int32_t b200mart_param_count(const b200mart_handle* h);
+int64_t b200mart_param_total(const b200mart_handle* h);              /* elements of the flat buffers */
+int32_t b200mart_param_info(const b200mart_handle* h, int32_t index, const char** name, int64_t* offset,
+                            int32_t* ndim, int64_t shape[4], int32_t* decay, int32_t* unused_in_finetune);
+/* params16[i] = bf16(params32[i]) over the whole flat buffer */
+int32_t b200mart_cast_params(const b200mart_handle* h, const float* params32, void* params16, void* stream);
+
+/* Workspace: activations saved for backward + scratch, for a batch of B samples x L text tokens. */
+int64_t b200mart_workspace_bytes(const b200mart_handle* h, int32_t B, int32_t L);
+
+typedef struct b200mart_buffers {
+    const float* params32;     /* flat fp32 parameters (biases, LayerNorm, embeddings are read from here) */
+    const void* params16;      /* flat bf16 mirror (GEMM operands) */
+    float* grads32;            /* flat fp32 gradients, ACCUMULATED into (caller zeroes); may be NULL for inference */
+    void* workspace;
+    int64_t workspace_bytes;
+} b200mart_buffers;
+
+/* One batch, as produced by the reference collator (MarT/data/data_module.py:48-182) and passed as
+ * `self.model(**batch)` at MarT/lit_models/transformer.py:68.  Device pointers. */
+typedef struct b200mart_batch {
+    int32_t B, L;
+    const int64_t* input_ids;       /* (B, L) */
+    const int64_t* attention_mask;  /* (B, L) */
+    const int64_t* token_type_ids;  /* (B, L) or NULL (zeros) */
+    const float* pixel_values;      /* (B, 2, 3, S, S) fp32 */
+    const int64_t* sep_idx;         /* (B, 6) or NULL: no adaptive scaling (pre-training) */
+} b200mart_batch;
+
+/* UnimoForMaskedLM.forward (modeling_unimo.py:848-893) in eval-mode arithmetic (dropout p = 0).
+ *   z_out      (B, L, hidden) fp32: trans_hidden_states = model_output[1]              (may be NULL)
+ *   logits_out (B, L, vocab)  fp32: model_output[0].logits, the dense "compat" head    (may be NULL)
+ * Activations needed by b200mart_backward stay in the workspace until the next forward. */
+int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* bufs, const b200mart_batch* batch,
+                         float* z_out, float* logits_out, void* stream);
+
+/* Score head + loss on the [MASK] rows only (TransformerLitModel.training_step, transformer.py:59-113).
+ *   mode 0 (fine-tune, :92-109): logits over `col_ids` (n_cols analogy entity ids), loss =
+ *       LS-CE(label) + alpha * relaxation(rel_idx, q_head_idx, a_head_idx).
+ *   mode 1 (pre-train, :72-90): rows with pre_type != 2 are scored over [ent_st, ent_ed), rows with
+ *       pre_type == 2 over [rel_st, rel_ed); loss = CE_entity + CE_relation.
+ * label_smoothing = 0 selects plain cross-entropy (transformer.py:22-25).
+ *   loss_out        device float[1]
+ *   mask_logits_out fp32, mode 0: (B, n_cols); mode 1: (B, n_ent + n_rel) = [entity | relation] scores  (may be NULL)
+ *   ranks_out       int64, mode 0: (B); mode 1: (B) rank within the row's own group (_eval, :115-166) (may be NULL)
+ * With compute_grad != 0 the gradient wrt trans_hidden_states is left in the workspace for
+ * b200mart_backward and the tied-embedding / decoder-bias gradients are accumulated into grads32. */
+typedef struct b200mart_head {
+    int32_t mode;
+    const int64_t* col_ids; int32_t n_cols;
+    int32_t ent_st, ent_ed, rel_st, rel_ed;
+    const int64_t* label;
+    const int64_t* pre_type;
+    const int64_t* rel_idx;      /* (B, 2) */
+    const int64_t* q_head_idx;   /* (B) */
+    const int64_t* a_head_idx;   /* (B) */
+    float label_smoothing, alpha;
+    int32_t mask_token_id;
+} b200mart_head;
+
+int32_t b200mart_head_loss(b200mart_handle* h, const b200mart_buffers* bufs, const b200mart_batch* batch,
+                           const b200mart_head* head, float* loss_out, float* mask_logits_out, int64_t* ranks_out,
+                           int32_t compute_grad, void* stream);
+
+/* Backward of b200mart_forward (what torch autograd does for the reference graph).  The gradient wrt
+ * trans_hidden_states is the one left by b200mart_head_loss, plus dz_extra (B, L, hidden) fp32 when given
+ * (use_head_grad = 0: dz_extra alone).  dlogits (B, L, vocab) fp32, when given, is the gradient of the dense
+ * compat logits; dlogits_scratch must then hold B*L*roundup(vocab, 8) bf16.  Accumulates into grads32. */
+int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers* bufs, const b200mart_batch* batch,
+                          int32_t use_head_grad, const float* dz_extra, const float* dlogits, void* dlogits_scratch,
+                          void* stream);
+
+/* torch.optim.AdamW step as configured at transformer.py:224-241 over the flat buffers, refreshing the bf16
+ * mirror.  `step` is 1-based.  Parameters the reference never gives a gradient (text_pooler, vision_post_layernorm,
+ * fusion_dense of text layers < fuse_from; in pre-training also adaptive_weight) are left untouched, as torch skips
+ * parameters whose .grad is None. */
+int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* params16, const float* grads32, float* exp_avg,
+                       float* exp_avg_sq, int32_t step, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int32_t pretrain, void* stream);
+
+/* Device-side status flags of the last calls on this workspace (synchronises the stream):
+ * bit0 token id out of range, bit1 token type out of range, bit2 a row without exactly one [MASK]. */
+int32_t b200mart_status(b200mart_handle* h, const b200mart_buffers* bufs, void* stream, int32_t* flags_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone operators (kernel-level parity tests; also the building blocks of the functions above).
+ */
+/* Fused attention, head_dim 64 (BertSelfAttention :317-377 with adaptive scaling :342-349 and -1e4 mask;
+ * CLIPAttention :212-272 with an optional K/V prefix).  q/k/v bf16 row-major with leading dimensions in
+ * elements, head h at columns [64h, 64h+64).  prefix_k/v: (B*n_prefix rows) or NULL. */
+typedef struct b200mart_attn_desc {
+    int32_t B, Lq, heads, n_prefix, n_keys;
+    float scale;
+    const void* q; int64_t ldq;
+    const void* prefix_k; const void* prefix_v; int64_t ld_prefix;
+    const void* k; const void* v; int64_t ldkv;
+    const int64_t* key_mask;     /* (B, n_keys) 1 = keep, NULL = no mask */
+    const int64_t* sep_idx;      /* (B, 6) or NULL */
+    const float* w0; const float* w1;
+    void* out; int64_t ldo;      /* bf16 context (B*Lq, heads*64) */
+    float* out_f32;              /* optional fp32 copy, same layout */
+    float* lse;                  /* (B, heads, Lq) */
+    /* backward only */
+    const float* dout; int64_t lddo;
+    void* dq; void* dk; void* dv; int64_t ldd;             /* bf16 */
+    const float* dk_add; const float* dv_add; int64_t ldadd;
+    float* dprefix_k; float* dprefix_v; int64_t ldd_prefix; /* fp32 */
+    float* dw0; float* dw1;
+    float* delta;                /* scratch (B, heads, Lq) */
+} b200mart_attn_desc;
+int32_t b200mart_attention_fwd(const b200mart_attn_desc* d, void* stream);
+int32_t b200mart_attention_bwd(const b200mart_attn_desc* d, void* stream);
+
+/* BertFusion (modeling_unimo.py:400-414), fp32: out = softmax(ctx vh^T) vh. */
+int32_t b200mart_fusion_fwd(const float* ctx, const float* vh, void* out_bf16, float* lse, int32_t B, int32_t L,
+                            int32_t Nv, int32_t H, void* stream);
+int32_t b200mart_fusion_bwd(const float* dg, const float* ctx, const float* vh, const float* lse, float* pbuf,
+                            float* dsbuf, float* dctx_accum, const float* dvh_in, float* dvh_out, int32_t B, int32_t L,
+                            int32_t Nv, int32_t H, void* stream);
+
+/* LayerNorm forward / backward over (M, H) fp32 rows, H % 128 == 0, H <= 1024. */
+int32_t b200mart_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y32, void* y16,
+                               float* mean, float* rstd, int32_t M, int32_t H, void* stream);
+int32_t b200mart_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                               const float* add, float* dx32, void* dx16, float* dgamma, float* dbeta, int32_t M,
+                               int32_t H, void* stream);
+
+/* LabelSmoothSoftmaxCEV1 (lit_models/utils.py:42-66) fused with its backward: loss[0] += mean loss,
+ * dlogits (B, C) fp32. */
+int32_t b200mart_ls_ce(const float* logits, int32_t B, int32_t C, const int64_t* label, float eps, float* loss,
+                       float* dlogits, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200mart.so")
 
+vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
 
 class B200MartError(RuntimeError):
     pass
@@ -17,23 +19,93 @@ class B200MartError(RuntimeError):
 
 class GemmDesc(C.Structure):
     _fields_ = [
-        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("K2", C.c_int32),
-        ("a_mn", C.c_int32), ("b_mn", C.c_int32),
-        ("A", C.c_void_p), ("lda", C.c_int64),
-        ("B", C.c_void_p), ("ldb", C.c_int64),
-        ("A2", C.c_void_p), ("lda2", C.c_int64),
-        ("B2", C.c_void_p), ("ldb2", C.c_int64),
-        ("alpha", C.c_float),
-        ("bias", C.c_void_p),
-        ("out_preact", C.c_void_p), ("ldp", C.c_int64),
-        ("act", C.c_int32),
-        ("dact_src", C.c_void_p), ("ldx", C.c_int64), ("dact", C.c_int32),
-        ("residual", C.c_void_p), ("ldr", C.c_int64),
-        ("out_f32", C.c_void_p), ("ldo32", C.c_int64),
-        ("out_bf16", C.c_void_p), ("ldo16", C.c_int64),
-        ("accumulate", C.c_int32), ("split_k", C.c_int32), ("bn", C.c_int32),
+        ("M", i32), ("N", i32), ("K", i32), ("K2", i32),
+        ("a_mn", i32), ("b_mn", i32),
+        ("A", vp), ("lda", i64),
+        ("B", vp), ("ldb", i64),
+        ("A2", vp), ("lda2", i64),
+        ("B2", vp), ("ldb2", i64),
+        ("alpha", f32),
+        ("bias", vp),
+        ("bias2", vp),
+        ("out_preact", vp), ("ldp", i64),
+        ("act", i32),
+        ("dact_src", vp), ("ldx", i64), ("dact", i32),
+        ("residual", vp), ("ldr", i64),
+        ("out_f32", vp), ("ldo32", i64),
+        ("out_bf16", vp), ("ldo16", i64),
+        ("accumulate", i32), ("split_k", i32), ("bn", i32),
     ]
 
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("hidden", i32), ("layers", i32), ("heads", i32), ("intermediate", i32),
+        ("vocab", i32), ("max_position", i32), ("type_vocab", i32),
+        ("image_size", i32), ("patch", i32), ("fuse_from", i32),
+        ("text_eps", f32), ("vision_eps", f32),
+    ]
+
+
+class Buffers(C.Structure):
+    _fields_ = [("params32", vp), ("params16", vp), ("grads32", vp), ("workspace", vp), ("workspace_bytes", i64)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("B", i32), ("L", i32), ("input_ids", vp), ("attention_mask", vp), ("token_type_ids", vp),
+                ("pixel_values", vp), ("sep_idx", vp)]
+
+
+class Head(C.Structure):
+    _fields_ = [("mode", i32), ("col_ids", vp), ("n_cols", i32),
+                ("ent_st", i32), ("ent_ed", i32), ("rel_st", i32), ("rel_ed", i32),
+                ("label", vp), ("pre_type", vp), ("rel_idx", vp), ("q_head_idx", vp), ("a_head_idx", vp),
+                ("label_smoothing", f32), ("alpha", f32), ("mask_token_id", i32)]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("B", i32), ("Lq", i32), ("heads", i32), ("n_prefix", i32), ("n_keys", i32),
+        ("scale", f32),
+        ("q", vp), ("ldq", i64),
+        ("prefix_k", vp), ("prefix_v", vp), ("ld_prefix", i64),
+        ("k", vp), ("v", vp), ("ldkv", i64),
+        ("key_mask", vp), ("sep_idx", vp), ("w0", vp), ("w1", vp),
+        ("out", vp), ("ldo", i64), ("out_f32", vp), ("lse", vp),
+        ("dout", vp), ("lddo", i64),
+        ("dq", vp), ("dk", vp), ("dv", vp), ("ldd", i64),
+        ("dk_add", vp), ("dv_add", vp), ("ldadd", i64),
+        ("dprefix_k", vp), ("dprefix_v", vp), ("ldd_prefix", i64),
+        ("dw0", vp), ("dw1", vp), ("delta", vp),
+    ]
+
+
+# every symbol include/b200mart.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "b200mart_last_error": (C.c_char_p, []),
+    "b200mart_version": (i32, []),
+    "b200mart_gemm_bf16": (i32, [C.POINTER(GemmDesc), vp]),
+    "b200mart_create": (i32, [C.POINTER(ModelDesc), C.POINTER(vp)]),
+    "b200mart_destroy": (None, [vp]),
+    "b200mart_param_count": (i32, [vp]),
+    "b200mart_param_total": (i64, [vp]),
+    "b200mart_param_info": (i32, [vp, i32, C.POINTER(C.c_char_p), C.POINTER(i64), C.POINTER(i32), C.POINTER(i64 * 4),
+                                  C.POINTER(i32), C.POINTER(i32)]),
+    "b200mart_cast_params": (i32, [vp, vp, vp, vp]),
+    "b200mart_workspace_bytes": (i64, [vp, i32, i32]),
+    "b200mart_forward": (i32, [vp, C.POINTER(Buffers), C.POINTER(Batch), vp, vp, vp]),
+    "b200mart_head_loss": (i32, [vp, C.POINTER(Buffers), C.POINTER(Batch), C.POINTER(Head), vp, vp, vp, i32, vp]),
+    "b200mart_backward": (i32, [vp, C.POINTER(Buffers), C.POINTER(Batch), i32, vp, vp, vp, vp]),
+    "b200mart_adamw": (i32, [vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, i32, vp]),
+    "b200mart_status": (i32, [vp, C.POINTER(Buffers), vp, C.POINTER(i32)]),
+    "b200mart_attention_fwd": (i32, [C.POINTER(AttnDesc), vp]),
+    "b200mart_attention_bwd": (i32, [C.POINTER(AttnDesc), vp]),
+    "b200mart_fusion_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "b200mart_fusion_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "b200mart_layernorm_fwd": (i32, [vp, vp, vp, f32, vp, vp, vp, vp, i32, i32, vp]),
+    "b200mart_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
+    "b200mart_ls_ce": (i32, [vp, i32, i32, vp, f32, vp, vp, vp]),
+}
 
 _lib = None
 
@@ -48,10 +120,10 @@ def lib():
             f"{LIB_PATH} not found: build it with `python -m mkg_analogy_b200.build` "
             "(there is no CPU or PyTorch fallback for this path)")
     l = C.CDLL(LIB_PATH)
-    l.b200mart_last_error.restype = C.c_char_p
-    l.b200mart_version.restype = C.c_int32
-    l.b200mart_gemm_bf16.restype = C.c_int32
-    l.b200mart_gemm_bf16.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(l, name)          # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
     _lib = l
     return l
 
@@ -61,15 +133,20 @@ def check(rc):
         raise B200MartError(f"b200mart error {rc}: {lib().b200mart_last_error().decode()}")
 
 
-def _ptr(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
+def ptr(t):
+    """Device (or host) address of a tensor, None for None."""
+    return None if t is None else t.data_ptr()
 
 
-def gemm_bf16(A, B, *, a_mn=False, b_mn=False, A2=None, B2=None, alpha=1.0, bias=None, act=0,
+def cur_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def gemm_bf16(A, B, *, a_mn=False, b_mn=False, A2=None, B2=None, alpha=1.0, bias=None, bias2=None, act=0,
               out_preact=None, dact_src=None, dact=0, residual=None, out_f32=None, out_bf16=None,
               accumulate=False, split_k=1, bn=0, stream=None):
     """D = epilogue(A @ B^T) on the tcgen05 kernel. Shapes: A [M,K] (or [K,M] when a_mn), B [N,K] (or [K,N])."""
-    import torch
     M, K = (A.shape[1], A.shape[0]) if a_mn else A.shape
     N = B.shape[1] if b_mn else B.shape[0]
     d = GemmDesc()
@@ -80,7 +157,8 @@ def gemm_bf16(A, B, *, a_mn=False, b_mn=False, A2=None, B2=None, alpha=1.0, bias
         d.K2 = A2.shape[0] if a_mn else A2.shape[1]
         d.A2, d.lda2, d.B2, d.ldb2 = A2.data_ptr(), A2.stride(0), B2.data_ptr(), B2.stride(0)
     d.alpha = alpha
-    d.bias = bias.data_ptr() if bias is not None else None
+    d.bias = ptr(bias)
+    d.bias2 = ptr(bias2)
     if out_preact is not None:
         d.out_preact, d.ldp = out_preact.data_ptr(), out_preact.stride(0)
     d.act = act
@@ -93,5 +171,5 @@ def gemm_bf16(A, B, *, a_mn=False, b_mn=False, A2=None, B2=None, alpha=1.0, bias
     if out_bf16 is not None:
         d.out_bf16, d.ldo16 = out_bf16.data_ptr(), out_bf16.stride(0)
     d.accumulate, d.split_k, d.bn = int(accumulate), split_k, bn
-    s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-    check(lib().b200mart_gemm_bf16(C.byref(d), C.c_void_p(s)))
+    s = stream if stream is not None else cur_stream()
+    check(lib().b200mart_gemm_bf16(C.byref(d), s))

@@ -1,20 +1,25 @@
-"""In-tree build of libb200mart.so (nvcc, sm_100a only) and of the oracle's C helpers.
+"""In-tree build of libb200mart.so (nvcc, sm_100a only).
 
-The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+Each csrc/*.cu is compiled to an object file in parallel (objects are cached by content hash under
+csrc/.obj/), then linked into one shared library.  The .so is git-ignored but travels to the GPU box with
+the gpurun snapshot.
 """
 import hashlib
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, ".obj")
 LIB = os.path.join(HERE, "libb200mart.so")
 STAMP = os.path.join(HERE, ".libb200mart.stamp")
+HEADER = os.path.join(HERE, "..", "include", "b200mart.h")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--use_fast_math",
+    "-Xcompiler", "-fPIC", "--use_fast_math",
 ]
 
 
@@ -22,17 +27,28 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _digest():
+def _headers_digest():
     h = hashlib.sha256()
-    files = sorted(os.listdir(CSRC)) + ["../../include/b200mart.h"]
-    for f in files:
-        p = os.path.join(CSRC, f)
-        if os.path.isfile(p):
-            h.update(f.encode())
-            with open(p, "rb") as fh:
-                h.update(fh.read())
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith(".cuh") or f.endswith(".h"):
+            with open(os.path.join(CSRC, f), "rb") as fh:
+                h.update(f.encode() + fh.read())
+    with open(HEADER, "rb") as fh:
+        h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
-    return h.hexdigest()
+    return h
+
+
+def _obj_digest(src, hd):
+    h = hd.copy()
+    with open(src, "rb") as fh:
+        h.update(fh.read())
+    return h.hexdigest()[:24]
+
+
+def _digest():
+    hd = _headers_digest()
+    return hashlib.sha256("".join(_obj_digest(s, hd) for s in sources()).encode()).hexdigest()
 
 
 def is_current():
@@ -47,13 +63,33 @@ def build(force=False, verbose=False):
     if not force and is_current():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libb200mart.so")
+    os.makedirs(OBJ, exist_ok=True)
+    hd = _headers_digest()
+
+    def compile_one(src):
+        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + "." + _obj_digest(src, hd) + ".o")
+        if os.path.exists(obj) and not force:
+            return obj, ""
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{res.stdout}{res.stderr}")
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, sources()))
+    objs = [o for o, _ in results]
     if verbose:
-        sys.stderr.write(res.stderr)
+        sys.stderr.write("".join(log for _, log in results))
+    # drop stale objects
+    keep = set(objs)
+    for f in os.listdir(OBJ):
+        p = os.path.join(OBJ, f)
+        if p not in keep:
+            os.remove(p)
+    res = subprocess.run([nvcc, "-shared", "-o", LIB] + objs, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link of libb200mart.so failed:\n" + res.stdout + res.stderr)
     with open(STAMP, "w") as fh:
         fh.write(_digest())
     return LIB

@@ -24,7 +24,7 @@ extern "C" int32_t b200mart_gemm_bf16(const b200mart_gemm_desc* d, void* stream)
     op.a_mn = d->a_mn; op.b_mn = d->b_mn;
     op.A = (const bf16*)d->A; op.lda = d->lda; op.B = (const bf16*)d->B; op.ldb = d->ldb;
     op.A2 = (const bf16*)d->A2; op.lda2 = d->lda2; op.B2 = (const bf16*)d->B2; op.ldb2 = d->ldb2;
-    op.alpha = d->alpha; op.bias = d->bias;
+    op.alpha = d->alpha; op.bias = d->bias; op.bias2 = d->bias2;
     op.out_preact = (bf16*)d->out_preact; op.ldp = d->ldp;
     op.act = d->act; op.dact_src = (const bf16*)d->dact_src; op.ldx = d->ldx; op.dact = d->dact;
     op.residual = d->residual; op.ldr = d->ldr;

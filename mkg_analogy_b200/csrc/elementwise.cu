@@ -1,0 +1,502 @@
+// HBM-bound kernels of the MKGformer step: casts, im2col, embedding gathers + LayerNorm, LayerNorm
+// forward/backward, column sums (bias gradients), embedding scatter-adds, AdamW.
+// Layout rule: one warp per row for everything LayerNorm-shaped (H % 128 == 0, H <= 1024), lanes own
+// float4 columns {lane*4 + 128*t}; all global accesses are 16-byte vectors.
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int MAXV = 8;  // float4 per lane -> H <= 1024
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4_bf16(bf16* p, float4 v) {
+    uint2 q = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    *reinterpret_cast<uint2*>(p) = q;
+}
+
+// ---------------------------------------------------------------- casts / fills
+__global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long n) {
+    long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const long stride = (long)gridDim.x * blockDim.x * 8;
+    for (; i + 8 <= n; i += stride) {
+        float4 a = ld4(src + i), b = ld4(src + i + 4);
+        uint4 q = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+        *reinterpret_cast<uint4*>(dst + i) = q;
+    }
+    if (i < n) for (long j = i; j < n && j < i + 8; ++j) dst[j] = __float2bfloat16(src[j]);
+}
+__global__ void fill_kernel(float* dst, float v, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = v;
+}
+
+__global__ void axpy_kernel(const float* __restrict__ src, float* dst, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] += src[i];
+}
+// row-wise fp32 -> bf16 cast into a padded destination (columns [cols, ld_dst) are zeroed)
+__global__ void cast_pad_bf16_kernel(const float* __restrict__ src, long ld_src, bf16* __restrict__ dst, long ld_dst, int rows,
+                                     int cols) {
+    const long total = (long)rows * ld_dst;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / ld_dst;
+        const int c = (int)(i % ld_dst);
+        dst[i] = __float2bfloat16(c < cols ? src[r * ld_src + c] : 0.f);
+    }
+}
+
+// ---------------------------------------------------------------- im2col (patch gather)
+// one thread per VW consecutive pixels of a patch row: coalesced vector loads along the image row.
+// out rows have leading dimension ldo (>= 3*p*p; padding columns are never read by the GEMM).
+template <int VW>
+__global__ void im2col_kernel(const float* __restrict__ px, bf16* __restrict__ out, int B, int S, int p, long ldo) {
+    const int g = S / p, P = g * g;
+    const int SV = S / VW;
+    const long total = (long)B * 2 * 3 * S * SV;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const int xv = (int)(t % SV);
+        long r = t / SV;
+        const int y = (int)(r % S); r /= S;
+        const int c = (int)(r % 3); r /= 3;
+        const int img = (int)(r % 2);
+        const int b = (int)(r / 2);
+        const float* src = px + ((((long)b * 2 + img) * 3 + c) * S + y) * S + xv * VW;
+        const int x = xv * VW;
+        const int py = y / p, iy = y % p, pxx = x / p, ix = x % p;  // p % VW == 0 checked on the host
+        const long row = ((long)b * 2 + img) * P + py * g + pxx;
+        bf16* dst = out + row * ldo + (long)c * p * p + iy * p + ix;
+        if (VW == 4) {
+            st4_bf16(dst, ld4(src));
+        } else if (VW == 2) {
+            const float2 v = *reinterpret_cast<const float2*>(src);
+            *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(v.x, v.y);
+        } else {
+            *dst = __float2bfloat16(*src);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- LayerNorm core (warp per row)
+template <bool WRITE_STATS>
+__device__ __forceinline__ void ln_row(float4 (&v)[MAXV], int nv, int H, const float* gamma, const float* beta, float eps,
+                                       float* y32, bf16* y16, float* mean_out, float* rstd_out, int lane) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < MAXV; ++t)
+        if (t < nv) s += v[t].x + v[t].y + v[t].z + v[t].w;
+    const float mean = warp_sum(s) / H;
+    float q = 0.f;
+#pragma unroll
+    for (int t = 0; t < MAXV; ++t)
+        if (t < nv) {
+            float a = v[t].x - mean, b = v[t].y - mean, c = v[t].z - mean, d = v[t].w - mean;
+            q += a * a + b * b + c * c + d * d;
+        }
+    const float rstd = rsqrtf(warp_sum(q) / H + eps);
+    if (WRITE_STATS && lane == 0) { *mean_out = mean; *rstd_out = rstd; }
+#pragma unroll
+    for (int t = 0; t < MAXV; ++t)
+        if (t < nv) {
+            const int col = lane * 4 + t * 128;
+            const float4 g = ld4(gamma + col), b = ld4(beta + col);
+            float4 o;
+            o.x = (v[t].x - mean) * rstd * g.x + b.x;
+            o.y = (v[t].y - mean) * rstd * g.y + b.y;
+            o.z = (v[t].z - mean) * rstd * g.z + b.z;
+            o.w = (v[t].w - mean) * rstd * g.w + b.w;
+            if (y32) st4(y32 + col, o);
+            if (y16) st4_bf16(y16 + col, o);
+        }
+}
+
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float eps, float* y32, bf16* y16, float* mean,
+                                     float* rstd, int M, int H) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nv = H / 128;
+    float4 v[MAXV];
+#pragma unroll
+    for (int t = 0; t < MAXV; ++t)
+        if (t < nv) v[t] = ld4(x + (long)row * H + lane * 4 + t * 128);
+    ln_row<true>(v, nv, H, gamma, beta, eps, y32 ? y32 + (long)row * H : nullptr, y16 ? y16 + (long)row * H : nullptr,
+                 mean + row, rstd + row, lane);
+}
+
+__global__ void vision_embed_ln_kernel(const float* __restrict__ patch_out, const float* __restrict__ cls,
+                                       const float* __restrict__ pos, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, float* x0, float* out, float* mean,
+                                       float* rstd, int B, int P, int H) {
+    const int Nv = 1 + 2 * P;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B * Nv) return;
+    const int b = row / Nv, t = row % Nv;
+    // token 0 = class embedding + pos[0]; token 1..P = image 0 patches + pos[1..P]; P+1..2P = image 1 + pos[1..P]
+    const float* src = (t == 0) ? cls : patch_out + ((long)b * 2 * P + (t - 1)) * H;
+    const int pidx = (t == 0) ? 0 : 1 + (t - 1) % P;
+    const int nv = H / 128;
+    float4 v[MAXV];
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k)
+        if (k < nv) {
+            const int col = lane * 4 + k * 128;
+            float4 a = ld4(src + col), p = ld4(pos + (long)pidx * H + col);
+            v[k] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+            st4(x0 + (long)row * H + col, v[k]);
+        }
+    ln_row<true>(v, nv, H, gamma, beta, eps, out + (long)row * H, nullptr, mean + row, rstd + row, lane);
+}
+
+__global__ void text_embed_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ tt,
+                                     const float* __restrict__ E, const float* __restrict__ pos,
+                                     const float* __restrict__ type, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float eps, float* pre, float* out32, bf16* out16,
+                                     float* mean, float* rstd, int B, int L, int H, int V, int* status) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B * L) return;
+    const int l = row % L;
+    long id = ids[row];
+    long ty = tt ? tt[row] : 0;
+    if (id < 0 || id >= V) { if (lane == 0) atomicOr(status, 1); id = 0; }  // reference would raise IndexError
+    if (ty < 0 || ty > 1) { if (lane == 0) atomicOr(status, 2); ty = 0; }
+    const int nv = H / 128;
+    float4 v[MAXV];
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k)
+        if (k < nv) {
+            const int col = lane * 4 + k * 128;
+            float4 a = ld4(E + id * H + col), p = ld4(pos + (long)l * H + col), t = ld4(type + ty * H + col);
+            v[k] = make_float4(a.x + t.x + p.x, a.y + t.y + p.y, a.z + t.z + p.z, a.w + t.w + p.w);
+            st4(pre + (long)row * H + col, v[k]);
+        }
+    ln_row<true>(v, nv, H, gamma, beta, eps, out32 + (long)row * H, out16 + (long)row * H, mean + row, rstd + row, lane);
+}
+
+// LayerNorm backward. Each warp walks rows r = warp_id, warp_id + nwarps, ...; dgamma/dbeta partials stay in
+// registers (same lane->column mapping for every row) and are reduced through shared memory + one atomic per
+// column per block.
+__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     const float* __restrict__ gamma, const float* __restrict__ add,
+                                     const bf16* __restrict__ dact_src, int dact, float* dx32, bf16* dx16, float* dgamma,
+                                     float* dbeta, int M, int H) {
+    extern __shared__ float red[];  // [warps][H] x 2
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nv = H / 128;
+    float4 g[MAXV], ag[MAXV], ab[MAXV];
+#pragma unroll
+    for (int t = 0; t < MAXV; ++t) {
+        ag[t] = make_float4(0, 0, 0, 0);
+        ab[t] = make_float4(0, 0, 0, 0);
+        if (t < nv) g[t] = ld4(gamma + lane * 4 + t * 128);
+    }
+    for (int row = blockIdx.x * nw + warp; row < M; row += gridDim.x * nw) {
+        const float mu = mean[row], rs = rstd[row];
+        float4 d[MAXV], xh[MAXV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < MAXV; ++t)
+            if (t < nv) {
+                const long off = (long)row * H + lane * 4 + t * 128;
+                d[t] = ld4(dy + off);
+                float4 xv = ld4(x + off);
+                xh[t] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                ab[t].x += d[t].x; ab[t].y += d[t].y; ab[t].z += d[t].z; ab[t].w += d[t].w;
+                ag[t].x += d[t].x * xh[t].x; ag[t].y += d[t].y * xh[t].y; ag[t].z += d[t].z * xh[t].z; ag[t].w += d[t].w * xh[t].w;
+                d[t].x *= g[t].x; d[t].y *= g[t].y; d[t].z *= g[t].z; d[t].w *= g[t].w;
+                s1 += d[t].x + d[t].y + d[t].z + d[t].w;
+                s2 += d[t].x * xh[t].x + d[t].y * xh[t].y + d[t].z * xh[t].z + d[t].w * xh[t].w;
+            }
+        s1 = warp_sum(s1) / H;
+        s2 = warp_sum(s2) / H;
+#pragma unroll
+        for (int t = 0; t < MAXV; ++t)
+            if (t < nv) {
+                const long off = (long)row * H + lane * 4 + t * 128;
+                float4 o;
+                o.x = rs * (d[t].x - s1 - xh[t].x * s2);
+                o.y = rs * (d[t].y - s1 - xh[t].y * s2);
+                o.z = rs * (d[t].z - s1 - xh[t].z * s2);
+                o.w = rs * (d[t].w - s1 - xh[t].w * s2);
+                if (dact) {
+                    const uint2 q = *reinterpret_cast<const uint2*>(dact_src + off);
+                    const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+                    const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+                    if (dact == 1) {
+                        o.x *= gelu_erf_grad(f0.x); o.y *= gelu_erf_grad(f0.y); o.z *= gelu_erf_grad(f1.x); o.w *= gelu_erf_grad(f1.y);
+                    } else {
+                        o.x *= quick_gelu_grad(f0.x); o.y *= quick_gelu_grad(f0.y); o.z *= quick_gelu_grad(f1.x); o.w *= quick_gelu_grad(f1.y);
+                    }
+                }
+                if (add) {
+                    float4 a = ld4(add + off);
+                    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                }
+                if (dx32) st4(dx32 + off, o);
+                if (dx16) st4_bf16(dx16 + off, o);
+            }
+    }
+    float* rg = red;
+    float* rb = red + nw * H;
+#pragma unroll
+    for (int t = 0; t < MAXV; ++t)
+        if (t < nv) {
+            st4(rg + warp * H + lane * 4 + t * 128, ag[t]);
+            st4(rb + warp * H + lane * 4 + t * 128, ab[t]);
+        }
+    __syncthreads();
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        float sg = 0.f, sb = 0.f;
+        for (int w = 0; w < nw; ++w) { sg += rg[w * H + c]; sb += rb[w * H + c]; }
+        atomicAdd(dgamma + c, sg);
+        atomicAdd(dbeta + c, sb);
+    }
+}
+
+// ---------------------------------------------------------------- column sums (bias gradients)
+// block = 32 x 8 threads over a 32-column x ROWS strip; coalesced row-major reads, one atomic per column per block.
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, long ld, float* out, int M, int N, int rows_per_block) {
+    __shared__ float part[8][33];
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(M, r0 + rows_per_block);
+    float s = 0.f;
+    if (col < N)
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) s += (float)x[(long)r * ld + col];
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+        atomicAdd(out + col, t);
+    }
+}
+
+// ---------------------------------------------------------------- embedding backward
+__global__ void text_embed_bwd_kernel(const float* __restrict__ d, const int64_t* __restrict__ ids,
+                                      const int64_t* __restrict__ tt, float* dE, float* dpos, float* dtype, int B, int L,
+                                      int H) {
+    const int row = blockIdx.x;
+    const int l = row % L;
+    const long id = ids[row];
+    const long ty = tt ? tt[row] : 0;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        const float v = d[(long)row * H + c];
+        atomicAdd(dE + id * H + c, v);
+        atomicAdd(dpos + (long)l * H + c, v);
+        atomicAdd(dtype + ty * H + c, v);
+    }
+}
+
+__global__ void vision_embed_bwd_kernel(const float* __restrict__ dx0, float* dcls, float* dpos, bf16* dpatch, int B,
+                                        int P, int H) {
+    const int Nv = 1 + 2 * P;
+    const int row = blockIdx.x;
+    const int b = row / Nv, t = row % Nv;
+    const int pidx = (t == 0) ? 0 : 1 + (t - 1) % P;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        const float v = dx0[(long)row * H + c];
+        atomicAdd(dpos + (long)pidx * H + c, v);
+        if (t == 0) atomicAdd(dcls + c, v);
+        else dpatch[((long)b * 2 * P + (t - 1)) * H + c] = __float2bfloat16(v);
+    }
+}
+
+// ---------------------------------------------------------------- gathers / scatters
+__global__ void gather_rows_bf16_kernel(const bf16* __restrict__ src, const int64_t* __restrict__ idx, bf16* out, int R, int H) {
+    const int r = blockIdx.x;
+    const uint4* s = reinterpret_cast<const uint4*>(src + idx[r] * H);
+    uint4* o = reinterpret_cast<uint4*>(out + (long)r * H);
+    for (int c = threadIdx.x; c < H / 8; c += blockDim.x) o[c] = s[c];
+}
+__global__ void gather_f32_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, float* out, int R) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) out[r] = src[idx[r]];
+}
+__global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, float* dst, int R, int H) {
+    const int r = blockIdx.x;
+    const long o = idx[r] * H;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) atomicAdd(dst + o + c, src[(long)r * H + c]);
+}
+__global__ void scatter_add_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, float* dst, int R) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) atomicAdd(dst + idx[r], src[r]);
+}
+
+// ---------------------------------------------------------------- AdamW (torch.optim.AdamW semantics)
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, bf16* __restrict__ p16, const AdamSeg* __restrict__ segs, int nseg,
+                             long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2) {
+    // one block per 4096-element chunk; the owning segment is found by binary search on the chunk start
+    // (segments are aligned to 8 elements and chunks never straddle an unaligned boundary element-wise: each
+    // thread re-checks its own element range).
+    const long base = (long)blockIdx.x * 4096;
+    for (int it = 0; it < 4; ++it) {
+        const long i = base + ((long)it * blockDim.x + threadIdx.x) * 4;
+        if (i >= n) return;
+        int lo = 0, hi = nseg - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (segs[mid].end <= i) lo = mid + 1; else hi = mid;
+        }
+        const AdamSeg sg = segs[lo];
+        float4 pv = ld4(p + i);
+        if (!sg.skip && i >= sg.begin) {
+            const float4 gv = ld4(g + i);
+            float4 mv = ld4(m + i), vv = ld4(v + i);
+            const float decay = sg.decay ? (1.0f - lr * wd) : 1.0f;
+            const float step = lr / bc1;
+            const float inv_sqrt_bc2 = rsqrtf(bc2);
+#define ADAM1(P, G, Mm, Vv)                                                   \
+    P *= decay; Mm = b1 * Mm + (1.0f - b1) * G; Vv = b2 * Vv + (1.0f - b2) * G * G; \
+    P -= step * Mm / (sqrtf(Vv) * inv_sqrt_bc2 + eps);
+            ADAM1(pv.x, gv.x, mv.x, vv.x)
+            ADAM1(pv.y, gv.y, mv.y, vv.y)
+            ADAM1(pv.z, gv.z, mv.z, vv.z)
+            ADAM1(pv.w, gv.w, mv.w, vv.w)
+#undef ADAM1
+            st4(p + i, pv); st4(m + i, mv); st4(v + i, vv);
+        }
+        if (p16) st4_bf16(p16 + i, pv);
+    }
+}
+
+inline int blocks_for(long n, int per_block, int cap = 148 * 16) {
+    long b = (n + per_block - 1) / per_block;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+int launch_cast_bf16(const float* src, bf16* dst, long n, cudaStream_t s) {
+    cast_bf16_kernel<<<blocks_for(n, 256 * 8), 256, 0, s>>>(src, dst, n);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_fill_f32(float* dst, float v, long n, cudaStream_t s) {
+    fill_kernel<<<blocks_for(n, 1024), 256, 0, s>>>(dst, v, n);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_axpy_f32(const float* src, float* dst, long n, cudaStream_t s) {
+    axpy_kernel<<<blocks_for(n, 1024), 256, 0, s>>>(src, dst, n);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_cast_pad_bf16(const float* src, long ld_src, bf16* dst, long ld_dst, int rows, int cols, cudaStream_t s) {
+    cast_pad_bf16_kernel<<<blocks_for((long)rows * ld_dst, 1024), 256, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_im2col(const float* px, bf16* out, int B, int S, int p, long ldo, cudaStream_t s) {
+    B2_CHECK(S % p == 0 && ldo >= 3L * p * p, "im2col: patch %d must divide image size %d", p, S);
+    const int vw = (p % 4 == 0 && ldo % 4 == 0) ? 4 : ((p % 2 == 0 && ldo % 2 == 0) ? 2 : 1);
+    const long total = (long)B * 2 * 3 * S * (S / vw);
+    if (vw == 4) im2col_kernel<4><<<blocks_for(total, 256), 256, 0, s>>>(px, out, B, S, p, ldo);
+    else if (vw == 2) im2col_kernel<2><<<blocks_for(total, 256), 256, 0, s>>>(px, out, B, S, p, ldo);
+    else im2col_kernel<1><<<blocks_for(total, 256), 256, 0, s>>>(px, out, B, S, p, ldo);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+static int check_h(int H) {
+    B2_CHECK(H % 128 == 0 && H <= 128 * MAXV, "hidden size %d must be a multiple of 128 and <= %d", H, 128 * MAXV);
+    return 0;
+}
+int launch_vision_embed_ln(const float* patch_out, const float* cls, const float* pos, const float* gamma,
+                           const float* beta, float eps, float* x0, float* out_f32, float* mean, float* rstd, int B,
+                           int P, int H, cudaStream_t s) {
+    B2_TRY(check_h(H));
+    const int rows = B * (1 + 2 * P);
+    vision_embed_ln_kernel<<<(rows + 3) / 4, 128, 0, s>>>(patch_out, cls, pos, gamma, beta, eps, x0, out_f32, mean, rstd, B, P, H);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_text_embed_ln(const int64_t* ids, const int64_t* tt, const float* E, const float* pos, const float* type,
+                         const float* gamma, const float* beta, float eps, float* pre, float* out_f32, bf16* out_bf16,
+                         float* mean, float* rstd, int B, int L, int H, int V, int* status, cudaStream_t s) {
+    B2_TRY(check_h(H));
+    text_embed_ln_kernel<<<(B * L + 3) / 4, 128, 0, s>>>(ids, tt, E, pos, type, gamma, beta, eps, pre, out_f32, out_bf16,
+                                                        mean, rstd, B, L, H, V, status);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y32, bf16* y16,
+                         float* mean, float* rstd, int M, int H, cudaStream_t s) {
+    B2_TRY(check_h(H));
+    layernorm_fwd_kernel<<<(M + 3) / 4, 128, 0, s>>>(x, gamma, beta, eps, y32, y16, mean, rstd, M, H);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                         const float* add, const bf16* dact_src, int dact, float* dx32, bf16* dx16, float* dgamma,
+                         float* dbeta, int M, int H, cudaStream_t s) {
+    B2_TRY(check_h(H));
+    const int nw = 4;
+    int blocks = (M + nw - 1) / nw;
+    if (blocks > 148 * 2) blocks = 148 * 2;
+    layernorm_bwd_kernel<<<blocks, nw * 32, 2 * nw * H * sizeof(float), s>>>(dy, x, mean, rstd, gamma, add, dact_src,
+                                                                            dact_src ? dact : 0, dx32, dx16, dgamma, dbeta, M, H);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_colsum_bf16(const bf16* x, long ld, float* out, int M, int N, cudaStream_t s) {
+    const int rpb = 128;
+    colsum_kernel<bf16><<<dim3((N + 31) / 32, (M + rpb - 1) / rpb), dim3(32, 8), 0, s>>>(x, ld, out, M, N, rpb);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_colsum_f32(const float* x, long ld, float* out, int M, int N, cudaStream_t s) {
+    const int rpb = 128;
+    colsum_kernel<float><<<dim3((N + 31) / 32, (M + rpb - 1) / rpb), dim3(32, 8), 0, s>>>(x, ld, out, M, N, rpb);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_text_embed_bwd(const float* d, const int64_t* ids, const int64_t* tt, float* dE, float* dpos, float* dtype,
+                          int B, int L, int H, cudaStream_t s) {
+    text_embed_bwd_kernel<<<B * L, 256, 0, s>>>(d, ids, tt, dE, dpos, dtype, B, L, H);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_vision_embed_bwd(const float* dx0, float* dcls, float* dpos, bf16* dpatch, int B, int P, int H,
+                            cudaStream_t s) {
+    vision_embed_bwd_kernel<<<B * (1 + 2 * P), 256, 0, s>>>(dx0, dcls, dpos, dpatch, B, P, H);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_gather_rows_bf16(const bf16* src, const int64_t* idx, bf16* out, int R, int H, cudaStream_t s) {
+    B2_CHECK(H % 8 == 0, "gather_rows: H %d must be a multiple of 8", H);
+    gather_rows_bf16_kernel<<<R, 96, 0, s>>>(src, idx, out, R, H);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_gather_f32(const float* src, const int64_t* idx, float* out, int R, cudaStream_t s) {
+    gather_f32_kernel<<<(R + 255) / 256, 256, 0, s>>>(src, idx, out, R);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_scatter_add_rows_f32(const float* src, const int64_t* idx, float* dst, int R, int H, cudaStream_t s) {
+    scatter_add_rows_kernel<<<R, 256, 0, s>>>(src, idx, dst, R, H);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_scatter_add_f32(const float* src, const int64_t* idx, float* dst, int R, cudaStream_t s) {
+    scatter_add_kernel<<<(R + 255) / 256, 256, 0, s>>>(src, idx, dst, R);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_adamw(float* p, const float* g, float* m, float* v, bf16* p16, const AdamSeg* segs_dev, int nseg, long n,
+                 float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, cudaStream_t s) {
+    B2_CHECK(n % 8 == 0, "adamw: flat length %ld must be a multiple of 8", n);
+    const long blocks = (n + 4095) / 4096;
+    adamw_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, g, m, v, p16, segs_dev, nseg, n, lr, b1, b2, eps, wd, bc1, bc2);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

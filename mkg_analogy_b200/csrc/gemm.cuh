@@ -20,6 +20,7 @@ struct GemmOp {
     // epilogue, applied in this order
     float alpha = 1.0f;
     const float* bias = nullptr;          // + bias[n]
+    const float* bias2 = nullptr;         // + bias2[n] (second operand pair's bias)
     bf16* out_preact = nullptr; long ldp = 0;   // store value before activation (saved for backward)
     int act = 0;                          // 0 none, 1 gelu(erf), 2 quick_gelu
     const bf16* dact_src = nullptr; long ldx = 0; int dact = 0;  // *= act'(dact_src[m,n]) (backward)

@@ -22,6 +22,7 @@ struct GemmDev {
     int kb1, kb_total;  // k-blocks served by pair 1 / total
     float alpha;
     const float* bias;
+    const float* bias2;
     bf16* out_preact; long ldp;
     int act;
     const bf16* dact_src; long ldx; int dact;
@@ -171,6 +172,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
+                }
+                if (p.bias2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) v[j] += __ldg(p.bias2 + col0 + j);
                 }
                 if (p.out_preact) {
                     bf16* dst = p.out_preact + (long)row * p.ldp + col0;
@@ -329,7 +335,7 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
     B2_CHECK(op.M > 0 && op.N > 0 && op.K1 > 0, "gemm: bad shape M=%d N=%d K1=%d", op.M, op.N, op.K1);
     B2_CHECK(op.K2 == 0 || op.K1 % BK == 0, "gemm: K1=%d must be a multiple of %d when a second operand pair is used", op.K1, BK);
     B2_CHECK(op.split_k >= 1, "gemm: split_k must be >= 1");
-    B2_CHECK(op.split_k == 1 || (op.accumulate && op.out_f32 && !op.out_bf16 && !op.out_preact && !op.bias &&
+    B2_CHECK(op.split_k == 1 || (op.accumulate && op.out_f32 && !op.out_bf16 && !op.out_preact && !op.bias && !op.bias2 &&
                                  !op.residual && op.act == 0 && op.dact == 0),
              "gemm: split-K needs a pure fp32 accumulate epilogue");
     const int bn = op.bn ? op.bn : 128;
@@ -356,7 +362,7 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
     d.M = op.M; d.N = op.N;
     d.kb1 = (op.K1 + BK - 1) / BK;
     d.kb_total = d.kb1 + (op.K2 + BK - 1) / BK;
-    d.alpha = op.alpha; d.bias = op.bias;
+    d.alpha = op.alpha; d.bias = op.bias; d.bias2 = op.bias2;
     d.out_preact = op.out_preact; d.ldp = op.ldp;
     d.act = op.act; d.dact_src = op.dact_src; d.ldx = op.ldx; d.dact = op.dact_src ? op.dact : 0;
     d.residual = op.residual; d.ldr = op.ldr;
