@@ -36,6 +36,8 @@ extern "C" {
 
 const char* b200mart_last_error(void);
 int32_t b200mart_version(void);
+/* kernels launched by this library in this process so far (bench.py reports the per-step difference) */
+int64_t b200mart_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Stand-alone tensor-core product (tcgen05 + TMA), used by the model functions below and exposed
@@ -176,6 +178,13 @@ int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* params16, cons
 /* Device-side status flags of the last calls on this workspace (synchronises the stream):
  * bit0 token id out of range, bit1 token type out of range, bit2 a row without exactly one [MASK]. */
 int32_t b200mart_status(b200mart_handle* h, const b200mart_buffers* bufs, void* stream, int32_t* flags_out);
+
+/* Optional device timing by kernel family, for roofline reporting: between begin and end every tensor-core GEMM
+ * (index 0), fused attention (1) and fusion (2) launch is bracketed by CUDA events on the launching stream.
+ * end synchronises the stream; gemm_flops = sum of 2*M*N*K over the GEMM launches. Never used in a timed region. */
+int32_t b200mart_profile_begin(b200mart_handle* h);
+int32_t b200mart_profile_end(b200mart_handle* h, void* stream, double ms_by_cat[3], int64_t launches_by_cat[3],
+                             double* gemm_flops);
 
 /* ------------------------------------------------------------------------------------------------
  * Stand-alone operators (kernel-level parity tests; also the building blocks of the functions above).

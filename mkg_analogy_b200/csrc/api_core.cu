@@ -4,6 +4,7 @@
 #include <stdarg.h>
 
 thread_local char g_b200mart_err[512] = "";
+unsigned long long g_b200mart_launches = 0;
 
 int b200mart_set_err(int code, const char* fmt, ...) {
     va_list ap;
@@ -16,6 +17,8 @@ int b200mart_set_err(int code, const char* fmt, ...) {
 extern "C" const char* b200mart_last_error(void) { return g_b200mart_err; }
 
 extern "C" int32_t b200mart_version(void) { return B200MART_VERSION; }
+
+extern "C" int64_t b200mart_launch_count(void) { return (int64_t)g_b200mart_launches; }
 
 extern "C" int32_t b200mart_gemm_bf16(const b200mart_gemm_desc* d, void* stream) {
     if (!d) return b200mart_set_err(1, "gemm: null descriptor");

@@ -549,7 +549,7 @@ int launch_attention_fwd(const AttnFwd& a, float* out32, cudaStream_t s) {
     const size_t smem = (size_t)2 * n * KPAD * 2 + (size_t)(ATT_WARPS + 1) * n * 4;
     B2_TRY(set_smem(attention_fwd_kernel, smem));
     attention_fwd_kernel<<<dim3(a.nh, a.B), ATT_WARPS * 32, smem, s>>>(a, a.out, out32);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 
@@ -571,11 +571,11 @@ int launch_attention_bwd(const AttnBwd& g, float* delta, cudaStream_t s) {
         B2_TRY(set_smem(attention_bwd_rows_kernel<MAX_KEY_ITERS>, smem1));
         attention_bwd_rows_kernel<MAX_KEY_ITERS><<<dim3(a.nh, a.B), ATT_WARPS * 32, smem1, s>>>(g, delta);
     }
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     const size_t smem2 = (size_t)2 * a.Lq * KPAD * 2 + (size_t)(2 * ATT_WARPS + 2) * a.Lq * 4;
     B2_TRY(set_smem(attention_bwd_keys_kernel, smem2));
     attention_bwd_keys_kernel<<<dim3(a.nh, a.B), ATT_WARPS * 32, smem2, s>>>(g, delta);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 
@@ -584,7 +584,7 @@ int launch_fusion_fwd(const float* ctx, const float* vh, bf16* out, float* lse, 
     const size_t smem = (size_t)(FROWS * H + FROWS * Nv) * 4;
     B2_TRY(set_smem(fusion_fwd_kernel, smem));
     fusion_fwd_kernel<<<dim3((L + FROWS - 1) / FROWS, B), FTHREADS, smem, s>>>(ctx, vh, out, lse, L, Nv, H);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 
@@ -594,7 +594,7 @@ int launch_fusion_bwd_rows(const float* dg, const float* ctx, const float* vh, c
     const size_t smem = (size_t)(FROWS * H + 2 * FROWS * Nv) * 4;
     B2_TRY(set_smem(fusion_bwd_rows_kernel, smem));
     fusion_bwd_rows_kernel<<<dim3((L + FROWS - 1) / FROWS, B), FTHREADS, smem, s>>>(dg, ctx, vh, lse, pbuf, dsbuf, dctx, L, Nv, H);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 
@@ -603,6 +603,6 @@ int launch_fusion_bwd_keys(const float* dg, const float* ctx, const float* pbuf,
     const size_t smem = (size_t)2 * L * FROWS * 4;
     B2_TRY(set_smem(fusion_bwd_keys_kernel, smem));
     fusion_bwd_keys_kernel<<<dim3((Nv + FROWS - 1) / FROWS, B), FTHREADS, smem, s>>>(dg, ctx, pbuf, dsbuf, dvh_in, dvh32, dvh16, L, Nv, H);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }

@@ -23,6 +23,14 @@ int b200mart_set_err(int code, const char* fmt, ...);
                                     cudaGetErrorName(_e), cudaGetErrorString(_e));         \
     } while (0)
 
+// every kernel launch site: check the launch and count it (b200mart_launch_count, for bench.py's gpu_launches)
+extern unsigned long long g_b200mart_launches;
+#define B2_LAUNCHED()                                                                      \
+    do {                                                                                   \
+        CUDA_TRY(cudaGetLastError());                                                      \
+        ++g_b200mart_launches;                                                             \
+    } while (0)
+
 #define B2_CHECK(cond, ...)                                                                \
     do {                                                                                   \
         if (!(cond)) return b200mart_set_err(1, __VA_ARGS__);                              \

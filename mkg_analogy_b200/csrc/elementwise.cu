@@ -378,22 +378,22 @@ inline int blocks_for(long n, int per_block, int cap = 148 * 16) {
 
 int launch_cast_bf16(const float* src, bf16* dst, long n, cudaStream_t s) {
     cast_bf16_kernel<<<blocks_for(n, 256 * 8), 256, 0, s>>>(src, dst, n);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_fill_f32(float* dst, float v, long n, cudaStream_t s) {
     fill_kernel<<<blocks_for(n, 1024), 256, 0, s>>>(dst, v, n);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_axpy_f32(const float* src, float* dst, long n, cudaStream_t s) {
     axpy_kernel<<<blocks_for(n, 1024), 256, 0, s>>>(src, dst, n);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_cast_pad_bf16(const float* src, long ld_src, bf16* dst, long ld_dst, int rows, int cols, cudaStream_t s) {
     cast_pad_bf16_kernel<<<blocks_for((long)rows * ld_dst, 1024), 256, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_im2col(const float* px, bf16* out, int B, int S, int p, long ldo, cudaStream_t s) {
@@ -403,7 +403,7 @@ int launch_im2col(const float* px, bf16* out, int B, int S, int p, long ldo, cud
     if (vw == 4) im2col_kernel<4><<<blocks_for(total, 256), 256, 0, s>>>(px, out, B, S, p, ldo);
     else if (vw == 2) im2col_kernel<2><<<blocks_for(total, 256), 256, 0, s>>>(px, out, B, S, p, ldo);
     else im2col_kernel<1><<<blocks_for(total, 256), 256, 0, s>>>(px, out, B, S, p, ldo);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 static int check_h(int H) {
@@ -416,7 +416,7 @@ int launch_vision_embed_ln(const float* patch_out, const float* cls, const float
     B2_TRY(check_h(H));
     const int rows = B * (1 + 2 * P);
     vision_embed_ln_kernel<<<(rows + 3) / 4, 128, 0, s>>>(patch_out, cls, pos, gamma, beta, eps, x0, out_f32, mean, rstd, B, P, H);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_text_embed_ln(const int64_t* ids, const int64_t* tt, const float* E, const float* pos, const float* type,
@@ -425,14 +425,14 @@ int launch_text_embed_ln(const int64_t* ids, const int64_t* tt, const float* E, 
     B2_TRY(check_h(H));
     text_embed_ln_kernel<<<(B * L + 3) / 4, 128, 0, s>>>(ids, tt, E, pos, type, gamma, beta, eps, pre, out_f32, out_bf16,
                                                         mean, rstd, B, L, H, V, status);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y32, bf16* y16,
                          float* mean, float* rstd, int M, int H, cudaStream_t s) {
     B2_TRY(check_h(H));
     layernorm_fwd_kernel<<<(M + 3) / 4, 128, 0, s>>>(x, gamma, beta, eps, y32, y16, mean, rstd, M, H);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
@@ -444,52 +444,52 @@ int launch_layernorm_bwd(const float* dy, const float* x, const float* mean, con
     if (blocks > 148 * 2) blocks = 148 * 2;
     layernorm_bwd_kernel<<<blocks, nw * 32, 2 * nw * H * sizeof(float), s>>>(dy, x, mean, rstd, gamma, add, dact_src,
                                                                             dact_src ? dact : 0, dx32, dx16, dgamma, dbeta, M, H);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_colsum_bf16(const bf16* x, long ld, float* out, int M, int N, cudaStream_t s) {
     const int rpb = 128;
     colsum_kernel<bf16><<<dim3((N + 31) / 32, (M + rpb - 1) / rpb), dim3(32, 8), 0, s>>>(x, ld, out, M, N, rpb);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_colsum_f32(const float* x, long ld, float* out, int M, int N, cudaStream_t s) {
     const int rpb = 128;
     colsum_kernel<float><<<dim3((N + 31) / 32, (M + rpb - 1) / rpb), dim3(32, 8), 0, s>>>(x, ld, out, M, N, rpb);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_text_embed_bwd(const float* d, const int64_t* ids, const int64_t* tt, float* dE, float* dpos, float* dtype,
                           int B, int L, int H, cudaStream_t s) {
     text_embed_bwd_kernel<<<B * L, 256, 0, s>>>(d, ids, tt, dE, dpos, dtype, B, L, H);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_vision_embed_bwd(const float* dx0, float* dcls, float* dpos, bf16* dpatch, int B, int P, int H,
                             cudaStream_t s) {
     vision_embed_bwd_kernel<<<B * (1 + 2 * P), 256, 0, s>>>(dx0, dcls, dpos, dpatch, B, P, H);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_gather_rows_bf16(const bf16* src, const int64_t* idx, bf16* out, int R, int H, cudaStream_t s) {
     B2_CHECK(H % 8 == 0, "gather_rows: H %d must be a multiple of 8", H);
     gather_rows_bf16_kernel<<<R, 96, 0, s>>>(src, idx, out, R, H);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_gather_f32(const float* src, const int64_t* idx, float* out, int R, cudaStream_t s) {
     gather_f32_kernel<<<(R + 255) / 256, 256, 0, s>>>(src, idx, out, R);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_scatter_add_rows_f32(const float* src, const int64_t* idx, float* dst, int R, int H, cudaStream_t s) {
     scatter_add_rows_kernel<<<R, 256, 0, s>>>(src, idx, dst, R, H);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_scatter_add_f32(const float* src, const int64_t* idx, float* dst, int R, cudaStream_t s) {
     scatter_add_kernel<<<(R + 255) / 256, 256, 0, s>>>(src, idx, dst, R);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_adamw(float* p, const float* g, float* m, float* v, bf16* p16, const AdamSeg* segs_dev, int nseg, long n,
@@ -497,6 +497,6 @@ int launch_adamw(float* p, const float* g, float* m, float* v, bf16* p16, const 
     B2_CHECK(n % 8 == 0, "adamw: flat length %ld must be a multiple of 8", n);
     const long blocks = (n + 4095) / 4096;
     adamw_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, g, m, v, p16, segs_dev, nseg, n, lr, b1, b2, eps, wd, bc1, bc2);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }

@@ -391,6 +391,6 @@ double gemm_plan_flops(const GemmPlan* p) { return p->flops; }
 
 int gemm_plan_launch(const GemmPlan* p, cudaStream_t stream) {
     p->kernel<<<p->grid, GEMM_THREADS, p->smem, stream>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, p->dev);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }

@@ -176,13 +176,13 @@ ranks_kernel(const float* __restrict__ logits, long ld, int C, const int64_t* __
 
 int launch_find_mask(const int64_t* ids, int* mask_pos, int B, int L, int mask_id, int* status, cudaStream_t s) {
     find_mask_kernel<<<(B + 3) / 4, 128, 0, s>>>(ids, mask_pos, B, L, mask_id, status);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_gather_mask_rows(const bf16* z16, const int* mask_pos, bf16* zm, int B, int L, int H, cudaStream_t s) {
     B2_CHECK(H % 8 == 0, "gather_mask_rows: H %d must be a multiple of 8", H);
     gather_mask_rows_kernel<<<B, 96, 0, s>>>(z16, mask_pos, zm, L, H);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_ls_ce(const LossGroup& g, const int64_t* label, const int64_t* pre_type, float eps, float* loss, int B,
@@ -190,23 +190,23 @@ int launch_ls_ce(const LossGroup& g, const int64_t* label, const int64_t* pre_ty
     B2_CHECK(g.C > 0 && g.ldd >= g.C, "ls_ce: bad class count %d / gradient leading dimension %ld", g.C, g.ldd);
     B2_CHECK(g.select == 0 || pre_type != nullptr, "ls_ce: row selection needs pre_type");
     ls_ce_kernel<<<B, 256, 0, s>>>(g, label, pre_type, eps, loss, B);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_relaxation(const float* z, const int64_t* rel_idx, const int64_t* q_head, const int64_t* a_head, float alpha,
                       float* loss, float* dz, int B, int L, int H, cudaStream_t s) {
     relaxation_kernel<<<B, 128, 0, s>>>(z, rel_idx, q_head, a_head, alpha, loss, dz, B, L, H);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_scatter_mask_rows(const float* dzm, const int* mask_pos, float* dz, int B, int L, int H, cudaStream_t s) {
     scatter_mask_rows_kernel<<<B, 256, 0, s>>>(dzm, mask_pos, dz, L, H);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }
 int launch_ranks(const float* logits, long ld, int C, const int64_t* label, const int64_t* pre_type, int select,
                  int64_t* ranks, int B, cudaStream_t s) {
     ranks_kernel<<<B, 256, 0, s>>>(logits, ld, C, label, pre_type, select, ranks, B);
-    CUDA_TRY(cudaGetLastError());
+    B2_LAUNCHED();
     return 0;
 }

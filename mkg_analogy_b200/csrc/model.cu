@@ -90,10 +90,36 @@ struct b200mart_handle {
     int nseg = 0;
     // cached workspace carving
     Workspace ws; void* ws_base = nullptr;
+    // optional per-category device timing (CUDA events around each launch group; see b200mart_profile_begin/end)
+    bool profiling = false;
+    struct ProfRec { cudaEvent_t e0, e1; int cat; };
+    std::vector<ProfRec> prof;
+    size_t prof_used = 0;
+    double prof_flops = 0.0;
     ~b200mart_handle() {
         for (auto& kv : plans) gemm_plan_destroy(kv.second);
         for (auto* p : segs_dev) if (p) cudaFree(p);
+        for (auto& r : prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     }
+};
+
+enum { CAT_GEMM = 0, CAT_ATTN = 1, CAT_FUSION = 2, CAT_COUNT = 3 };
+
+// RAII: when profiling, brackets the launches issued in its scope with two events on the launching stream
+struct ProfScope {
+    b200mart_handle* h; cudaStream_t s; b200mart_handle::ProfRec* rec = nullptr;
+    ProfScope(b200mart_handle* h_, cudaStream_t s_, int cat) : h(h_), s(s_) {
+        if (!h->profiling) return;
+        if (h->prof_used == h->prof.size()) {
+            b200mart_handle::ProfRec r;
+            if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+            h->prof.push_back(r);
+        }
+        rec = &h->prof[h->prof_used++];
+        rec->cat = cat;
+        cudaEventRecord(rec->e0, s);
+    }
+    ~ProfScope() { if (rec) cudaEventRecord(rec->e1, s); }
 };
 
 namespace {
@@ -283,6 +309,8 @@ int run_gemm(b200mart_handle* h, const GemmOp& op, cudaStream_t s) {
     } else {
         plan = it->second;
     }
+    ProfScope ps(h, s, CAT_GEMM);
+    if (h->profiling) h->prof_flops += gemm_plan_flops(plan);
     return gemm_plan_launch(plan, s);
 }
 
@@ -476,7 +504,7 @@ extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* 
             at.k2 = a.qkv16 + H; at.v2 = a.qkv16 + 2 * H; at.ld2 = 3 * H; at.n2 = Nv;
             at.B = B; at.Lq = Nv; at.nh = nh; at.scale = 0.125f;
             at.out = a.ctx16; at.ldo = H; at.lse = a.lse;
-            B2_TRY(launch_attention_fwd(at, nullptr, s));
+            { ProfScope ps(h, s, CAT_ATTN); B2_TRY(launch_attention_fwd(at, nullptr, s)); }
             B2_TRY(r.linear(Mv, H, H, a.ctx16, p.o_w, p.o_b, 0, nullptr, w.V32[i], a.x1, nullptr));
             B2_TRY(launch_layernorm_fwd(a.x1, r.p32(p.ln2_w), r.p32(p.ln2_b), d.vision_eps, nullptr, a.u2_16, a.mean2, a.rstd2, Mv, H, s));
             B2_TRY(r.linear(Mv, F, H, a.u2_16, p.fc1_w, p.fc1_b, 2, a.pre16, nullptr, nullptr, a.h16));
@@ -494,9 +522,9 @@ extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* 
             at.key_mask = batch->attention_mask;
             if (batch->sep_idx) { at.sep_idx = batch->sep_idx; at.w0 = r.p32(p.aw0); at.w1 = r.p32(p.aw1); }
             at.out = a.ctx16; at.ldo = H; at.lse = a.lse;
-            B2_TRY(launch_attention_fwd(at, fused ? a.ctx32 : nullptr, s));
+            { ProfScope ps(h, s, CAT_ATTN); B2_TRY(launch_attention_fwd(at, fused ? a.ctx32 : nullptr, s)); }
             if (fused)   // BertFusion on the context with the vision output of THIS layer index (:373, :627)
-                B2_TRY(launch_fusion_fwd(a.ctx32, w.V32[i + 1], a.g16, a.flse, B, L, Nv, H, s));
+                { ProfScope ps(h, s, CAT_FUSION); B2_TRY(launch_fusion_fwd(a.ctx32, w.V32[i + 1], a.g16, a.flse, B, L, Nv, H, s)); }
             B2_TRY(r.linear(Mt, H, H, a.ctx16, p.ao_w, p.ao_b, 0, nullptr, w.T32[i], a.apre, nullptr));
             B2_TRY(launch_layernorm_fwd(a.apre, r.p32(p.aln_w), r.p32(p.aln_b), d.text_eps, a.a32, a.a16, a.amean, a.arstd, Mt, H, s));
             if (fused)
@@ -686,8 +714,8 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             B2_TRY(r.grad_weight(Mt, H, H, w.t16a, H, a.ctx16, H, p.ao_w, p.ao_b));
             B2_TRY(r.grad_input(Mt, H, H, w.t16a, p.ao_w, nullptr, 0, nullptr, w.t32b, nullptr));      // d ctx
             if (fused) {
-                B2_TRY(launch_fusion_bwd_rows(w.t32c, a.ctx32, w.V32[i + 1], a.flse, w.pbuf, w.dsbuf, w.t32b, B, L, Nv, H, s));
-                B2_TRY(launch_fusion_bwd_keys(w.t32c, a.ctx32, w.pbuf, w.dsbuf, (i == D - 1) ? nullptr : w.dV, w.dV, w.dV16, B, L, Nv, H, s));
+                { ProfScope ps(h, s, CAT_FUSION); B2_TRY(launch_fusion_bwd_rows(w.t32c, a.ctx32, w.V32[i + 1], a.flse, w.pbuf, w.dsbuf, w.t32b, B, L, Nv, H, s)); }
+                { ProfScope ps(h, s, CAT_FUSION); B2_TRY(launch_fusion_bwd_keys(w.t32c, a.ctx32, w.pbuf, w.dsbuf, (i == D - 1) ? nullptr : w.dV, w.dV, w.dV16, B, L, Nv, H, s)); }
             }
             AttnBwd ab{};
             AttnFwd& at = ab.f;
@@ -700,7 +728,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             ab.dout = w.t32b; ab.lddo = H;
             ab.dq = w.tdqkv16; ab.dk2 = w.tdqkv16 + H; ab.dv2 = w.tdqkv16 + 2 * H; ab.ldd = 3 * H;
             if (i + 1 < D && i + 1 >= d.fuse_from) { ab.dk2_add = w.dk1; ab.dv2_add = w.dv1; ab.ldadd = H; }   // from vision layer i+1
-            B2_TRY(launch_attention_bwd(ab, w.delta, s));
+            { ProfScope ps(h, s, CAT_ATTN); B2_TRY(launch_attention_bwd(ab, w.delta, s)); }
             B2_TRY(r.grad_weight(Mt, 3 * H, H, w.tdqkv16, 3 * H, w.T16[i], H, p.qkv_w, p.qkv_b));
             B2_TRY(r.grad_input(Mt, 3 * H, H, w.tdqkv16, p.qkv_w, nullptr, 0, w.t32a, w.dT, nullptr));  // d T^i
         }
@@ -726,7 +754,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             ab.dout = w.v32a; ab.lddo = H;
             ab.dq = w.vdqkv16; ab.dk2 = w.vdqkv16 + H; ab.dv2 = w.vdqkv16 + 2 * H; ab.ldd = 3 * H;
             if (fused) { ab.dk1 = w.dk1; ab.dv1 = w.dv1; ab.ldd1 = H; }
-            B2_TRY(launch_attention_bwd(ab, w.delta, s));
+            { ProfScope ps(h, s, CAT_ATTN); B2_TRY(launch_attention_bwd(ab, w.delta, s)); }
             B2_TRY(r.grad_weight(Mv, 3 * H, H, w.vdqkv16, 3 * H, a.u16, H, p.qkv_w, p.qkv_b));
             B2_TRY(r.grad_input(Mv, 3 * H, H, w.vdqkv16, p.qkv_w, nullptr, 0, nullptr, w.v32a, nullptr));
             B2_TRY(launch_layernorm_bwd(w.v32a, w.V32[i], a.mean1, a.rstd1, r.p32(p.ln1_w), w.v32b, nullptr, 0, w.dV, w.dV16,
@@ -760,6 +788,31 @@ extern "C" int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* par
     const float bc1 = (float)bc1d, bc2 = (float)bc2d;
     return launch_adamw(params32, grads32, exp_avg, exp_avg_sq, reinterpret_cast<bf16*>(params16), h->segs_dev[mode],
                         h->nseg, h->lay.total, lr, beta1, beta2, eps, weight_decay, bc1, bc2, (cudaStream_t)stream);
+}
+
+// --------------------------------------------------------------------------------------- profiling
+extern "C" int32_t b200mart_profile_begin(b200mart_handle* h) {
+    B2_CHECK(h, "profile_begin: null handle");
+    h->profiling = true;
+    h->prof_used = 0;
+    h->prof_flops = 0.0;
+    return 0;
+}
+
+extern "C" int32_t b200mart_profile_end(b200mart_handle* h, void* stream, double ms_by_cat[3], int64_t launches_by_cat[3],
+                                        double* gemm_flops) {
+    B2_CHECK(h && ms_by_cat && launches_by_cat && gemm_flops, "profile_end: null argument");
+    h->profiling = false;
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int c = 0; c < CAT_COUNT; ++c) { ms_by_cat[c] = 0.0; launches_by_cat[c] = 0; }
+    for (size_t i = 0; i < h->prof_used; ++i) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->prof[i].e0, h->prof[i].e1));
+        ms_by_cat[h->prof[i].cat] += ms;
+        launches_by_cat[h->prof[i].cat] += 1;
+    }
+    *gemm_flops = h->prof_flops;
+    return 0;
 }
 
 // --------------------------------------------------------------------------------------- stand-alone operators

@@ -69,18 +69,21 @@ def _read_layout(l, h):
 
 class Engine:
     def __init__(self, cfg: MKGformerConfig, device="cuda"):
-        if not torch.cuda.is_available():
-            raise _lib.B200MartError("b200mart needs a CUDA device (sm_100a); there is no CPU fallback")
+        """device 'cpu' gives parameter STORAGE only (state_dict surgery before .cuda(), as MarT/main.py does);
+        every compute call then raises: there is no CPU fallback."""
         self.cfg = cfg
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.l = _lib.lib()
         self.h = _lib.vp()
         d = _model_desc(cfg)
         _lib.check(self.l.b200mart_create(C.byref(d), C.byref(self.h)))
         self.infos, self.total = _read_layout(self.l, self.h)
         self.by_name = {p.name: p for p in self.infos}
-        with torch.cuda.device(self.device):
-            self.params32 = torch.zeros(self.total, device=self.device, dtype=torch.float32)
+        self.params32 = torch.zeros(self.total, device=self.device, dtype=torch.float32)
+        self.params16 = self.grads32 = None
+        if self.device.type == "cuda":
             self.params16 = torch.zeros(self.total, device=self.device, dtype=torch.bfloat16)
             self.grads32 = torch.zeros(self.total, device=self.device, dtype=torch.float32)
         self.exp_avg = None
@@ -98,6 +101,27 @@ class Engine:
         except Exception:
             pass
 
+    def _need_cuda(self):
+        if self.device.type != "cuda":
+            raise _lib.B200MartError("b200mart computes on a CUDA device (sm_100a) only: move the module with .cuda(); "
+                                     "there is no CPU fallback")
+
+    def move(self, device):
+        """Re-home the flat buffers (parameters and optimizer state keep their values; gradients are reset)."""
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.params32 = self.params32.to(device)
+        self.device = device
+        self.params16 = self.grads32 = None
+        if device.type == "cuda":
+            self.params16 = torch.zeros(self.total, device=device, dtype=torch.bfloat16)
+            self.grads32 = torch.zeros(self.total, device=device, dtype=torch.float32)
+        if self.exp_avg is not None:
+            self.exp_avg, self.exp_avg_sq = self.exp_avg.to(device), self.exp_avg_sq.to(device)
+        self.ws = self.ws_key = None
+        self.mirror_stale = True
+
     # ------------------------------------------------------------------ parameter access
     def view(self, name, flat=None):
         p = self.by_name[name]
@@ -105,6 +129,7 @@ class Engine:
         return flat[p.offset:p.offset + p.numel].view(p.shape)
 
     def grad_view(self, name):
+        self._need_cuda()
         return self.view(name, self.grads32)
 
     def load(self, params):
@@ -115,12 +140,14 @@ class Engine:
         with torch.no_grad():
             for n in self.by_name:
                 self.view(n).copy_(params[n].to(self.device, torch.float32))
-        self.sync_mirror()
+        if self.device.type == "cuda":
+            self.sync_mirror()
 
     def state(self):
         return {n: self.view(n).clone() for n in self.by_name}
 
     def sync_mirror(self):
+        self._need_cuda()
         _lib.check(self.l.b200mart_cast_params(self.h, self.params32.data_ptr(), self.params16.data_ptr(), _lib.cur_stream()))
         self.mirror_stale = False
 
@@ -129,6 +156,7 @@ class Engine:
 
     # ------------------------------------------------------------------ C-ABI plumbing
     def _bufs(self, B, L, need_grad=True):
+        self._need_cuda()
         key = (B, L)
         if self.ws_key != key:
             nbytes = self.l.b200mart_workspace_bytes(self.h, B, L)
@@ -165,6 +193,7 @@ class Engine:
     # ------------------------------------------------------------------ the path
     def forward(self, batch, want_z=True, want_logits=False):
         """UnimoForMaskedLM.forward. Returns (z (B,L,H) fp32 or None, logits (B,L,V) fp32 or None)."""
+        self._need_cuda()
         if self.mirror_stale:
             self.sync_mirror()
         cb = self._batch(batch)
@@ -217,6 +246,7 @@ class Engine:
                                             _lib.ptr(dlogits), _lib.ptr(scratch), _lib.cur_stream()))
 
     def adamw(self, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, pretrain=False):
+        self._need_cuda()
         if self.exp_avg is None:
             self.exp_avg = torch.zeros_like(self.params32)
             self.exp_avg_sq = torch.zeros_like(self.params32)
@@ -225,6 +255,19 @@ class Engine:
                                          float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(pretrain),
                                          _lib.cur_stream()))
         self.mirror_stale = False
+
+    # ------------------------------------------------------------------ instrumentation (bench / profiles only)
+    def launch_count(self):
+        return self.l.b200mart_launch_count()
+
+    def profile_begin(self):
+        _lib.check(self.l.b200mart_profile_begin(self.h))
+
+    def profile_end(self):
+        """{'gemm'|'attention'|'fusion': (device ms, launches)}, gemm flops."""
+        ms, n, fl = (C.c_double * 3)(), (_lib.i64 * 3)(), C.c_double()
+        _lib.check(self.l.b200mart_profile_end(self.h, _lib.cur_stream(), C.byref(ms), C.byref(n), C.byref(fl)))
+        return {k: (ms[i], n[i]) for i, k in enumerate(("gemm", "attention", "fusion"))}, fl.value
 
     def status(self):
         if self.ws is None:

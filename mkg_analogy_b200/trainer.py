@@ -1,0 +1,139 @@
+"""Fused training / evaluation step of the MarT hot path on one GPU (one process per GPU when data-parallel).
+
+This is the B200-native counterpart of what `TransformerLitModel.training_step` + `loss.backward()` + the AdamW /
+linear-warmup scheduler of `configure_optimizers` do in the reference (MarT/lit_models/transformer.py:59-113, :224-241;
+MarT/lit_models/base.py:30-32,:86-91), with the score head evaluated on the [MASK] rows only (SURVEY.md §8 b4
+"fused" mode).  Data parallelism: every rank holds a replica, processes its own shard of the global
+batch, and the flat fp32 gradient buffer is averaged across ranks with NCCL all-reduce before the optimizer step.
+"""
+import torch
+
+from .config import MKGformerConfig
+from .data import VocabLayout
+from .engine import Engine
+
+BATCH_KEYS = ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "sep_idx", "label", "rel_idx", "q_head_idx",
+              "a_head_idx", "pre_type")
+
+
+def linear_warmup_lr(step, total_steps, base_lr, warmup_ratio):
+    """get_linear_schedule_with_warmup as used at transformer.py:233-240: `step` optimizer steps already taken."""
+    warm = total_steps * warmup_ratio
+    if step < warm:
+        return base_lr * step / max(1.0, warm)
+    return base_lr * max(0.0, (total_steps - step) / max(1.0, total_steps - warm))
+
+
+def init_weights_(engine: Engine, seed=0):
+    """Seeded synthetic weights generated on the device: N(0, 0.02) for matrices / embeddings / biases,
+    LayerNorm (1, 0), class_embedding ~ N(0, 1), adaptive weights U(0, 0.5) and exactly 0.5 (modeling_unimo.py:305-310)."""
+    g = torch.Generator(device=engine.device).manual_seed(seed)
+    with torch.no_grad():
+        engine.params32.normal_(0.0, 0.02, generator=g)
+        for info in engine.infos:
+            n, v = info.name, engine.view(info.name)
+            if "LayerNorm.weight" in n or "layer_norm1.weight" in n or "layer_norm2.weight" in n or \
+                    n.endswith("layrnorm.weight") or n.endswith("layernorm.weight"):
+                v.fill_(1.0)
+            elif "LayerNorm.bias" in n or "layer_norm1.bias" in n or "layer_norm2.bias" in n or \
+                    n.endswith("layrnorm.bias") or n.endswith("layernorm.bias"):
+                v.zero_()
+            elif n.endswith("adaptive_weight.0"):
+                v.uniform_(0.0, 0.5, generator=g)
+            elif n.endswith("adaptive_weight.1"):
+                v.fill_(0.5)
+            elif n.endswith("class_embedding"):
+                v.normal_(0.0, 1.0, generator=g)
+    engine.sync_mirror()
+
+
+class MartTrainer:
+    def __init__(self, cfg: MKGformerConfig, vocab: VocabLayout, *, pretrain=False, lr=5e-5, weight_decay=0.01,
+                 warmup_ratio=0.1, total_steps=1000, alpha=0.43, label_smoothing=0.1, device=None, process_group=None,
+                 grad_buckets=8):
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.cfg, self.vocab, self.pretrain = cfg, vocab, bool(pretrain)
+        self.engine = Engine(cfg, device)
+        self.device = self.engine.device
+        self.lr, self.weight_decay, self.warmup_ratio, self.total_steps = lr, weight_decay, warmup_ratio, total_steps
+        self.alpha, self.label_smoothing = alpha, label_smoothing
+        self.col_ids = torch.as_tensor(vocab.analogy_entity_ids(), device=self.device, dtype=torch.int64)
+        self.steps_done = 0
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.grad_buckets = grad_buckets
+        self._dev_batch = None
+
+    # ------------------------------------------------------------------ pieces
+    def _head(self, batch):
+        if self.pretrain:
+            return dict(mode="pretrain", entity_range=(self.vocab.entity_id_st, self.vocab.entity_id_ed),
+                        relation_range=(self.vocab.relation_id_st, self.vocab.relation_id_ed), label=batch["label"],
+                        pre_type=batch["pre_type"], label_smoothing=self.label_smoothing)
+        return dict(mode="finetune", col_ids=self.col_ids, label=batch["label"], rel_idx=batch["rel_idx"],
+                    q_head_idx=batch["q_head_idx"], a_head_idx=batch["a_head_idx"], alpha=self.alpha,
+                    label_smoothing=self.label_smoothing)
+
+    def _model_inputs(self, batch):
+        b = {k: batch[k] for k in ("input_ids", "attention_mask", "pixel_values")}
+        if batch.get("token_type_ids") is not None:
+            b["token_type_ids"] = batch["token_type_ids"]
+        if not self.pretrain and batch.get("sep_idx") is not None:
+            b["sep_idx"] = batch["sep_idx"]      # the pre-train collator supplies no sep_idx
+        return b
+
+    def allreduce_grads(self):
+        """Average the flat gradient buffer over the data-parallel ranks (NCCL over NVLink). A few large buckets:
+        launch latency, not link count, is what matters on NVSwitch."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        g = self.engine.grads32
+        n = g.numel()
+        per = (n + self.grad_buckets - 1) // self.grad_buckets
+        per = (per + 1023) // 1024 * 1024
+        for st in range(0, n, per):
+            dist.all_reduce(g[st:min(n, st + per)], op=dist.ReduceOp.AVG, group=self.pg)
+
+    # ------------------------------------------------------------------ public API
+    def train_step(self, batch):
+        """One optimizer step on a device-resident batch. Returns the loss as a device tensor (1,)."""
+        eng = self.engine
+        mb = self._model_inputs(batch)
+        eng.zero_grad()
+        eng.forward(mb, want_z=False)
+        loss, _, _ = eng.head_loss(mb, self._head(batch), compute_grad=True)
+        eng.backward(mb)
+        self.allreduce_grads()
+        lr = linear_warmup_lr(self.steps_done, self.total_steps, self.lr, self.warmup_ratio)
+        self.steps_done += 1
+        eng.adamw(self.steps_done, lr, weight_decay=self.weight_decay, pretrain=self.pretrain)
+        return loss
+
+    def train_step_host(self, host_batch):
+        """End-to-end step from (pinned) host tensors: H2D copies, step, D2H read of the loss. Returns a float."""
+        return float(self.train_step(self.to_device(host_batch)).item())
+
+    def to_device(self, host_batch):
+        if self._dev_batch is None or any(self._dev_batch[k].shape != v.shape for k, v in host_batch.items() if k in self._dev_batch):
+            self._dev_batch = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host_batch.items()
+                               if k in BATCH_KEYS}
+        for k, d in self._dev_batch.items():
+            d.copy_(host_batch[k], non_blocking=True)
+        return self._dev_batch
+
+    @torch.no_grad()
+    def eval_step(self, batch):
+        """_eval (transformer.py:115-166): ranks of the gold entity (1-based), and the [MASK]-row scores."""
+        eng = self.engine
+        mb = self._model_inputs(batch)
+        eng.forward(mb, want_z=False)
+        loss, logits, ranks = eng.head_loss(mb, self._head(batch), compute_grad=False, want_logits=True, want_ranks=True)
+        return ranks, logits, loss
+
+    @staticmethod
+    def h2d_bytes(host_batch):
+        return int(sum(v.numel() * v.element_size() for k, v in host_batch.items() if k in BATCH_KEYS))
