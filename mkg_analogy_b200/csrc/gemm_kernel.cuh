@@ -1,0 +1,395 @@
+// Persistent tcgen05 GEMM kernel for sm_100a (device code; instantiated per N-tile in gemm_inst*.cu).
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared-memory ring -> tcgen05.mma (one elected thread, fp32
+//   accumulators in TMEM, DOUBLE-BUFFERED so the epilogue of tile i overlaps the main loop of tile i+1) ->
+//   tcgen05.ld epilogue with a compile-time-specialised fused epilogue.
+//   One CTA per SM loops over output tiles (static round-robin scheduler); three pipelines: smem full/empty
+//   (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue) and the tile loop.
+//
+// Replaces, for the MarT hot path, every nn.Linear product of the reference model
+// (MarT/models/modeling_unimo.py:212-287 CLIP attention/MLP, :317-478 BERT attention/FFN,
+// :956-976 MLM head) and their autograd transposes (dX = dY W, dW = dY^T X).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31, i.e. 32 rows of the 128-row tile).
+// Epilogue data path: TMEM -> registers (lane = row, 64 columns at a time) -> per-warp shared-memory transpose
+// -> lane = column PAIR, so that every global access of the epilogue (bias, saved pre-activation, residual,
+// outputs, reductions) is a coalesced 256-byte (fp32) / 128-byte (bf16) row segment.
+#pragma once
+#include "gemm.cuh"
+
+namespace gemmk {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int GEMM_THREADS = 192;
+constexpr int EPI_COLS = 64;   // columns per epilogue pass
+constexpr int EPI_LD = 65;     // padded row of the per-warp transpose buffer (fp32 words)
+
+// fused epilogues (compile-time).  Every kind except GENERIC requires even N and even leading dimensions.
+enum EpiKind {
+    EPI_GENERIC = 0,  // any combination of the GemmOp epilogue fields, scalar accesses
+    EPI_BF16 = 1,     // out_bf16 = acc*alpha + bias (+bias2)
+    EPI_ACT = 2,      // pre = acc*alpha + bias (+bias2); out_preact = pre; out_bf16 = act(pre)
+    EPI_RES = 3,      // out_f32 = acc*alpha (+bias) + residual   [+ out_bf16 copy]
+    EPI_F32 = 4,      // out_f32 = acc*alpha (+bias)
+    EPI_DACT = 5,     // out_bf16 = acc*alpha * act'(dact_src)
+    EPI_ACC = 6,      // out_f32 += acc*alpha   (vector reductions; split-K safe)
+};
+
+struct GemmDev {
+    int M, N;
+    int kb1, kb_total;  // k-blocks served by pair 1 / total
+    int mt, nt, nsplit, kb_per;   // tile grid, split-K factor, k-blocks per split
+    float alpha;
+    const float* bias;
+    const float* bias2;
+    bf16* out_preact; long ldp;
+    int act;
+    const bf16* dact_src; long ldx; int dact;
+    const float* residual; long ldr;
+    float* out_f32; long ldo32;
+    bf16* out_bf16; long ldo16;
+    int accumulate;
+    int debug;   // B200MART_GEMM_DEBUG bitmask (bring-up only): 1 no epilogue global access, 2 no TMA, 4 no MMA
+};
+
+template <int BN>
+struct SmemLayout {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN >= 256) ? 4 : ((BN >= 128) ? 5 : 6);
+    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+    static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+    static constexpr int TMEM_COLS = 2 * BN;               // two accumulator buffers (power of two >= 32)
+};
+
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float act_fwd(int act, float v) {
+    return act == 1 ? gelu_erf(v) : (act == 2 ? quick_gelu(v) : v);
+}
+__device__ __forceinline__ float act_grad(int act, float x) { return act == 1 ? gelu_erf_grad(x) : quick_gelu_grad(x); }
+
+// One 32-row x 64-column block of the output, values staged in `stg` (row-major, EPI_LD), lane = column pair.
+template <int EPI>
+__device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* stg, int row0, int nrows, int col0, int lane) {
+    if (EPI == EPI_GENERIC) {
+        // scalar, any flags: lane handles columns col0+lane and col0+32+lane
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int col = col0 + half * 32 + lane;
+            if (col >= p.N) continue;
+            float badd = 0.f;
+            if (p.bias) badd = __ldg(p.bias + col);
+            if (p.bias2) badd += __ldg(p.bias2 + col);
+#pragma unroll 1
+            for (int rr = 0; rr < nrows; ++rr) {
+                const long row = row0 + rr;
+                float v = stg[rr * EPI_LD + half * 32 + lane] * p.alpha + badd;
+                if (p.out_preact) p.out_preact[row * p.ldp + col] = __float2bfloat16(v);
+                v = act_fwd(p.act, v);
+                if (p.dact) v *= act_grad(p.dact, __bfloat162float(p.dact_src[row * p.ldx + col]));
+                if (p.residual) v += p.residual[row * p.ldr + col];
+                if (p.out_f32) {
+                    if (p.accumulate) atomicAdd(p.out_f32 + row * p.ldo32 + col, v);
+                    else p.out_f32[row * p.ldo32 + col] = v;
+                }
+                if (p.out_bf16) p.out_bf16[row * p.ldo16 + col] = __float2bfloat16(v);
+            }
+        }
+        return;
+    }
+    const int col = col0 + 2 * lane;       // even; N even -> the pair is valid or invalid together
+    if (col >= p.N) return;
+    float b0 = 0.f, b1 = 0.f;
+    if (EPI == EPI_BF16 || EPI == EPI_ACT || EPI == EPI_RES || EPI == EPI_F32) {
+        if (p.bias) { const float2 t = __ldg(reinterpret_cast<const float2*>(p.bias + col)); b0 = t.x; b1 = t.y; }
+        if ((EPI == EPI_BF16 || EPI == EPI_ACT) && p.bias2) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(p.bias2 + col)); b0 += t.x; b1 += t.y;
+        }
+    }
+    constexpr int RB = 4;   // rows per batch: loads first, then math, then stores
+#pragma unroll 1
+    for (int r0 = 0; r0 < nrows; r0 += RB) {
+        float v0[RB], v1[RB];
+        float2 rs[RB];
+        uint32_t xs[RB];
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            const int rr = r0 + u;
+            const long row = row0 + rr;
+            if (rr < nrows) {
+                if (EPI == EPI_RES) rs[u] = *reinterpret_cast<const float2*>(p.residual + row * p.ldr + col);
+                if (EPI == EPI_DACT) xs[u] = *reinterpret_cast<const uint32_t*>(p.dact_src + row * p.ldx + col);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            const int rr = min(r0 + u, 31);
+            v0[u] = stg[rr * EPI_LD + 2 * lane] * p.alpha + b0;
+            v1[u] = stg[rr * EPI_LD + 2 * lane + 1] * p.alpha + b1;
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            const int rr = r0 + u;
+            const long row = row0 + rr;
+            if (rr >= nrows) break;
+            if (EPI == EPI_BF16) {
+                *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(v0[u], v1[u]);
+            } else if (EPI == EPI_ACT) {
+                *reinterpret_cast<uint32_t*>(p.out_preact + row * p.ldp + col) = pack_bf16x2(v0[u], v1[u]);
+                *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) =
+                    pack_bf16x2(act_fwd(p.act, v0[u]), act_fwd(p.act, v1[u]));
+            } else if (EPI == EPI_RES) {
+                const float o0 = v0[u] + rs[u].x, o1 = v1[u] + rs[u].y;
+                *reinterpret_cast<float2*>(p.out_f32 + row * p.ldo32 + col) = make_float2(o0, o1);
+                if (p.out_bf16) *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(o0, o1);
+            } else if (EPI == EPI_F32) {
+                *reinterpret_cast<float2*>(p.out_f32 + row * p.ldo32 + col) = make_float2(v0[u], v1[u]);
+            } else if (EPI == EPI_DACT) {
+                const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[u]));
+                *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) =
+                    pack_bf16x2(v0[u] * act_grad(p.dact, x.x), v1[u] * act_grad(p.dact, x.y));
+            } else if (EPI == EPI_ACC) {
+                red_add_v2(p.out_f32 + row * p.ldo32 + col, v0[u], v1[u]);
+            }
+        }
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                  const GemmDev p) {
+    using L = SmemLayout<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled tiles need a 1024-byte aligned base
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (L::STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * L::STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * L::STAGES + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * L::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.mt * p.nt * p.nsplit;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < L::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 4);   // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, L::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    // tile -> (m block, n block, k range).  m fastest: concurrently running CTAs share few B (weight) tiles.
+    auto tile_coords = [&](int t, int& m0, int& n0, int& kb_begin, int& kb_end) {
+        const int mb = t % p.mt;
+        const int rest = t / p.mt;
+        const int nb = rest % p.nt;
+        const int z = rest / p.nt;
+        m0 = mb * BM;
+        n0 = nb * BN;
+        kb_begin = z * p.kb_per;
+        kb_end = min(p.kb_total, kb_begin + p.kb_per);
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int m0, n0, kb_begin, kb_end;
+                tile_coords(t, m0, n0, kb_begin, kb_end);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sA = smem_base + stage * L::STAGE_BYTES;
+                    const uint32_t sB = sA + L::A_BYTES;
+                    if (p.debug & 2) {
+                        mbar_arrive(full_bar(stage));
+                        if (++stage == L::STAGES) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
+                    mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
+                    const bool second = kb >= p.kb1;
+                    const CUtensorMap* ma = second ? &tmA2 : &tmA;
+                    const CUtensorMap* mb = second ? &tmB2 : &tmB;
+                    const int k0 = (second ? kb - p.kb1 : kb) * BK;
+                    if (!A_MN) {
+                        tma_load_2d(sA, ma, full_bar(stage), k0, m0);  // box {64 k, 128 m}
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BM / 64; ++c)  // box {64 m, 64 k}
+                            tma_load_2d(sA + c * (BK * 128), ma, full_bar(stage), m0 + c * 64, k0);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sB, mb, full_bar(stage), k0, n0);  // box {64 k, BN n}
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BN / 64; ++c)
+                            tma_load_2d(sB + c * (BK * 128), mb, full_bar(stage), n0 + c * 64, k0);
+                    }
+                    if (++stage == L::STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int m0, n0, kb_begin, kb_end;
+                tile_coords(t, m0, n0, kb_begin, kb_end);
+                if (kb_end <= kb_begin) continue;
+                const int ab = it & 1;
+                const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+                ++it;
+                mbar_wait(tempty_bar(ab), aph ^ 1u);   // epilogue has drained this accumulator buffer
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(ab * BN);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_base + stage * L::STAGE_BYTES;
+                    const uint32_t sB = sA + L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        if (p.debug & 4) break;
+                        // K-major: rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO); a UMMA_K=16
+                        //          slice is 32 B further along the row.
+                        // MN-major: 64-element MN chunks BK*128 B apart (LBO), 8-k-row atoms 1024 B
+                        //          apart (SBO); a UMMA_K=16 slice is 16 rows = 2048 B further.
+                        const uint64_t da = A_MN ? umma_desc_sw128(sA + k * 2048, BK * 128, 1024)
+                                                 : umma_desc_sw128(sA + k * 32, 16, 1024);
+                        const uint64_t db = B_MN ? umma_desc_sw128(sB + k * 2048, BK * 128, 1024)
+                                                 : umma_desc_sw128(sB + k * 32, 16, 1024);
+                        umma_bf16(tacc, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+                    if (++stage == L::STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull_bar(ab));  // accumulator complete
+            }
+        }
+    } else {
+        // ===================== epilogue (4 warps) =====================
+        const int quad = warp & 3;
+        float* stg = reinterpret_cast<float*>(smem_gen + L::EPI_OFFSET) + (warp - 2) * 32 * EPI_LD;
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            int m0, n0, kb_begin, kb_end;
+            tile_coords(t, m0, n0, kb_begin, kb_end);
+            if (kb_end <= kb_begin) continue;
+            const int ab = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            ++it;
+            mbar_wait(tfull_bar(ab), aph);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN);
+            const int row0 = m0 + quad * 32;
+            const int nrows = min(32, p.M - row0);   // may be <= 0 for the ragged last tile
+#pragma unroll 1
+            for (int c = 0; c < BN / EPI_COLS; ++c) {
+                uint32_t r[EPI_COLS];
+                tmem_ld32(tacc + (uint32_t)(c * EPI_COLS), r);
+                tmem_ld32(tacc + (uint32_t)(c * EPI_COLS + 32), r + 32);
+                tmem_ld_wait();
+                if (c == BN / EPI_COLS - 1) {   // all TMEM reads of this buffer are done: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(ab));
+                }
+                const int col0 = n0 + c * EPI_COLS;
+                if (col0 >= p.N || nrows <= 0 || (p.debug & 1)) continue;   // warp-uniform
+#pragma unroll
+                for (int j = 0; j < EPI_COLS; ++j) stg[lane * EPI_LD + j] = __uint_as_float(r[j]);
+                __syncwarp();
+                epilogue_block<EPI>(p, stg, row0, nrows, col0, lane);
+                __syncwarp();   // the transpose buffer is reused by the next pass
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, L::TMEM_COLS);
+    }
+}
+
+typedef void (*GemmKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmDev);
+
+// the (layout, epilogue) combinations the model uses get a specialised kernel; everything else is GENERIC
+template <int BN>
+inline GemmKernel pick_kernel_bn(int a_mn, int b_mn, int epi) {
+    if (!a_mn && !b_mn) {
+        switch (epi) {
+            case EPI_BF16: return gemm_bf16_tcgen05<BN, false, false, EPI_BF16>;
+            case EPI_ACT: return gemm_bf16_tcgen05<BN, false, false, EPI_ACT>;
+            case EPI_RES: return gemm_bf16_tcgen05<BN, false, false, EPI_RES>;
+            case EPI_F32: return gemm_bf16_tcgen05<BN, false, false, EPI_F32>;
+            default: return gemm_bf16_tcgen05<BN, false, false, EPI_GENERIC>;
+        }
+    }
+    if (!a_mn && b_mn) {
+        switch (epi) {
+            case EPI_DACT: return gemm_bf16_tcgen05<BN, false, true, EPI_DACT>;
+            case EPI_RES: return gemm_bf16_tcgen05<BN, false, true, EPI_RES>;
+            case EPI_F32: return gemm_bf16_tcgen05<BN, false, true, EPI_F32>;
+            case EPI_ACC: return gemm_bf16_tcgen05<BN, false, true, EPI_ACC>;
+            default: return gemm_bf16_tcgen05<BN, false, true, EPI_GENERIC>;
+        }
+    }
+    if (a_mn && b_mn) {
+        switch (epi) {
+            case EPI_ACC: return gemm_bf16_tcgen05<BN, true, true, EPI_ACC>;
+            case EPI_F32: return gemm_bf16_tcgen05<BN, true, true, EPI_F32>;
+            default: return gemm_bf16_tcgen05<BN, true, true, EPI_GENERIC>;
+        }
+    }
+    return gemm_bf16_tcgen05<BN, true, false, EPI_GENERIC>;
+}
+
+// true when pick_kernel_bn has a specialised kernel for this combination
+inline bool has_specialised(int a_mn, int b_mn, int epi) {
+    if (epi == EPI_GENERIC) return true;
+    if (!a_mn && !b_mn) return epi == EPI_BF16 || epi == EPI_ACT || epi == EPI_RES || epi == EPI_F32;
+    if (!a_mn && b_mn) return epi == EPI_DACT || epi == EPI_RES || epi == EPI_F32 || epi == EPI_ACC;
+    if (a_mn && b_mn) return epi == EPI_ACC || epi == EPI_F32;
+    return false;
+}
+
+}  // namespace gemmk
+
+// defined in gemm_inst{64,128,256}.cu
+gemmk::GemmKernel gemm_pick_kernel_64(int a_mn, int b_mn, int epi);
+gemmk::GemmKernel gemm_pick_kernel_128(int a_mn, int b_mn, int epi);
+gemmk::GemmKernel gemm_pick_kernel_256(int a_mn, int b_mn, int epi);
