@@ -47,7 +47,7 @@ int64_t b200mart_launch_count(void);
  *   a_mn/b_mn: 0 = operand stored [rows][K] (K contiguous); 1 = stored [K][rows].
  *   (A2,B2,K2): optional second operand pair extending the contraction (K must be a multiple of 64).
  *   epilogue order: *alpha, +bias[n] (+bias2[n]), store out_preact, act (1 gelu-erf, 2 quick-gelu),
- *                   *act'(dact_src) (dact 1/2), +residual, store out_f32 (or atomically accumulate) / out_bf16.
+ *                   *act'(dact_src) (dact 1/2) or *dact_src (dact 3), +residual, store out_f32 (or atomically accumulate) / out_bf16.
  */
 typedef struct b200mart_gemm_desc {
     int32_t M, N, K, K2;
@@ -61,7 +61,8 @@ typedef struct b200mart_gemm_desc {
     const float* bias2;            /* optional second bias (bias of the second operand pair) */
     void* out_preact; int64_t ldp; /* bf16 */
     int32_t act;
-    const void* dact_src; int64_t ldx; int32_t dact;
+    int32_t save_grad;             /* out_preact receives act'(pre-activation) (bf16) instead of the pre-activation */
+    const void* dact_src; int64_t ldx; int32_t dact;   /* dact 1/2: *= act'(dact_src); 3: *= dact_src (saved derivative) */
     const float* residual; int64_t ldr;
     float* out_f32; int64_t ldo32;
     void* out_bf16; int64_t ldo16;

@@ -29,7 +29,7 @@ class GemmDesc(C.Structure):
         ("bias", vp),
         ("bias2", vp),
         ("out_preact", vp), ("ldp", i64),
-        ("act", i32),
+        ("act", i32), ("save_grad", i32),
         ("dact_src", vp), ("ldx", i64), ("dact", i32),
         ("residual", vp), ("ldr", i64),
         ("out_f32", vp), ("ldo32", i64),
@@ -147,7 +147,7 @@ def cur_stream():
 
 
 def gemm_bf16(A, B, *, a_mn=False, b_mn=False, A2=None, B2=None, alpha=1.0, bias=None, bias2=None, act=0,
-              out_preact=None, dact_src=None, dact=0, residual=None, out_f32=None, out_bf16=None,
+              out_preact=None, save_grad=False, dact_src=None, dact=0, residual=None, out_f32=None, out_bf16=None,
               accumulate=False, split_k=1, bn=0, stream=None):
     """D = epilogue(A @ B^T) on the tcgen05 kernel. Shapes: A [M,K] (or [K,M] when a_mn), B [N,K] (or [K,N])."""
     M, K = (A.shape[1], A.shape[0]) if a_mn else A.shape
@@ -165,6 +165,7 @@ def gemm_bf16(A, B, *, a_mn=False, b_mn=False, A2=None, B2=None, alpha=1.0, bias
     if out_preact is not None:
         d.out_preact, d.ldp = out_preact.data_ptr(), out_preact.stride(0)
     d.act = act
+    d.save_grad = int(save_grad)
     if dact_src is not None:
         d.dact_src, d.ldx, d.dact = dact_src.data_ptr(), dact_src.stride(0), dact
     if residual is not None:

@@ -29,7 +29,7 @@ extern "C" int32_t b200mart_gemm_bf16(const b200mart_gemm_desc* d, void* stream)
     op.A2 = (const bf16*)d->A2; op.lda2 = d->lda2; op.B2 = (const bf16*)d->B2; op.ldb2 = d->ldb2;
     op.alpha = d->alpha; op.bias = d->bias; op.bias2 = d->bias2;
     op.out_preact = (bf16*)d->out_preact; op.ldp = d->ldp;
-    op.act = d->act; op.dact_src = (const bf16*)d->dact_src; op.ldx = d->ldx; op.dact = d->dact;
+    op.act = d->act; op.save_grad = d->save_grad; op.dact_src = (const bf16*)d->dact_src; op.ldx = d->ldx; op.dact = d->dact;
     op.residual = d->residual; op.ldr = d->ldr;
     op.out_f32 = d->out_f32; op.ldo32 = d->ldo32; op.out_bf16 = (bf16*)d->out_bf16; op.ldo16 = d->ldo16;
     op.accumulate = d->accumulate; op.split_k = d->split_k > 0 ? d->split_k : 1; op.bn = d->bn;

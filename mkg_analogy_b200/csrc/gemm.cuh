@@ -23,7 +23,8 @@ struct GemmOp {
     const float* bias2 = nullptr;         // + bias2[n] (second operand pair's bias)
     bf16* out_preact = nullptr; long ldp = 0;   // store value before activation (saved for backward)
     int act = 0;                          // 0 none, 1 gelu(erf), 2 quick_gelu
-    const bf16* dact_src = nullptr; long ldx = 0; int dact = 0;  // *= act'(dact_src[m,n]) (backward)
+    int save_grad = 0;                    // out_preact receives act'(pre-activation) instead of the pre-activation
+    const bf16* dact_src = nullptr; long ldx = 0; int dact = 0;  // *= act'(dact_src[m,n]) (backward); dact = 3: dact_src already holds act'
     const float* residual = nullptr; long ldr = 0;   // + residual[m,n] (fp32)
     float* out_f32 = nullptr; long ldo32 = 0;
     bf16* out_bf16 = nullptr; long ldo16 = 0;

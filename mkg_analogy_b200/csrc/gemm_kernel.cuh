@@ -29,10 +29,10 @@ constexpr int EPI_LD = 65;     // padded row of the per-warp transpose buffer (f
 enum EpiKind {
     EPI_GENERIC = 0,  // any combination of the GemmOp epilogue fields, scalar accesses
     EPI_BF16 = 1,     // out_bf16 = acc*alpha + bias (+bias2)
-    EPI_ACT = 2,      // pre = acc*alpha + bias (+bias2); out_preact = pre; out_bf16 = act(pre)
+    EPI_ACT = 2,      // pre = acc*alpha + bias (+bias2); out_preact = pre (or act'(pre)); out_bf16 = act(pre)
     EPI_RES = 3,      // out_f32 = acc*alpha (+bias) + residual   [+ out_bf16 copy]
     EPI_F32 = 4,      // out_f32 = acc*alpha (+bias)
-    EPI_DACT = 5,     // out_bf16 = acc*alpha * act'(dact_src)
+    EPI_DACT = 5,     // out_bf16 = acc*alpha * dact_src   (dact_src holds the saved activation derivative, dact = 3)
     EPI_ACC = 6,      // out_f32 += acc*alpha   (vector reductions; split-K safe)
 };
 
@@ -44,7 +44,7 @@ struct GemmDev {
     const float* bias;
     const float* bias2;
     bf16* out_preact; long ldp;
-    int act;
+    int act, save_grad;
     const bf16* dact_src; long ldx; int dact;
     const float* residual; long ldr;
     float* out_f32; long ldo32;
@@ -74,9 +74,93 @@ __device__ __forceinline__ float act_fwd(int act, float v) {
 }
 __device__ __forceinline__ float act_grad(int act, float x) { return act == 1 ? gelu_erf_grad(x) : quick_gelu_grad(x); }
 
-// One 32-row x 64-column block of the output, values staged in `stg` (row-major, EPI_LD), lane = column pair.
+// Per-pass epilogue inputs that come from HBM (residual / saved pre-activation): one 32-row x 64-column block,
+// lane = column pair, ALL 32 rows issued back to back so that a warp keeps 32 x 256 B (128 B) loads in flight; they are
+// issued before the TMEM read + transpose of the pass (pass 0: before the accumulator-ready wait).
 template <int EPI>
-__device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* stg, int row0, int nrows, int col0, int lane) {
+struct EpiIn {
+    static constexpr bool kRes = (EPI == EPI_RES), kDact = (EPI == EPI_DACT);
+    float2 rs[kRes ? 32 : 1];
+    uint32_t xs[kDact ? 32 : 1];
+    __device__ __forceinline__ void load(const GemmDev& p, int row0, int nrows, int col0, int lane) {
+        const int col = col0 + 2 * lane;
+        if (!(kRes || kDact) || col >= p.N) return;
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+            if (rr < nrows) {
+                const long row = row0 + rr;
+                if (kRes) rs[rr] = *reinterpret_cast<const float2*>(p.residual + row * p.ldr + col);
+                if (kDact) xs[rr] = *reinterpret_cast<const uint32_t*>(p.dact_src + row * p.ldx + col);
+            }
+        }
+    }
+};
+
+// activation value and derivative from one evaluation of the transcendental part
+template <int ACT> __device__ __forceinline__ void act_both(float x, float& y, float& dy) {
+    if (ACT == 1) {          // exact (erf) GELU: y = x Phi(x), y' = Phi(x) + x phi(x)
+        const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+        y = x * cdf;
+        dy = cdf + x * 0.39894228040143268f * __expf(-0.5f * x * x);
+    } else {                 // quick GELU: y = x s, s = sigmoid(1.702 x), y' = s + 1.702 x s (1 - s)
+        const float sg = 1.0f / (1.0f + __expf(-1.702f * x));
+        y = x * sg;
+        dy = sg + 1.702f * x * sg * (1.0f - sg);
+    }
+}
+
+// One 32-row x 64-column block of the output, values staged in `stg` (row-major, EPI_LD), lane = column pair.
+// ACT: compile-time activation (1 gelu-erf, 2 quick-gelu) for EPI_ACT / EPI_DACT.
+template <int EPI, int ACT>
+__device__ __forceinline__ void epilogue_row(const GemmDev& p, const float* stg, float2 rs, uint32_t xs, long row, int rr, int col,
+                                             float b0, float b1, int lane) {
+    const float v0 = stg[rr * EPI_LD + 2 * lane] * p.alpha + b0;
+    const float v1 = stg[rr * EPI_LD + 2 * lane + 1] * p.alpha + b1;
+    if (EPI == EPI_BF16) {
+        *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(v0, v1);
+    } else if (EPI == EPI_ACT) {
+        float y0, y1, d0, d1;
+        act_both<ACT>(v0, y0, d0);
+        act_both<ACT>(v1, y1, d1);
+        // saved for backward: the pre-activation, or directly the activation derivative (save_grad)
+        *reinterpret_cast<uint32_t*>(p.out_preact + row * p.ldp + col) = p.save_grad ? pack_bf16x2(d0, d1) : pack_bf16x2(v0, v1);
+        *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(y0, y1);
+    } else if (EPI == EPI_RES) {
+        const float o0 = v0 + rs.x, o1 = v1 + rs.y;
+        *reinterpret_cast<float2*>(p.out_f32 + row * p.ldo32 + col) = make_float2(o0, o1);
+        if (p.out_bf16) *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(o0, o1);
+    } else if (EPI == EPI_F32) {
+        *reinterpret_cast<float2*>(p.out_f32 + row * p.ldo32 + col) = make_float2(v0, v1);
+    } else if (EPI == EPI_DACT) {
+        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs));
+        *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(v0 * x.x, v1 * x.y);
+    } else if (EPI == EPI_ACC) {
+        red_add_v2(p.out_f32 + row * p.ldo32 + col, v0, v1);
+    }
+}
+
+// One 32-row x 64-column block of the output, values staged in `stg` (row-major, EPI_LD), lane = column pair.
+// ACT: compile-time activation (1 gelu-erf, 2 quick-gelu) for EPI_ACT.
+template <int EPI, int ACT>
+__device__ __forceinline__ void epilogue_rows(const GemmDev& p, const float* stg, const EpiIn<EPI>& in, int row0, int nrows,
+                                              int col, float b0, float b1, int lane) {
+    if (EPI == EPI_RES || EPI == EPI_DACT) {
+        // per-row register arrays -> compile-time indices (full unroll, predicated rows)
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr)
+            if (rr < nrows)
+                epilogue_row<EPI, ACT>(p, stg, in.rs[EpiIn<EPI>::kRes ? rr : 0], in.xs[EpiIn<EPI>::kDact ? rr : 0], row0 + rr, rr, col,
+                                       b0, b1, lane);
+    } else {
+#pragma unroll 2
+        for (int rr = 0; rr < nrows; ++rr)
+            epilogue_row<EPI, ACT>(p, stg, make_float2(0.f, 0.f), 0u, row0 + rr, rr, col, b0, b1, lane);
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* stg, const EpiIn<EPI>& in, int row0, int nrows,
+                                               int col0, int lane) {
     if (EPI == EPI_GENERIC) {
         // scalar, any flags: lane handles columns col0+lane and col0+32+lane
 #pragma unroll 1
@@ -90,9 +174,12 @@ __device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* st
             for (int rr = 0; rr < nrows; ++rr) {
                 const long row = row0 + rr;
                 float v = stg[rr * EPI_LD + half * 32 + lane] * p.alpha + badd;
-                if (p.out_preact) p.out_preact[row * p.ldp + col] = __float2bfloat16(v);
+                if (p.out_preact) p.out_preact[row * p.ldp + col] = __float2bfloat16((p.save_grad && p.act) ? act_grad(p.act, v) : v);
                 v = act_fwd(p.act, v);
-                if (p.dact) v *= act_grad(p.dact, __bfloat162float(p.dact_src[row * p.ldx + col]));
+                if (p.dact) {
+                    const float x = __bfloat162float(p.dact_src[row * p.ldx + col]);
+                    v *= (p.dact == 3) ? x : act_grad(p.dact, x);
+                }
                 if (p.residual) v += p.residual[row * p.ldr + col];
                 if (p.out_f32) {
                     if (p.accumulate) atomicAdd(p.out_f32 + row * p.ldo32 + col, v);
@@ -112,52 +199,11 @@ __device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* st
             const float2 t = __ldg(reinterpret_cast<const float2*>(p.bias2 + col)); b0 += t.x; b1 += t.y;
         }
     }
-    constexpr int RB = 4;   // rows per batch: loads first, then math, then stores
-#pragma unroll 1
-    for (int r0 = 0; r0 < nrows; r0 += RB) {
-        float v0[RB], v1[RB];
-        float2 rs[RB];
-        uint32_t xs[RB];
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-            const int rr = r0 + u;
-            const long row = row0 + rr;
-            if (rr < nrows) {
-                if (EPI == EPI_RES) rs[u] = *reinterpret_cast<const float2*>(p.residual + row * p.ldr + col);
-                if (EPI == EPI_DACT) xs[u] = *reinterpret_cast<const uint32_t*>(p.dact_src + row * p.ldx + col);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-            const int rr = min(r0 + u, 31);
-            v0[u] = stg[rr * EPI_LD + 2 * lane] * p.alpha + b0;
-            v1[u] = stg[rr * EPI_LD + 2 * lane + 1] * p.alpha + b1;
-        }
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-            const int rr = r0 + u;
-            const long row = row0 + rr;
-            if (rr >= nrows) break;
-            if (EPI == EPI_BF16) {
-                *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(v0[u], v1[u]);
-            } else if (EPI == EPI_ACT) {
-                *reinterpret_cast<uint32_t*>(p.out_preact + row * p.ldp + col) = pack_bf16x2(v0[u], v1[u]);
-                *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) =
-                    pack_bf16x2(act_fwd(p.act, v0[u]), act_fwd(p.act, v1[u]));
-            } else if (EPI == EPI_RES) {
-                const float o0 = v0[u] + rs[u].x, o1 = v1[u] + rs[u].y;
-                *reinterpret_cast<float2*>(p.out_f32 + row * p.ldo32 + col) = make_float2(o0, o1);
-                if (p.out_bf16) *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(o0, o1);
-            } else if (EPI == EPI_F32) {
-                *reinterpret_cast<float2*>(p.out_f32 + row * p.ldo32 + col) = make_float2(v0[u], v1[u]);
-            } else if (EPI == EPI_DACT) {
-                const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[u]));
-                *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) =
-                    pack_bf16x2(v0[u] * act_grad(p.dact, x.x), v1[u] * act_grad(p.dact, x.y));
-            } else if (EPI == EPI_ACC) {
-                red_add_v2(p.out_f32 + row * p.ldo32 + col, v0[u], v1[u]);
-            }
-        }
+    if (EPI == EPI_ACT) {
+        if (p.act == 1) epilogue_rows<EPI, 1>(p, stg, in, row0, nrows, col, b0, b1, lane);
+        else epilogue_rows<EPI, 2>(p, stg, in, row0, nrows, col, b0, b1, lane);
+    } else {
+        epilogue_rows<EPI, 0>(p, stg, in, row0, nrows, col, b0, b1, lane);
     }
 }
 
@@ -310,13 +356,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int ab = it & 1;
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
             ++it;
+            const int row0 = m0 + quad * 32;
+            const int nrows = min(32, p.M - row0);   // may be <= 0 for the ragged last tile
+            EpiIn<EPI> cur;
+            if (!(p.debug & 1)) cur.load(p, row0, nrows, n0, lane);   // pass 0: fetched while the main loop still runs
             mbar_wait(tfull_bar(ab), aph);
             tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN);
-            const int row0 = m0 + quad * 32;
-            const int nrows = min(32, p.M - row0);   // may be <= 0 for the ragged last tile
 #pragma unroll 1
             for (int c = 0; c < BN / EPI_COLS; ++c) {
+                // HBM inputs of this pass are requested before the TMEM read + transpose so that their latency overlaps
+                if (c > 0 && !(p.debug & 1)) cur.load(p, row0, nrows, n0 + c * EPI_COLS, lane);
                 uint32_t r[EPI_COLS];
                 tmem_ld32(tacc + (uint32_t)(c * EPI_COLS), r);
                 tmem_ld32(tacc + (uint32_t)(c * EPI_COLS + 32), r + 32);
@@ -331,7 +381,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < EPI_COLS; ++j) stg[lane * EPI_LD + j] = __uint_as_float(r[j]);
                 __syncwarp();
-                epilogue_block<EPI>(p, stg, row0, nrows, col0, lane);
+                epilogue_block<EPI>(p, stg, cur, row0, nrows, col0, lane);
                 __syncwarp();   // the transpose buffer is reused by the next pass
             }
         }

@@ -83,10 +83,11 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
         if (op.accumulate && op.out_f32 && !op.out_bf16 && !op.out_preact && !op.bias && !op.bias2 && !op.residual &&
             op.act == 0 && !has_dact)
             epi = EPI_ACC;
-        else if (!op.accumulate && has_dact && op.out_bf16 && !op.out_f32 && !op.out_preact && !op.bias && !op.bias2 &&
+        else if (!op.accumulate && has_dact && op.dact == 3 && op.out_bf16 && !op.out_f32 && !op.out_preact && !op.bias && !op.bias2 &&
                  !op.residual && op.act == 0)
             epi = EPI_DACT;
-        else if (!op.accumulate && !has_dact && op.out_preact && op.out_bf16 && !op.out_f32 && !op.residual && op.bias)
+        else if (!op.accumulate && !has_dact && op.out_preact && op.out_bf16 && !op.out_f32 && !op.residual && op.bias &&
+                 (op.act == 1 || op.act == 2))
             epi = EPI_ACT;
         else if (!op.accumulate && !has_dact && !op.out_preact && op.act == 0 && !op.bias2 && op.residual && op.out_f32)
             epi = EPI_RES;
@@ -134,7 +135,7 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
     d.kb_total = d.kb1 + (op.K2 + BK - 1) / BK;
     d.alpha = op.alpha; d.bias = op.bias; d.bias2 = op.bias2;
     d.out_preact = op.out_preact; d.ldp = op.ldp;
-    d.act = op.act; d.dact_src = op.dact_src; d.ldx = op.ldx; d.dact = op.dact_src ? op.dact : 0;
+    d.act = op.act; d.save_grad = op.save_grad; d.dact_src = op.dact_src; d.ldx = op.ldx; d.dact = op.dact_src ? op.dact : 0;
     d.residual = op.residual; d.ldr = op.ldr;
     d.out_f32 = op.out_f32; d.ldo32 = op.ldo32; d.out_bf16 = op.out_bf16; d.ldo16 = op.ldo16;
     d.accumulate = op.accumulate;

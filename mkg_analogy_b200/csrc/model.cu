@@ -49,6 +49,7 @@ struct Carver {
     }
 };
 
+// pre16 / ipre16 hold the activation DERIVATIVE act'(pre-activation) (saved by the forward GEMM epilogue)
 struct VisLayerA { bf16 *u16, *qkv16, *ctx16, *u2_16, *pre16, *h16; float *mean1, *rstd1, *lse, *x1, *mean2, *rstd2; };
 struct TxtLayerA {
     bf16 *qkv16, *ctx16, *g16, *a16, *ipre16, *i16;
@@ -340,6 +341,8 @@ struct Run {
         if (X2) { op.K2 = K; op.A2 = X2; op.lda2 = K; op.B2 = p16(w2_off); op.ldb2 = K; op.bias2 = p32(b2_off); }
         op.bias = p32(b_off);
         op.act = act; op.out_preact = preact; op.ldp = N;
+        // bf16-output activations save act'(pre) for backward (cheap multiply there); the fp32-output head saves pre itself
+        op.save_grad = (preact != nullptr && out32 == nullptr && act != 0) ? 1 : 0;
         op.residual = residual; op.ldr = N;
         op.out_f32 = out32; op.ldo32 = N; op.out_bf16 = out16; op.ldo16 = N;
         return run_gemm(h, op, s);
@@ -703,7 +706,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             B2_TRY(launch_layernorm_bwd(w.dT, a.opre, a.omean, a.orstd, r.p32(p.oln_w), nullptr, nullptr, 0, w.t32a, w.t16a,
                                         r.g32(p.oln_w), r.g32(p.oln_b), Mt, H, s));
             B2_TRY(r.grad_weight(Mt, H, F, w.t16a, H, a.i16, F, p.o_w, p.o_b));
-            B2_TRY(r.grad_input(Mt, H, F, w.t16a, p.o_w, a.ipre16, 1, nullptr, nullptr, w.tF16));     // d(pre-GELU)
+            B2_TRY(r.grad_input(Mt, H, F, w.t16a, p.o_w, a.ipre16, 3, nullptr, nullptr, w.tF16));     // d(pre-GELU)
             B2_TRY(r.grad_weight(Mt, F, H, w.tF16, F, a.a16, H, p.i_w, p.i_b));
             if (fused) B2_TRY(r.grad_weight(Mt, F, H, w.tF16, F, a.g16, H, p.f_w, p.f_b));
             B2_TRY(r.grad_input(Mt, F, H, w.tF16, p.i_w, nullptr, 0, w.t32a, w.t32b, nullptr));        // d a32 (incl. residual)
@@ -737,7 +740,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             const VisLayerP& p = l.vis[i];
             VisLayerA& a = w.vl[i];
             B2_TRY(r.grad_weight(Mv, H, F, w.dV16, H, a.h16, F, p.fc2_w, p.fc2_b));
-            B2_TRY(r.grad_input(Mv, H, F, w.dV16, p.fc2_w, a.pre16, 2, nullptr, nullptr, w.vF16));
+            B2_TRY(r.grad_input(Mv, H, F, w.dV16, p.fc2_w, a.pre16, 3, nullptr, nullptr, w.vF16));
             B2_TRY(r.grad_weight(Mv, F, H, w.vF16, F, a.u2_16, H, p.fc1_w, p.fc1_b));
             B2_TRY(r.grad_input(Mv, F, H, w.vF16, p.fc1_w, nullptr, 0, nullptr, w.v32a, nullptr));
             B2_TRY(launch_layernorm_bwd(w.v32a, a.x1, a.mean2, a.rstd2, r.p32(p.ln2_w), w.dV, nullptr, 0, w.v32b, w.v16a,

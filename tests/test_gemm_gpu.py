@@ -92,6 +92,60 @@ def test_gemm_epilogue_fwd(act):
     assert (pre.float() - z).abs().max().item() < 1e-4 + z.abs().max().item() * 2 ** -8
 
 
+@pytest.mark.parametrize("act", [1, 2])
+def test_gemm_saved_derivative_roundtrip(act):
+    """Model path: the forward epilogue saves act'(pre) (save_grad), the backward epilogue multiplies by it (dact=3)."""
+    from mkg_analogy_b200 import _lib
+    M, N, K = 3168, 3072, 768
+    A, B = _mk((M, K), 21), _mk((N, K), 22)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(23)).cuda()
+    y16 = torch.zeros((M, N), device="cuda", dtype=torch.bfloat16)
+    g16 = torch.zeros((M, N), device="cuda", dtype=torch.bfloat16)
+    _lib.gemm_bf16(A, B, bias=bias, act=act, out_preact=g16, save_grad=True, out_bf16=y16)
+    z = (A.float() @ B.float().t() + bias).requires_grad_(True)
+    y = torch.nn.functional.gelu(z) if act == 1 else z * torch.sigmoid(1.702 * z)
+    (gz,) = torch.autograd.grad(y.sum(), z)
+    assert (y16.float() - y.detach()).abs().max().item() < 2e-3 + y.abs().max().item() * 2 ** -8
+    assert (g16.float() - gz).abs().max().item() < 2e-3 + gz.abs().max().item() * 2 ** -8
+    dY, W = _mk((M, K), 24), _mk((K, N), 25)       # dX = (dY @ W) * act'(z), W stored [K][N]
+    d16 = torch.zeros((M, N), device="cuda", dtype=torch.bfloat16)
+    _lib.gemm_bf16(dY, W, b_mn=True, dact_src=g16, dact=3, out_bf16=d16)
+    torch.cuda.synchronize()
+    ref = (dY.float() @ W.float()) * g16.float()
+    assert (d16.float() - ref).abs().max().item() < 2e-3 + ref.abs().max().item() * 2 ** -7
+
+
+@pytest.mark.parametrize("kind", ["res", "f32", "acc", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(3168, 768, 768), (2048, 2304, 768), (100, 202, 192)])
+def test_gemm_specialised_epilogues(kind, M, N, K):
+    """Every fused epilogue kind on ragged and model-sized shapes, automatic N-tile choice."""
+    from mkg_analogy_b200 import _lib
+    A, B = _mk((M, K), 31), _mk((N, K), 32)
+    g = torch.Generator().manual_seed(33)
+    bias = torch.randn(N, generator=g).cuda()
+    ref = A.float() @ B.float().t()
+    if kind == "res":
+        res = torch.randn(M, N, generator=g).cuda()
+        out = torch.full((M, N), float("nan"), device="cuda")
+        o16 = torch.zeros((M, N), device="cuda", dtype=torch.bfloat16)
+        _lib.gemm_bf16(A, B, bias=bias, residual=res, out_f32=out, out_bf16=o16)
+        _check(out, ref + bias + res, K)
+        _check(o16, ref + bias + res, K, bf16_out=True)
+    elif kind == "f32":
+        out = torch.full((M, N), float("nan"), device="cuda")
+        _lib.gemm_bf16(A, B, bias=bias, out_f32=out)
+        _check(out, ref + bias, K)
+    elif kind == "acc":
+        out = torch.ones((M, N), device="cuda")
+        _lib.gemm_bf16(A, B, out_f32=out, accumulate=True, split_k=3)
+        _check(out, ref + 1.0, K)
+    else:
+        o16 = torch.zeros((M, N), device="cuda", dtype=torch.bfloat16)
+        _lib.gemm_bf16(A, B, bias=bias, out_bf16=o16)
+        _check(o16, ref + bias, K, bf16_out=True)
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("dact", [1, 2])
 def test_gemm_epilogue_dact(dact):
     from mkg_analogy_b200 import _lib

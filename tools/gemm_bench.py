@@ -30,7 +30,7 @@ def run(name, M, N, K, a_mn, b_mn, kind, split, bn, iters=20):
     if kind == "act":
         kw["act"] = 2; kw["out_preact"] = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     if kind == "dact":
-        kw["dact"] = 2; kw["dact_src"] = torch.randn(M, N, device="cuda").to(torch.bfloat16); kw.pop("bias")
+        kw["dact"] = 3; kw["dact_src"] = torch.randn(M, N, device="cuda").to(torch.bfloat16); kw.pop("bias")
     if kind in ("res", "f32", "acc"):
         kw["out_f32"] = torch.zeros(M, N, device="cuda")
     if kind == "res":
@@ -55,9 +55,9 @@ def run(name, M, N, K, a_mn, b_mn, kind, split, bn, iters=20):
 
 
 if __name__ == "__main__":
-    print(f"{'shape':12s} {'M':>5s} {'N':>5s} {'K':>5s}  " + "  ".join(f"bn={b:3d} us / TF" for b in (64, 128, 256)))
+    print(f"{'shape':12s} {'M':>5s} {'N':>5s} {'K':>5s}  " + "  ".join(f"bn={b:3d} us / TF" for b in (64, 128, 256, 0)))
     if "--few" in sys.argv:
         shapes = [s for s in shapes if s[0] in ("t.qkv fwd", "v.out fwd", "v.fc2 dX", "v.fc1 dW")]
     for sh in shapes:
-        res = [run(*sh, bn) for bn in (64, 128, 256)]
+        res = [run(*sh, bn) for bn in (64, 128, 256, 0)]
         print(f"{sh[0]:12s} {sh[1]:5d} {sh[2]:5d} {sh[3]:5d}  " + "  ".join(f"{us:8.1f} / {tf:5.0f}" for us, tf in res), flush=True)
