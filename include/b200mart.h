@@ -202,7 +202,7 @@ typedef struct b200mart_attn_desc {
     const int64_t* key_mask;     /* (B, n_keys) 1 = keep, NULL = no mask */
     const int64_t* sep_idx;      /* (B, 6) or NULL */
     const float* w0; const float* w1;
-    void* out; int64_t ldo;      /* bf16 context (B*Lq, heads*64) */
+    void* out; int64_t ldo;      /* bf16 context (B*Lq, heads*64): written by fwd, read by bwd (delta = rowsum(dO*O)) */
     float* out_f32;              /* optional fp32 copy, same layout */
     float* lse;                  /* (B, heads, Lq) */
     /* backward only */

@@ -1,0 +1,520 @@
+// Tensor-core fused attention (head_dim 64) for the MKGformer step, forward + two-pass backward.
+//   text   — BertSelfAttention.forward, MarT/models/modeling_unimo.py:317-377 (adaptive block scaling :342-349
+//            applied BEFORE the additive -1e4 padding mask :351-355)
+//   vision — CLIPAttention.forward :212-272 with the text K/V prefix (:227-229, unmasked)
+// One CTA (4 warps) per (head, sample).  Scores never leave the SM: each warp owns 16 query rows (forward, rows pass)
+// or 16 keys (keys pass) and streams the other side from shared memory in 64-wide chunks with an online softmax
+// (forward) or the saved log-sum-exp (backward).  The per-(sample, head) tiles are tiny (<= 99 x 163 x 64 at base
+// size), so the matrix products are warp-level mma.sync.m16n8k16 bf16 -> fp32 with ldmatrix fragments: a 128-row
+// tcgen05 tile would be >= 50 % padding for the 64-row text tiles and needs a CTA-wide TMEM round trip per product.
+// (The 97 % of the step's FLOPs that are large GEMMs run on tcgen05, gemm_kernel.cuh.)
+// Backward = rows pass (dQ, dW0/dW1, delta) + keys pass (dK, dV; fp32 for prefix keys), both recomputing P.
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int D = 64;
+constexpr int LDS = 72;         // padded smem row (bf16 elements): 144 B keeps ldmatrix rows on distinct banks
+constexpr int WARPS = 4;
+constexpr float NEG_BIG = -1.0e30f;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// rows [row0, row0+16) x 64 columns of a bf16 global matrix as mma A fragments (4 k-steps); rows >= nrows_total read 0
+__device__ __forceinline__ void load_a_bf16(const bf16* base, long ld, int row0, int nrows_total, int lane, uint32_t (&a)[4][4]) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {       // row g / g+8
+            const int row = row0 + g + 8 * h;
+            const bool ok = row < nrows_total;
+            const bf16* p = base + (long)row * ld + ks * 16 + 2 * t;
+            a[ks][h] = ok ? *reinterpret_cast<const uint32_t*>(p) : 0u;
+            a[ks][h + 2] = ok ? *reinterpret_cast<const uint32_t*>(p + 8) : 0u;
+        }
+    }
+}
+// same from an fp32 matrix (rounded to bf16); also returns the fp32 values' dot with a bf16 matrix `o` (for delta)
+__device__ __forceinline__ void load_a_f32(const float* base, long ld, int row0, int nrows_total, int lane, uint32_t (&a)[4][4],
+                                           const bf16* o, long ldo, float (&dot)[2]) {
+    const int g = lane >> 2, t = lane & 3;
+    dot[0] = dot[1] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = row0 + g + 8 * h;
+            const bool ok = row < nrows_total;
+            float2 v0 = make_float2(0.f, 0.f), v1 = v0;
+            if (ok) {
+                const float* p = base + (long)row * ld + ks * 16 + 2 * t;
+                v0 = *reinterpret_cast<const float2*>(p);
+                v1 = *reinterpret_cast<const float2*>(p + 8);
+                if (o) {
+                    const bf16* q = o + (long)row * ldo + ks * 16 + 2 * t;
+                    const float2 o0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q));
+                    const float2 o1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + 8));
+                    dot[h] += v0.x * o0.x + v0.y * o0.y + v1.x * o1.x + v1.y * o1.y;
+                }
+            }
+            a[ks][h] = pack_bf16x2(v0.x, v0.y);
+            a[ks][h + 2] = pack_bf16x2(v1.x, v1.y);
+        }
+    }
+}
+
+// cooperative copy of `rows` x 64 bf16 (global stride ld) into padded smem rows; rows [rows, rows_pad) are zeroed
+__device__ __forceinline__ void stage_bf16(bf16* dst, const bf16* src, long ld, int rows, int rows_pad, int tid, int nthreads) {
+    for (int i = tid; i < rows_pad * 8; i += nthreads) {
+        const int r = i >> 3, c = i & 7;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (r < rows) q = *reinterpret_cast<const uint4*>(src + (long)r * ld + c * 8);
+        *reinterpret_cast<uint4*>(dst + r * LDS + c * 8) = q;
+    }
+}
+__device__ __forceinline__ void stage_f32_as_bf16(bf16* dst, const float* src, long ld, int rows, int rows_pad, int tid, int nthreads) {
+    for (int i = tid; i < rows_pad * 16; i += nthreads) {
+        const int r = i >> 4, c = i & 15;
+        uint2 q = make_uint2(0, 0);
+        if (r < rows) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (long)r * ld + c * 4);
+            q = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        }
+        *reinterpret_cast<uint2*>(dst + r * LDS + c * 4) = q;
+    }
+}
+
+// C[16 x 64 keys] = A[16 x 64] * Bs[key][d]^T for the 64 "n" rows starting at n0 of a padded smem matrix (n x k row-major)
+__device__ __forceinline__ void mma_a_bt(float (&c)[8][4], const uint32_t (&a)[4][4], const bf16* Bs, int n0, int lane) {
+    const uint32_t base = smem_u32(Bs);
+    const int lr = lane & 7, sel = lane >> 3;          // ldmatrix address lanes: matrix sel = lane / 8
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {                  // pairs of 8-wide n tiles
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t b[4];
+            const int row = n0 + np * 16 + (sel >> 1) * 8 + lr;
+            const int col = ks * 16 + (sel & 1) * 8;
+            ldsm_x4(base + (uint32_t)(row * LDS + col) * 2u, b);
+            mma16816(c[2 * np], a[ks], b[0], b[1]);
+            mma16816(c[2 * np + 1], a[ks], b[2], b[3]);
+        }
+    }
+}
+// C[16 x 64 d] += P[16 x 64 k] * Bs[k][d]  (k x n row-major smem rows k0..k0+63), P given as packed A fragments
+__device__ __forceinline__ void mma_p_b(float (&c)[8][4], const uint32_t (&pa)[4][4], const bf16* Bs, int k0, int lane) {
+    const uint32_t base = smem_u32(Bs);
+    const int lr = lane & 7, sel = lane >> 3;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            uint32_t b[4];
+            const int row = k0 + ks * 16 + (sel & 1) * 8 + lr;
+            const int col = np * 16 + (sel >> 1) * 8;
+            ldsm_x4_t(base + (uint32_t)(row * LDS + col) * 2u, b);
+            mma16816(c[2 * np], pa[ks], b[0], b[1]);
+            mma16816(c[2 * np + 1], pa[ks], b[2], b[3]);
+        }
+    }
+}
+// accumulator tiles (16 x 64) -> packed bf16 A fragments (4 k-steps of 16)
+__device__ __forceinline__ void acc_to_a(const float (&c)[8][4], uint32_t (&a)[4][4]) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        a[ks][0] = pack_bf16x2(c[2 * ks][0], c[2 * ks][1]);
+        a[ks][1] = pack_bf16x2(c[2 * ks][2], c[2 * ks][3]);
+        a[ks][2] = pack_bf16x2(c[2 * ks + 1][0], c[2 * ks + 1][1]);
+        a[ks][3] = pack_bf16x2(c[2 * ks + 1][2], c[2 * ks + 1][3]);
+    }
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    return v;
+}
+
+struct Adapt { int split; float w0c, w1c; };
+__device__ __forceinline__ Adapt load_adapt(const AttnFwd& a, int b) {
+    Adapt ad;
+    ad.split = -1; ad.w0c = ad.w1c = 1.f;
+    if (a.sep_idx) {
+        ad.split = (int)a.sep_idx[(long)b * 6 + 2];
+        ad.w0c = fminf(fmaxf(*a.w0, 0.f), 0.5f);
+        ad.w1c = fminf(fmaxf(*a.w1, 0.5f), 1.0f);
+    }
+    return ad;
+}
+// factor of score (query row r, own-key index j2 = key - n1); prefix keys (j2 < 0) are never scaled
+__device__ __forceinline__ float afactor(const Adapt& ad, int r, int j2) {
+    if (ad.split < 0 || j2 < ad.split) return 1.0f;
+    return (r < ad.split) ? ad.w0c : ad.w1c;
+}
+
+// shared: K/V staging of all keys (prefix first) + additive mask per key (NEG_BIG for padding keys >= n)
+__device__ __forceinline__ void stage_keys(const AttnFwd& a, int b, int h, bf16* Ks, bf16* Vs, float* madd, int n_pad, int tid) {
+    const int n1 = a.n1, n2 = a.n2, n = n1 + n2;
+    if (n1 > 0) {
+        stage_bf16(Ks, a.k1 + (long)b * n1 * a.ld1 + h * D, a.ld1, n1, n1, tid, WARPS * 32);
+        stage_bf16(Vs, a.v1 + (long)b * n1 * a.ld1 + h * D, a.ld1, n1, n1, tid, WARPS * 32);
+    }
+    stage_bf16(Ks + n1 * LDS, a.k2 + (long)b * n2 * a.ld2 + h * D, a.ld2, n2, n_pad - n1, tid, WARPS * 32);
+    stage_bf16(Vs + n1 * LDS, a.v2 + (long)b * n2 * a.ld2 + h * D, a.ld2, n2, n_pad - n1, tid, WARPS * 32);
+    for (int j = tid; j < n_pad; j += WARPS * 32) {
+        float m = 0.f;
+        if (j >= n) m = NEG_BIG;
+        else if (a.key_mask && j >= n1) m = (1.0f - (float)a.key_mask[(long)b * n2 + (j - n1)]) * -10000.0f;
+        madd[j] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(WARPS * 32)
+attn_fwd_mma(const AttnFwd a, float* __restrict__ out32) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int n1 = a.n1, n = a.n1 + a.n2, n_pad = (n + 63) & ~63;
+    bf16* Ks = reinterpret_cast<bf16*>(smem);
+    bf16* Vs = Ks + (size_t)n_pad * LDS;
+    float* madd = reinterpret_cast<float*>(Vs + (size_t)n_pad * LDS);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    stage_keys(a, b, h, Ks, Vs, madd, n_pad, tid);
+    const Adapt ad = load_adapt(a, b);
+    __syncthreads();
+
+    const bf16* qbase = a.q + (long)b * a.Lq * a.ldq + h * D;
+    for (int r0 = warp * 16; r0 < a.Lq; r0 += WARPS * 16) {
+        uint32_t qa[4][4];
+        load_a_bf16(qbase, a.ldq, r0, a.Lq, lane, qa);
+        float o[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+        float mrun[2] = {NEG_BIG, NEG_BIG}, lrun[2] = {0.f, 0.f};
+        for (int kc = 0; kc < n_pad; kc += 64) {
+            float s[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+            mma_a_bt(s, qa, Ks, kc, lane);
+            float mx[2] = {NEG_BIG, NEG_BIG};
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = kc + nt * 8 + 2 * t + (e & 1);
+                    const int row = r0 + g + 8 * (e >> 1);
+                    const float v = s[nt][e] * a.scale * afactor(ad, row, col - n1) + madd[col];
+                    s[nt][e] = v;
+                    mx[e >> 1] = fmaxf(mx[e >> 1], v);
+                }
+            }
+            float alpha[2];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const float mnew = fmaxf(mrun[hh], quad_max(mx[hh]));
+                alpha[hh] = __expf(mrun[hh] - mnew);
+                mrun[hh] = mnew;
+                lrun[hh] *= alpha[hh];
+            }
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float p = __expf(s[nt][e] - mrun[e >> 1]);
+                    s[nt][e] = p;
+                    lrun[e >> 1] += p;
+                }
+                o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0]; o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
+            }
+            uint32_t pa[4][4];
+            acc_to_a(s, pa);
+            mma_p_b(o, pa, Vs, kc, lane);
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int row = r0 + g + 8 * hh;
+            const float l = quad_sum(lrun[hh]);
+            const float inv = 1.0f / l;
+            if (row < a.Lq) {
+                if (t == 0 && a.lse) a.lse[((long)b * a.nh + h) * a.Lq + row] = mrun[hh] + __logf(l);
+                const long off = ((long)b * a.Lq + row) * a.ldo + h * D;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const float x0 = o[nt][2 * hh] * inv, x1 = o[nt][2 * hh + 1] * inv;
+                    *reinterpret_cast<uint32_t*>(a.out + off + nt * 8 + 2 * t) = pack_bf16x2(x0, x1);
+                    if (out32) *reinterpret_cast<float2*>(out32 + off + nt * 8 + 2 * t) = make_float2(x0, x1);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ backward, rows pass
+// per 16 query rows: delta = rowsum(dO * O); over key chunks: P, dP = dO V^T, dS = P (dP - delta); dQ += (dS f) K;
+// dW0/dW1 partial sums of dS * S_raw over the scaled blocks.
+__global__ void __launch_bounds__(WARPS * 32)
+attn_bwd_rows_mma(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx, float* __restrict__ delta) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const AttnFwd& a = gr.f;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int n1 = a.n1, n = a.n1 + a.n2, n_pad = (n + 63) & ~63;
+    bf16* Ks = reinterpret_cast<bf16*>(smem);
+    bf16* Vs = Ks + (size_t)n_pad * LDS;
+    float* madd = reinterpret_cast<float*>(Vs + (size_t)n_pad * LDS);
+    __shared__ float wred[2][WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    stage_keys(a, b, h, Ks, Vs, madd, n_pad, tid);
+    const Adapt ad = load_adapt(a, b);
+    __syncthreads();
+
+    const bf16* qbase = a.q + (long)b * a.Lq * a.ldq + h * D;
+    const float* dobase = gr.dout + (long)b * a.Lq * gr.lddo + h * D;
+    const bf16* obase = ctx + (long)b * a.Lq * ldctx + h * D;
+    float dw0 = 0.f, dw1 = 0.f;
+    for (int r0 = warp * 16; r0 < a.Lq; r0 += WARPS * 16) {
+        uint32_t qa[4][4], doa[4][4];
+        float dl[2];
+        load_a_bf16(qbase, a.ldq, r0, a.Lq, lane, qa);
+        load_a_f32(dobase, gr.lddo, r0, a.Lq, lane, doa, obase, ldctx, dl);
+        float lse[2];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            dl[hh] = quad_sum(dl[hh]);
+            const int row = r0 + g + 8 * hh;
+            lse[hh] = (row < a.Lq) ? a.lse[((long)b * a.nh + h) * a.Lq + row] : 0.f;
+            if (t == 0 && row < a.Lq) delta[((long)b * a.nh + h) * a.Lq + row] = dl[hh];
+        }
+        float dq[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+        for (int kc = 0; kc < n_pad; kc += 64) {
+            float s[8][4], dp[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+                dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+            }
+            mma_a_bt(s, qa, Ks, kc, lane);
+            mma_a_bt(dp, doa, Vs, kc, lane);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = kc + nt * 8 + 2 * t + (e & 1);
+                    const int row = r0 + g + 8 * (e >> 1);
+                    const int j2 = col - n1;
+                    const float f = afactor(ad, row, j2);
+                    const float sraw = s[nt][e] * a.scale;
+                    const float p = (row < a.Lq) ? __expf(sraw * f + madd[col] - lse[e >> 1]) : 0.f;
+                    const float ds = p * (dp[nt][e] - dl[e >> 1]);
+                    if (ad.split >= 0 && j2 >= ad.split && col < n) {
+                        if (row < ad.split) dw0 = fmaf(ds, sraw, dw0); else dw1 = fmaf(ds, sraw, dw1);
+                    }
+                    s[nt][e] = ds * f;
+                }
+            }
+            uint32_t da[4][4];
+            acc_to_a(s, da);
+            mma_p_b(dq, da, Ks, kc, lane);
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int row = r0 + g + 8 * hh;
+            if (row < a.Lq) {
+                const long off = ((long)b * a.Lq + row) * gr.ldd + h * D;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+                    *reinterpret_cast<uint32_t*>(gr.dq + off + nt * 8 + 2 * t) =
+                        pack_bf16x2(dq[nt][2 * hh] * a.scale, dq[nt][2 * hh + 1] * a.scale);
+            }
+        }
+    }
+    if (a.sep_idx) {
+        dw0 = warp_sum(dw0);
+        dw1 = warp_sum(dw1);
+        if (lane == 0) { wred[0][warp] = dw0; wred[1][warp] = dw1; }
+        __syncthreads();
+        if (tid == 0) {
+            float s0 = 0.f, s1 = 0.f;
+            for (int w = 0; w < WARPS; ++w) { s0 += wred[0][w]; s1 += wred[1][w]; }
+            // torch.clamp passes the gradient at both (inclusive) bounds
+            const float w0 = *a.w0, w1 = *a.w1;
+            if (w0 >= 0.f && w0 <= 0.5f) atomicAdd(gr.dw0, s0);
+            if (w1 >= 0.5f && w1 <= 1.0f) atomicAdd(gr.dw1, s1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ backward, keys pass
+// per 16 keys: over query-row chunks: S^T = K Q^T, dP^T = V dO^T, P^T, dS^T; dV += P^T dO; dK += (dS^T f) Q.
+__global__ void __launch_bounds__(WARPS * 32)
+attn_bwd_keys_mma(const AttnBwd gr, const float* __restrict__ delta) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const AttnFwd& a = gr.f;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int n1 = a.n1, n2 = a.n2, n = n1 + n2, Lq = a.Lq, Lq_pad = (Lq + 63) & ~63;
+    bf16* Qs = reinterpret_cast<bf16*>(smem);
+    bf16* Os = Qs + (size_t)Lq_pad * LDS;
+    float* lse_s = reinterpret_cast<float*>(Os + (size_t)Lq_pad * LDS);
+    float* dl_s = lse_s + Lq_pad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    stage_bf16(Qs, a.q + (long)b * Lq * a.ldq + h * D, a.ldq, Lq, Lq_pad, tid, WARPS * 32);
+    stage_f32_as_bf16(Os, gr.dout + (long)b * Lq * gr.lddo + h * D, gr.lddo, Lq, Lq_pad, tid, WARPS * 32);
+    for (int r = tid; r < Lq_pad; r += WARPS * 32) {
+        lse_s[r] = (r < Lq) ? a.lse[((long)b * a.nh + h) * Lq + r] : 0.f;
+        dl_s[r] = (r < Lq) ? delta[((long)b * a.nh + h) * Lq + r] : 0.f;
+    }
+    const Adapt ad = load_adapt(a, b);
+    __syncthreads();
+
+    for (int j0 = warp * 16; j0 < n; j0 += WARPS * 16) {
+        // this block's 16 keys may straddle the prefix / own boundary: fragments are gathered row by row
+        uint32_t ka[4][4], va[4][4];
+        float madd[2];
+        int j2v[2];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int j = j0 + g + 8 * hh;
+            const bool ok = j < n, prefix = j < n1;
+            const bf16* kr = prefix ? a.k1 + ((long)b * n1 + j) * a.ld1 + h * D : a.k2 + ((long)b * n2 + (j - n1)) * a.ld2 + h * D;
+            const bf16* vr = prefix ? a.v1 + ((long)b * n1 + j) * a.ld1 + h * D : a.v2 + ((long)b * n2 + (j - n1)) * a.ld2 + h * D;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                ka[ks][hh] = ok ? *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 2 * t) : 0u;
+                ka[ks][hh + 2] = ok ? *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 2 * t + 8) : 0u;
+                va[ks][hh] = ok ? *reinterpret_cast<const uint32_t*>(vr + ks * 16 + 2 * t) : 0u;
+                va[ks][hh + 2] = ok ? *reinterpret_cast<const uint32_t*>(vr + ks * 16 + 2 * t + 8) : 0u;
+            }
+            j2v[hh] = j - n1;
+            madd[hh] = 0.f;
+            if (!ok) madd[hh] = NEG_BIG;
+            else if (a.key_mask && !prefix) madd[hh] = (1.0f - (float)a.key_mask[(long)b * n2 + (j - n1)]) * -10000.0f;
+        }
+        float dk[8][4], dv[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+            dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+        }
+        for (int rc = 0; rc < Lq_pad; rc += 64) {
+            float st[8][4], dpt[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+                dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+            }
+            mma_a_bt(st, ka, Qs, rc, lane);
+            mma_a_bt(dpt, va, Os, rc, lane);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int r = rc + nt * 8 + 2 * t + (e & 1);      // query row (column of the transposed tile)
+                    const int hh = e >> 1;                            // key row g / g+8
+                    const float f = afactor(ad, r, j2v[hh]);
+                    const float p = (r < Lq) ? __expf(st[nt][e] * a.scale * f + madd[hh] - lse_s[r]) : 0.f;
+                    const float ds = p * (dpt[nt][e] - dl_s[r]);
+                    dpt[nt][e] = p;           // P^T
+                    st[nt][e] = ds * f;       // dS^T * f
+                }
+            }
+            uint32_t pa[4][4], da[4][4];
+            acc_to_a(dpt, pa);
+            acc_to_a(st, da);
+            mma_p_b(dv, pa, Os, rc, lane);
+            mma_p_b(dk, da, Qs, rc, lane);
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int j = j0 + g + 8 * hh;
+            if (j >= n) continue;
+            if (j < n1) {
+                const long off = ((long)b * n1 + j) * gr.ldd1 + h * D;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    *reinterpret_cast<float2*>(gr.dk1 + off + nt * 8 + 2 * t) = make_float2(dk[nt][2 * hh] * a.scale, dk[nt][2 * hh + 1] * a.scale);
+                    *reinterpret_cast<float2*>(gr.dv1 + off + nt * 8 + 2 * t) = make_float2(dv[nt][2 * hh], dv[nt][2 * hh + 1]);
+                }
+            } else {
+                const long row = (long)b * n2 + (j - n1);
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    float k0 = dk[nt][2 * hh] * a.scale, k1 = dk[nt][2 * hh + 1] * a.scale;
+                    float v0 = dv[nt][2 * hh], v1 = dv[nt][2 * hh + 1];
+                    if (gr.dk2_add) {
+                        const float2 ak = *reinterpret_cast<const float2*>(gr.dk2_add + row * gr.ldadd + h * D + nt * 8 + 2 * t);
+                        const float2 av = *reinterpret_cast<const float2*>(gr.dv2_add + row * gr.ldadd + h * D + nt * 8 + 2 * t);
+                        k0 += ak.x; k1 += ak.y; v0 += av.x; v1 += av.y;
+                    }
+                    *reinterpret_cast<uint32_t*>(gr.dk2 + row * gr.ldd + h * D + nt * 8 + 2 * t) = pack_bf16x2(k0, k1);
+                    *reinterpret_cast<uint32_t*>(gr.dv2 + row * gr.ldd + h * D + nt * 8 + 2 * t) = pack_bf16x2(v0, v1);
+                }
+            }
+        }
+    }
+}
+
+int check_attn(const AttnFwd& a) {
+    B2_CHECK(a.B > 0 && a.Lq > 0 && a.nh > 0 && a.n2 > 0 && a.n1 >= 0, "attention: bad sizes B=%d Lq=%d nh=%d n1=%d n2=%d", a.B,
+             a.Lq, a.nh, a.n1, a.n2);
+    B2_CHECK(a.ldq % 8 == 0 && a.ld2 % 8 == 0 && (a.n1 == 0 || a.ld1 % 8 == 0) && a.ldo % 2 == 0,
+             "attention: leading dimensions must be multiples of 8 elements");
+    B2_CHECK(a.sep_idx == nullptr || (a.w0 && a.w1 && a.n1 == 0), "attention: adaptive scaling needs w0/w1 and no key prefix");
+    return 0;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    B2_CHECK(bytes <= 227 * 1024, "attention: needs %zu bytes of shared memory (> 227 KB)", bytes);
+    CUDA_TRY(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+}  // namespace
+
+int launch_attention_fwd(const AttnFwd& a, float* out32, cudaStream_t s) {
+    B2_TRY(check_attn(a));
+    B2_CHECK(a.out, "attention: output missing");
+    const int n_pad = (a.n1 + a.n2 + 63) & ~63;
+    const size_t smem = (size_t)2 * n_pad * LDS * 2 + (size_t)n_pad * 4;
+    B2_TRY(set_smem(attn_fwd_mma, smem));
+    attn_fwd_mma<<<dim3(a.nh, a.B), WARPS * 32, smem, s>>>(a, out32);
+    B2_LAUNCHED();
+    return 0;
+}
+
+int launch_attention_bwd(const AttnBwd& g, const bf16* ctx, long ldctx, float* delta, cudaStream_t s) {
+    const AttnFwd& a = g.f;
+    B2_TRY(check_attn(a));
+    B2_CHECK(g.dout && g.dq && g.dk2 && g.dv2 && delta && a.lse && ctx, "attention bwd: missing buffers");
+    B2_CHECK(a.n1 == 0 || (g.dk1 && g.dv1), "attention bwd: prefix gradients need dk1/dv1");
+    B2_CHECK(g.lddo % 4 == 0 && g.ldd % 2 == 0 && ldctx % 2 == 0, "attention bwd: bad leading dimensions");
+    const int n_pad = (a.n1 + a.n2 + 63) & ~63;
+    const size_t smem1 = (size_t)2 * n_pad * LDS * 2 + (size_t)n_pad * 4;
+    B2_TRY(set_smem(attn_bwd_rows_mma, smem1));
+    attn_bwd_rows_mma<<<dim3(a.nh, a.B), WARPS * 32, smem1, s>>>(g, ctx, ldctx, delta);
+    B2_LAUNCHED();
+    const int lq_pad = (a.Lq + 63) & ~63;
+    const size_t smem2 = (size_t)2 * lq_pad * LDS * 2 + (size_t)2 * lq_pad * 4;
+    B2_TRY(set_smem(attn_bwd_keys_mma, smem2));
+    attn_bwd_keys_mma<<<dim3(a.nh, a.B), WARPS * 32, smem2, s>>>(g, delta);
+    B2_LAUNCHED();
+    return 0;
+}

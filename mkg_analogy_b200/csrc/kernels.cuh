@@ -42,7 +42,7 @@ struct AdamSeg { long begin, end; int decay; int skip; };
 int launch_adamw(float* p, const float* g, float* m, float* v, bf16* p16, const AdamSeg* segs_dev, int nseg, long n,
                  float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, cudaStream_t s);
 
-// ---- attention.cu
+// ---- attention_mma.cu (self-attention) / attention.cu (fusion)
 struct AttnFwd {
     // Q rows: [B*Lq] rows of q (ldq), head h at column h*64. Keys: optional prefix source (n1 keys per sample) then own (n2).
     const bf16* q; long ldq;
@@ -66,8 +66,8 @@ struct AttnBwd {
     float* dk1; float* dv1; long ldd1;             // fp32 grads wrt the prefix keys/values (plain store), when n1 > 0
     float* dw0; float* dw1;       // adaptive-weight gradients (atomic accumulate), when sep_idx != null
 };
-// delta: scratch [B, nh, Lq] fp32
-int launch_attention_bwd(const AttnBwd& a, float* delta, cudaStream_t s);
+// ctx: the forward output (bf16, [B*Lq, nh*64], leading dimension ldctx); delta: scratch [B, nh, Lq] fp32
+int launch_attention_bwd(const AttnBwd& a, const bf16* ctx, long ldctx, float* delta, cudaStream_t s);
 // BertFusion (modeling_unimo.py:400-414): out = softmax(ctx vh^T) vh, no scale, no mask
 int launch_fusion_fwd(const float* ctx, const float* vh, bf16* out, float* lse, int B, int L, int Nv, int H,
                       cudaStream_t s);

@@ -731,7 +731,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             ab.dout = w.t32b; ab.lddo = H;
             ab.dq = w.tdqkv16; ab.dk2 = w.tdqkv16 + H; ab.dv2 = w.tdqkv16 + 2 * H; ab.ldd = 3 * H;
             if (i + 1 < D && i + 1 >= d.fuse_from) { ab.dk2_add = w.dk1; ab.dv2_add = w.dv1; ab.ldadd = H; }   // from vision layer i+1
-            { ProfScope ps(h, s, CAT_ATTN); B2_TRY(launch_attention_bwd(ab, w.delta, s)); }
+            { ProfScope ps(h, s, CAT_ATTN); B2_TRY(launch_attention_bwd(ab, a.ctx16, H, w.delta, s)); }
             B2_TRY(r.grad_weight(Mt, 3 * H, H, w.tdqkv16, 3 * H, w.T16[i], H, p.qkv_w, p.qkv_b));
             B2_TRY(r.grad_input(Mt, 3 * H, H, w.tdqkv16, p.qkv_w, nullptr, 0, w.t32a, w.dT, nullptr));  // d T^i
         }
@@ -757,7 +757,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             ab.dout = w.v32a; ab.lddo = H;
             ab.dq = w.vdqkv16; ab.dk2 = w.vdqkv16 + H; ab.dv2 = w.vdqkv16 + 2 * H; ab.ldd = 3 * H;
             if (fused) { ab.dk1 = w.dk1; ab.dv1 = w.dv1; ab.ldd1 = H; }
-            { ProfScope ps(h, s, CAT_ATTN); B2_TRY(launch_attention_bwd(ab, w.delta, s)); }
+            { ProfScope ps(h, s, CAT_ATTN); B2_TRY(launch_attention_bwd(ab, a.ctx16, H, w.delta, s)); }
             B2_TRY(r.grad_weight(Mv, 3 * H, H, w.vdqkv16, 3 * H, a.u16, H, p.qkv_w, p.qkv_b));
             B2_TRY(r.grad_input(Mv, 3 * H, H, w.vdqkv16, p.qkv_w, nullptr, 0, nullptr, w.v32a, nullptr));
             B2_TRY(launch_layernorm_bwd(w.v32a, w.V32[i], a.mean1, a.rstd1, r.p32(p.ln1_w), w.v32b, nullptr, 0, w.dV, w.dV16,
@@ -848,7 +848,8 @@ extern "C" int32_t b200mart_attention_bwd(const b200mart_attn_desc* d, void* str
     g.dk1 = d->dprefix_k; g.dv1 = d->dprefix_v; g.ldd1 = d->ldd_prefix;
     g.dw0 = d->dw0; g.dw1 = d->dw1;
     B2_CHECK(!a.sep_idx || (g.dw0 && g.dw1), "attention_bwd: adaptive scaling needs dw0 / dw1");
-    return launch_attention_bwd(g, d->delta, (cudaStream_t)stream);
+    B2_CHECK(d->out, "attention_bwd: the forward output (out) is needed");
+    return launch_attention_bwd(g, (const bf16*)d->out, d->ldo, d->delta, (cudaStream_t)stream);
 }
 
 extern "C" int32_t b200mart_fusion_fwd(const float* ctx, const float* vh, void* out_bf16, float* lse, int32_t B, int32_t L, int32_t Nv,

@@ -29,7 +29,7 @@ def attention_fwd(q, k, v, heads, scale, *, prefix_k=None, prefix_v=None, key_ma
     return out, out32, lse
 
 
-def attention_bwd(dout, q, k, v, lse, heads, scale, *, prefix_k=None, prefix_v=None, key_mask=None, sep_idx=None, w0=None,
+def attention_bwd(dout, out, q, k, v, lse, heads, scale, *, prefix_k=None, prefix_v=None, key_mask=None, sep_idx=None, w0=None,
                   w1=None, dk_add=None, dv_add=None):
     """Returns dq, dk, dv (bf16), dprefix_k, dprefix_v (fp32 or None), dw0, dw1 (fp32 scalars or None)."""
     B, Lq, HD = q.shape
@@ -46,6 +46,7 @@ def attention_bwd(dout, q, k, v, lse, heads, scale, *, prefix_k=None, prefix_v=N
         d.dprefix_k, d.dprefix_v, d.ldd_prefix = dpk.data_ptr(), dpv.data_ptr(), HD
     d.key_mask, d.sep_idx, d.w0, d.w1 = ptr(key_mask), ptr(sep_idx), ptr(w0), ptr(w1)
     d.lse = lse.data_ptr()
+    d.out, d.ldo = out.data_ptr(), HD      # forward context (bf16): delta = rowsum(dO * O)
     dout = dout.contiguous()
     d.dout, d.lddo = dout.data_ptr(), HD
     dq = torch.empty(B, Lq, HD, device=q.device, dtype=torch.bfloat16)

@@ -1,6 +1,7 @@
 """Kernel-level parity (through the C ABI) of the non-GEMM operators against fp32 torch restatements of the
 reference ops (file:line in each test).  Inputs are bf16-rounded where the kernel consumes bf16, so the only
-differences are accumulation order, fast-math exp and the bf16 rounding of bf16 outputs (2^-8 relative)."""
+differences are accumulation order, fast-math exp, the bf16 rounding of bf16 outputs (2^-8 relative) and, in the
+tensor-core attention, the bf16 rounding of the P / dS / dO operands of the second product (2^-9 relative each)."""
 import math
 
 import pytest
@@ -65,20 +66,23 @@ def test_text_attention_fwd_bwd(B, L, heads):
     out, out32, lse = ops.attention_fwd(q, k, v, heads, 0.125, key_mask=mask, sep_idx=sep, w0=w0.detach(), w1=w1.detach(), want_f32=True)
     qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
     ref, ref_lse = _ref_attention(qf, kf, vf, heads, 0.125, mask, sep, w0, w1)
-    assert rel(out32, ref) < 2e-5 * 50 and rel(out.float(), ref) < 6e-3
+    print('attn fwd rel', rel(out32, ref), rel(out.float(), ref))
+    assert rel(out32, ref) < 5e-3 and rel(out.float(), ref) < 7e-3
     assert (lse - ref_lse).abs().max().item() < 1e-3
     dout = _rand((B, L, HD), 3, 1.0, bf16=False)
     ref.backward(dout)
     dk_add = _rand((B, L, HD), 4, 0.1, bf16=False)
     dv_add = _rand((B, L, HD), 5, 0.1, bf16=False)
-    dq, dk, dv, _, _, dw0, dw1 = ops.attention_bwd(dout, q, k, v, lse, heads, 0.125, key_mask=mask, sep_idx=sep,
+    dq, dk, dv, _, _, dw0, dw1 = ops.attention_bwd(dout, out, q, k, v, lse, heads, 0.125, key_mask=mask, sep_idx=sep,
                                                    w0=w0.detach(), w1=w1.detach(), dk_add=dk_add, dv_add=dv_add)
     # the key pass rounds dO to bf16 -> ~2^-9 relative noise on dK/dV
-    assert rel(dq.float(), qf.grad) < 8e-3
-    assert rel(dk.float(), kf.grad + dk_add) < 8e-3
-    assert rel(dv.float(), vf.grad + dv_add) < 8e-3
-    assert abs(dw0.item() - w0.grad.item()) <= 2e-3 * abs(w0.grad.item()) + 1e-4
-    assert abs(dw1.item() - w1.grad.item()) <= 2e-3 * abs(w1.grad.item()) + 1e-4
+    print('attn bwd rel', rel(dq.float(), qf.grad), rel(dk.float(), kf.grad + dk_add), rel(dv.float(), vf.grad + dv_add),
+          dw0.item(), w0.grad.item(), dw1.item(), w1.grad.item())
+    assert rel(dq.float(), qf.grad) < 1.2e-2
+    assert rel(dk.float(), kf.grad + dk_add) < 1.2e-2
+    assert rel(dv.float(), vf.grad + dv_add) < 1.2e-2
+    assert abs(dw0.item() - w0.grad.item()) <= 2e-2 * abs(w0.grad.item()) + 1e-2
+    assert abs(dw1.item() - w1.grad.item()) <= 2e-2 * abs(w1.grad.item()) + 1e-2
 
 
 def test_adaptive_weight_clamp_blocks_gradient():
@@ -93,9 +97,9 @@ def test_adaptive_weight_clamp_blocks_gradient():
     mask = torch.ones(B, L, dtype=torch.long, device="cuda")
     w0 = torch.tensor([0.7], device="cuda")
     w1 = torch.tensor([0.8], device="cuda")
-    _, _, lse = ops.attention_fwd(q, k, v, heads, 0.125, key_mask=mask, sep_idx=sep, w0=w0, w1=w1)
+    out, _, lse = ops.attention_fwd(q, k, v, heads, 0.125, key_mask=mask, sep_idx=sep, w0=w0, w1=w1)
     dout = _rand((B, L, HD), 4, bf16=False)
-    *_, dw0, dw1 = ops.attention_bwd(dout, q, k, v, lse, heads, 0.125, key_mask=mask, sep_idx=sep, w0=w0, w1=w1)
+    *_, dw0, dw1 = ops.attention_bwd(dout, out, q, k, v, lse, heads, 0.125, key_mask=mask, sep_idx=sep, w0=w0, w1=w1)
     assert dw0.item() == 0.0 and dw1.item() != 0.0
 
 
@@ -111,12 +115,13 @@ def test_vision_attention_with_text_prefix(B, Nv, L, heads):
     out, _, lse = ops.attention_fwd(q, k, v, heads, 0.125, prefix_k=pk, prefix_v=pv)
     qf, kf, vf, pkf, pvf = (t.float().clone().requires_grad_(True) for t in (q, k, v, pk, pv))
     ref, _ = _ref_attention(qf, kf, vf, heads, 0.125, pk=pkf, pv=pvf)
-    assert rel(out.float(), ref) < 6e-3
+    assert rel(out.float(), ref) < 7e-3
     dout = _rand((B, Nv, HD), 13, bf16=False)
     ref.backward(dout)
-    dq, dk, dv, dpk, dpv, _, _ = ops.attention_bwd(dout, q, k, v, lse, heads, 0.125, prefix_k=pk, prefix_v=pv)
-    assert rel(dq.float(), qf.grad) < 8e-3 and rel(dk.float(), kf.grad) < 8e-3 and rel(dv.float(), vf.grad) < 8e-3
-    assert rel(dpk, pkf.grad) < 6e-3 and rel(dpv, pvf.grad) < 6e-3
+    dq, dk, dv, dpk, dpv, _, _ = ops.attention_bwd(dout, out, q, k, v, lse, heads, 0.125, prefix_k=pk, prefix_v=pv)
+    print('vis attn bwd rel', rel(dq.float(), qf.grad), rel(dk.float(), kf.grad), rel(dv.float(), vf.grad), rel(dpk, pkf.grad), rel(dpv, pvf.grad))
+    assert rel(dq.float(), qf.grad) < 1.2e-2 and rel(dk.float(), kf.grad) < 1.2e-2 and rel(dv.float(), vf.grad) < 1.2e-2
+    assert rel(dpk, pkf.grad) < 1.2e-2 and rel(dpv, pvf.grad) < 1.2e-2
 
 
 @pytest.mark.parametrize("B,L,Nv,H", [(2, 24, 9, 128), (3, 64, 99, 768), (2, 30, 513, 1024)])

@@ -26,7 +26,8 @@ print(f"{len(rows)} launches, {tot / 1000:.3f} ms total")
 detail = "--detail" in sys.argv
 agg = defaultdict(lambda: [0, 0.0])
 for k, (c, us) in by.items():
-    fam = re.sub(r"<.*", "", k.split(" grid=")[0]).split("::")[-1]
+    fam = re.sub(r"<unnamed>::|gemmk::", "", k.split(" grid=")[0])
+    fam = re.sub(r"<.*", "", fam).split("::")[-1]
     agg[fam][0] += c
     agg[fam][1] += us
 print("-- by kernel family")
