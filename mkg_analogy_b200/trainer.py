@@ -24,6 +24,37 @@ def linear_warmup_lr(step, total_steps, base_lr, warmup_ratio):
     return base_lr * max(0.0, (total_steps - step) / max(1.0, total_steps - warm))
 
 
+def bucket_bounds(n, buckets, align=1024):
+    """Contiguous [start, end) ranges covering a flat buffer of n elements in about `buckets` aligned pieces."""
+    per = (n + buckets - 1) // max(1, buckets)
+    per = max(align, (per + align - 1) // align * align)
+    return [(st, min(n, st + per)) for st in range(0, n, per)]
+
+
+def allreduce_mean_(flat, group=None, buckets=8):
+    """In-place mean over the data-parallel ranks of a flat gradient buffer, a few large buckets at a time
+    (equal-sized shards, so the mean of per-rank batch-mean gradients is the global-batch gradient).
+    NCCL averages in the collective itself; other backends (gloo in the CPU tests) sum, then scale."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return flat
+    avg = dist.get_backend(group) == "nccl"
+    for st, ed in bucket_bounds(flat.numel(), buckets):
+        piece = flat[st:ed]
+        if avg:
+            dist.all_reduce(piece, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=group)
+            piece.mul_(1.0 / world)
+    return flat
+
+
+def shard_seed(base_seed, rank, step=0):
+    """Seed of the synthetic shard a rank draws at a step: distinct across ranks and steps, reproducible."""
+    return base_seed + 100003 * rank + step
+
+
 def init_weights_(engine: Engine, seed=0):
     """Seeded synthetic weights generated on the device: N(0, 0.02) for matrices / embeddings / biases,
     LayerNorm (1, 0), class_embedding ~ N(0, 1), adaptive weights U(0, 0.5) and exactly 0.5 (modeling_unimo.py:305-310)."""
@@ -90,13 +121,7 @@ class MartTrainer:
         launch latency, not link count, is what matters on NVSwitch."""
         if self.world == 1:
             return
-        import torch.distributed as dist
-        g = self.engine.grads32
-        n = g.numel()
-        per = (n + self.grad_buckets - 1) // self.grad_buckets
-        per = (per + 1023) // 1024 * 1024
-        for st in range(0, n, per):
-            dist.all_reduce(g[st:min(n, st + per)], op=dist.ReduceOp.AVG, group=self.pg)
+        allreduce_mean_(self.engine.grads32, self.pg, self.grad_buckets)
 
     # ------------------------------------------------------------------ public API
     def train_step(self, batch):

@@ -260,7 +260,7 @@ def adamw_step(params, grads, state, step, lr, betas=(0.9, 0.999), eps=1e-8, wei
 
 def linear_warmup_lr(step, total_steps, base_lr, warmup_ratio=0.1):
     """get_linear_schedule_with_warmup as used at transformer.py:233-240 (stepped every batch)."""
-    warm = int(total_steps * warmup_ratio)
+    warm = total_steps * warmup_ratio        # the reference passes the float product (transformer.py:234)
     if step < warm:
-        return base_lr * step / max(1, warm)
-    return base_lr * max(0.0, (total_steps - step) / max(1, total_steps - warm))
+        return base_lr * float(step) / float(max(1, warm))
+    return base_lr * max(0.0, float(total_steps - step) / float(max(1, total_steps - warm)))

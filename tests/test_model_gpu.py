@@ -208,3 +208,51 @@ def test_compat_dense_logits_backward(tiny):
     ((lr * dlogits).sum() + (zr * dz).sum()).backward()
     bad = _compare_grads(eng, {k: v.grad for k, v in Pg.items()}, [])
     assert not bad, bad[:10]
+
+
+def test_dropin_module_with_torch_autograd_and_optimizer(tiny):
+    """The compat route the unchanged reference LitModel uses: `model(**batch, return_dict=True)` -> ([0].logits, [1]),
+    loss built with torch ops exactly as training_step does (transformer.py:92-109), `loss.backward()`, torch AdamW."""
+    g, cfg, params, _, batch = tiny
+    from mkg_analogy_b200.modeling import MKGformerKGC
+    from oracle import mkgformer_oracle as O
+    model = MKGformerKGC(cfg, device="cuda")
+    model.load_state_dict({**model.state_dict(), **{k: v for k, v in params.items()}})
+    inputs = {k: batch[k] for k in ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "sep_idx")}
+    out = model(**inputs, return_dict=True)
+    logits, z = out[0].logits, out[1]
+    B = logits.shape[0]
+    _, mpos = (batch["input_ids"] == 103).nonzero(as_tuple=True)
+    ids = torch.as_tensor(TINY_VOCAB.analogy_entity_ids(), device="cuda")
+    mask_logits = logits[torch.arange(B), mpos][:, ids]
+    loss = O.label_smooth_ce(mask_logits, batch["label"], 0.1) + 0.43 * O.relaxation_loss(z, batch["rel_idx"], batch["q_head_idx"],
+                                                                                      batch["a_head_idx"])
+    assert abs(loss.item() - g["ft_loss"].item()) <= 2e-2
+    loss.backward()
+    _, _, ref_grads = _oracle_grads(cfg, params, batch)
+    named = dict(model.named_parameters())
+    worst = 0.0
+    for name, gr in ref_grads.items():
+        if gr is None:
+            assert named[name].grad is None, f"{name}: the reference leaves .grad = None"
+            continue
+        if gr.double().norm().item() < 1e-9:
+            continue
+        e = rel(named[name].grad, gr)
+        if "adaptive_weight" not in name and "k_proj.bias" not in name:
+            worst = max(worst, e)
+    print(f"drop-in module: worst gradient rel err {worst:.3e}")
+    assert worst <= 6e-2
+    # a torch optimizer over named_parameters() updates the flat buffer in place; the next forward sees it
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3)
+    w_before = named["cls.predictions.transform.dense.weight"].detach().clone()
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    assert not torch.equal(w_before, named["cls.predictions.transform.dense.weight"])
+    with torch.no_grad():
+        out2 = model(**inputs, return_dict=True)
+    assert (out2[1] - z.detach()).abs().max().item() > 1e-4
+    # second backward after zero_grad(set_to_none): gradients are fresh, not accumulated
+    out3 = model(**inputs, return_dict=True)
+    (out3[1].sum() * 0.0 + out3[0].logits[0, 0, 0]).backward()
+    assert named["cls.predictions.bias"].grad.abs().sum().item() == pytest.approx(1.0, rel=1e-3)

@@ -55,3 +55,31 @@ def test_adamw_restatement_matches_torch():
         O.adamw_step(params, {n: grads[n] * step for n in names}, state, step, 5e-5)
     for n in names:
         assert torch.allclose(params[n], tp[n].detach(), atol=1e-7, rtol=1e-6), n
+
+
+def test_reference_litmodel_accepts_dropin_module():
+    """The UNMODIFIED reference TransformerLitModel (lit_models/transformer.py:18-57) constructs around the drop-in
+    module and runs its vocabulary surgery (`resize_token_embeddings`, `_init_relation_word` incl. its tie asserts);
+    the no-decay parameter grouping of configure_optimizers (:225-230) sees the reference's names.  CPU: storage only."""
+    from mkg_analogy_b200.config import TINY
+    from mkg_analogy_b200.modeling import MKGformerKGC
+    cfg = MKGformerConfig(**{**TINY.to_dict(), "vocab": TINY_VOCAB.vocab - 1})
+    model = MKGformerKGC(cfg, device="cpu")
+    lit = RL.build_reference_lit(model, TINY_VOCAB)
+    lit.tokenizer.n = TINY_VOCAB.vocab - 1           # before "[R]" is added
+    lit.analogy_relation_ids = TINY_VOCAB.analogy_relation_ids()
+    lit._init_relation_word()                        # resize to vocab, set E["[R]"] = mean of relation rows, assert tie
+    assert model.get_input_embeddings().weight.shape[0] == TINY_VOCAB.vocab
+    E = model.get_input_embeddings().weight
+    assert torch.allclose(E[TINY_VOCAB.vocab - 1], E[TINY_VOCAB.analogy_relation_ids()].mean(0))
+    ref_model = RL.build_reference_model(TINY)
+    assert set(dict(model.named_parameters())) == set(dict(ref_model.named_parameters()))
+    assert set(model.state_dict()) == set(ref_model.state_dict())
+    nd = ["bias", "LayerNorm.weight"]
+    mine = sorted(n for n, p in model.named_parameters() if p.requires_grad and any(x in n for x in nd))
+    ref = sorted(n for n, p in ref_model.named_parameters() if p.requires_grad and any(x in n for x in nd))
+    assert mine == ref
+    # reference checkpoints load (main.py:133-134): state_dict of the reference module -> drop-in module
+    model.load_state_dict(ref_model.state_dict())
+    assert torch.equal(model.state_dict()["unimo.encoder.text_layer.3.attention.self.query.weight"],
+                       ref_model.state_dict()["unimo.encoder.text_layer.3.attention.self.query.weight"])
