@@ -256,3 +256,33 @@ def test_dropin_module_with_torch_autograd_and_optimizer(tiny):
     out3 = model(**inputs, return_dict=True)
     (out3[1].sum() * 0.0 + out3[0].logits[0, 0, 0]).backward()
     assert named["cls.predictions.bias"].grad.abs().sum().item() == pytest.approx(1.0, rel=1e-3)
+
+
+def test_fused_litmodel_shim_matches_engine(tiny):
+    """mkg_analogy_b200.lit: training_step / _eval overrides on a stand-in base class with the reference's attributes."""
+    g, cfg, params, _, batch = tiny
+    from argparse import Namespace
+    from mkg_analogy_b200.lit import make_fused_litmodel
+    from mkg_analogy_b200.modeling import MKGformerKGC
+
+    class Base(torch.nn.Module):                      # the attributes TransformerLitModel.__init__ sets (:19-34)
+        def __init__(self, model, args, tokenizer, data_config):
+            super().__init__()
+            self.model, self.args, self.tokenizer, self.alpha = model, args, tokenizer, args.alpha
+            self.__dict__.update(data_config)
+
+    model = MKGformerKGC(cfg, device="cuda")
+    model.load_state_dict({**model.state_dict(), **params})
+    args = Namespace(pretrain=0, label_smoothing=0.1, alpha=0.43)
+    tok = Namespace(mask_token_id=103)
+    lit = make_fused_litmodel(Base)(model, args, tok, dict(analogy_entity_ids=TINY_VOCAB.analogy_entity_ids()))
+    loss = lit.training_step({k: v.clone() for k, v in batch.items()}, 1)
+    loss.backward()
+    assert abs(loss.item() - g["ft_loss"].item()) <= 2e-2
+    _, _, ref_grads = _oracle_grads(cfg, params, batch)
+    named = dict(model.named_parameters())
+    name = "unimo.encoder.text_layer.9.attention.self.query.weight"
+    assert rel(named[name].grad, ref_grads[name]) <= 6e-2
+    assert named["unimo.text_pooler.dense.weight"].grad is None
+    ranks = lit._eval({k: v.clone() for k, v in batch.items()}, 0)["entity_ranks"]
+    assert ranks.shape == (g["B"],) and (ranks >= 1).all()
