@@ -178,22 +178,24 @@ __global__ void text_embed_ln_kernel(const int64_t* __restrict__ ids, const int6
     ln_row<true>(v, nv, H, gamma, beta, eps, out32 + (long)row * H, out16 + (long)row * H, mean + row, rstd + row, lane);
 }
 
-// LayerNorm backward. Each warp walks rows r = warp_id, warp_id + nwarps, ...; dgamma/dbeta partials stay in
-// registers (same lane->column mapping for every row) and are reduced through shared memory + one atomic per
-// column per block.
-__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                                     const float* __restrict__ gamma, const float* __restrict__ add,
-                                     const bf16* __restrict__ dact_src, int dact, float* dx32, bf16* dx16, float* dgamma,
-                                     float* dbeta, int M, int H) {
-    extern __shared__ float red[];  // [warps][H] x 2
+// LayerNorm backward. Each warp walks rows r = warp_id, warp_id + nwarps, ...; dgamma/dbeta (and, optionally, the column
+// sums of the produced dx = bias gradient of the linear layer that fed this LayerNorm's input) stay in registers (same
+// lane->column mapping for every row) and are reduced through shared memory + one atomic per column per block.
+template <bool COLSUM>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ add,
+                     const bf16* __restrict__ dact_src, int dact, float* dx32, bf16* dx16, float* dgamma, float* dbeta,
+                     float* dxsum, int M, int H) {
+    extern __shared__ float red[];  // [warps][H] x (2 or 3)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int nv = H / 128;
-    float4 g[MAXV], ag[MAXV], ab[MAXV];
+    float4 g[MAXV], ag[MAXV], ab[MAXV], ac[COLSUM ? MAXV : 1];
 #pragma unroll
     for (int t = 0; t < MAXV; ++t) {
         ag[t] = make_float4(0, 0, 0, 0);
         ab[t] = make_float4(0, 0, 0, 0);
+        if (COLSUM) ac[t] = make_float4(0, 0, 0, 0);
         if (t < nv) g[t] = ld4(gamma + lane * 4 + t * 128);
     }
     for (int row = blockIdx.x * nw + warp; row < M; row += gridDim.x * nw) {
@@ -238,24 +240,31 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
                     float4 a = ld4(add + off);
                     o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
                 }
+                if (COLSUM) { ac[t].x += o.x; ac[t].y += o.y; ac[t].z += o.z; ac[t].w += o.w; }
                 if (dx32) st4(dx32 + off, o);
                 if (dx16) st4_bf16(dx16 + off, o);
             }
     }
     float* rg = red;
     float* rb = red + nw * H;
+    float* rc = red + 2 * nw * H;
 #pragma unroll
     for (int t = 0; t < MAXV; ++t)
         if (t < nv) {
             st4(rg + warp * H + lane * 4 + t * 128, ag[t]);
             st4(rb + warp * H + lane * 4 + t * 128, ab[t]);
+            if (COLSUM) st4(rc + warp * H + lane * 4 + t * 128, ac[t]);
         }
     __syncthreads();
     for (int c = threadIdx.x; c < H; c += blockDim.x) {
-        float sg = 0.f, sb = 0.f;
-        for (int w = 0; w < nw; ++w) { sg += rg[w * H + c]; sb += rb[w * H + c]; }
+        float sg = 0.f, sb = 0.f, sc = 0.f;
+        for (int w = 0; w < nw; ++w) {
+            sg += rg[w * H + c]; sb += rb[w * H + c];
+            if (COLSUM) sc += rc[w * H + c];
+        }
         atomicAdd(dgamma + c, sg);
         atomicAdd(dbeta + c, sb);
+        if (COLSUM) atomicAdd(dxsum + c, sc);
     }
 }
 
@@ -437,13 +446,21 @@ int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
 }
 int launch_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                          const float* add, const bf16* dact_src, int dact, float* dx32, bf16* dx16, float* dgamma,
-                         float* dbeta, int M, int H, cudaStream_t s) {
+                         float* dbeta, float* dxsum, int M, int H, cudaStream_t s) {
     B2_TRY(check_h(H));
-    const int nw = 4;
+    const int nw = 8;
     int blocks = (M + nw - 1) / nw;
-    if (blocks > 148 * 2) blocks = 148 * 2;
-    layernorm_bwd_kernel<<<blocks, nw * 32, 2 * nw * H * sizeof(float), s>>>(dy, x, mean, rstd, gamma, add, dact_src,
-                                                                            dact_src ? dact : 0, dx32, dx16, dgamma, dbeta, M, H);
+    if (blocks > 148) blocks = 148;   // one block per SM: per-column atomics stay at <= 148 per address
+    const size_t smem = (size_t)(dxsum ? 3 : 2) * nw * H * sizeof(float);
+    if (dxsum) {
+        CUDA_TRY(cudaFuncSetAttribute((const void*)layernorm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        layernorm_bwd_kernel<true><<<blocks, nw * 32, smem, s>>>(dy, x, mean, rstd, gamma, add, dact_src, dact_src ? dact : 0, dx32,
+                                                               dx16, dgamma, dbeta, dxsum, M, H);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute((const void*)layernorm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        layernorm_bwd_kernel<false><<<blocks, nw * 32, smem, s>>>(dy, x, mean, rstd, gamma, add, dact_src, dact_src ? dact : 0, dx32,
+                                                                dx16, dgamma, dbeta, nullptr, M, H);
+    }
     B2_LAUNCHED();
     return 0;
 }

@@ -28,6 +28,8 @@ struct GemmOp {
     const float* residual = nullptr; long ldr = 0;   // + residual[m,n] (fp32)
     float* out_f32 = nullptr; long ldo32 = 0;
     bf16* out_bf16 = nullptr; long ldo16 = 0;
+    float* colsum_out = nullptr;          // with dact = 3 and a bf16 output: += column sums of the output (fp32, atomic)
+    float* colsum_out2 = nullptr;
     int accumulate = 0;                   // out_f32 += value (atomic; required when split_k > 1)
     int split_k = 1;
     int bn = 0;                           // N tile (0 = auto: 128)

@@ -50,6 +50,7 @@ struct GemmDev {
     float* out_f32; long ldo32;
     bf16* out_bf16; long ldo16;
     int accumulate;
+    float* colsum_out; float* colsum_out2;   // EPI_DACT: += column sums of the output (bias gradient of the producing layer)
     int debug;   // B200MART_GEMM_DEBUG bitmask (bring-up only): 1 no epilogue global access, 2 no TMA, 4 no MMA
 };
 
@@ -113,7 +114,7 @@ template <int ACT> __device__ __forceinline__ void act_both(float x, float& y, f
 // ACT: compile-time activation (1 gelu-erf, 2 quick-gelu) for EPI_ACT / EPI_DACT.
 template <int EPI, int ACT>
 __device__ __forceinline__ void epilogue_row(const GemmDev& p, const float* stg, float2 rs, uint32_t xs, long row, int rr, int col,
-                                             float b0, float b1, int lane) {
+                                             float b0, float b1, int lane, float& cs0, float& cs1) {
     const float v0 = stg[rr * EPI_LD + 2 * lane] * p.alpha + b0;
     const float v1 = stg[rr * EPI_LD + 2 * lane + 1] * p.alpha + b1;
     if (EPI == EPI_BF16) {
@@ -133,7 +134,9 @@ __device__ __forceinline__ void epilogue_row(const GemmDev& p, const float* stg,
         *reinterpret_cast<float2*>(p.out_f32 + row * p.ldo32 + col) = make_float2(v0, v1);
     } else if (EPI == EPI_DACT) {
         const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs));
-        *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(v0 * x.x, v1 * x.y);
+        const float o0 = v0 * x.x, o1 = v1 * x.y;
+        cs0 += o0; cs1 += o1;
+        *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(o0, o1);
     } else if (EPI == EPI_ACC) {
         red_add_v2(p.out_f32 + row * p.ldo32 + col, v0, v1);
     }
@@ -144,17 +147,22 @@ __device__ __forceinline__ void epilogue_row(const GemmDev& p, const float* stg,
 template <int EPI, int ACT>
 __device__ __forceinline__ void epilogue_rows(const GemmDev& p, const float* stg, const EpiIn<EPI>& in, int row0, int nrows,
                                               int col, float b0, float b1, int lane) {
+    float cs0 = 0.f, cs1 = 0.f;
     if (EPI == EPI_RES || EPI == EPI_DACT) {
         // per-row register arrays -> compile-time indices (full unroll, predicated rows)
 #pragma unroll
         for (int rr = 0; rr < 32; ++rr)
             if (rr < nrows)
                 epilogue_row<EPI, ACT>(p, stg, in.rs[EpiIn<EPI>::kRes ? rr : 0], in.xs[EpiIn<EPI>::kDact ? rr : 0], row0 + rr, rr, col,
-                                       b0, b1, lane);
+                                       b0, b1, lane, cs0, cs1);
+        if (EPI == EPI_DACT) {
+            if (p.colsum_out) red_add_v2(p.colsum_out + col, cs0, cs1);
+            if (p.colsum_out2) red_add_v2(p.colsum_out2 + col, cs0, cs1);
+        }
     } else {
 #pragma unroll 2
         for (int rr = 0; rr < nrows; ++rr)
-            epilogue_row<EPI, ACT>(p, stg, make_float2(0.f, 0.f), 0u, row0 + rr, rr, col, b0, b1, lane);
+            epilogue_row<EPI, ACT>(p, stg, make_float2(0.f, 0.f), 0u, row0 + rr, rr, col, b0, b1, lane, cs0, cs1);
     }
 }
 

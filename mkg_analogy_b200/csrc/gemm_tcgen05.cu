@@ -70,6 +70,8 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
     B2_CHECK(op.M > 0 && op.N > 0 && op.K1 > 0, "gemm: bad shape M=%d N=%d K1=%d", op.M, op.N, op.K1);
     B2_CHECK(op.K2 == 0 || op.K1 % BK == 0, "gemm: K1=%d must be a multiple of %d when a second operand pair is used", op.K1, BK);
     B2_CHECK(op.split_k >= 1, "gemm: split_k must be >= 1");
+    B2_CHECK(!(op.colsum_out || op.colsum_out2) || (op.dact_src && op.dact == 3 && op.out_bf16 && op.N % 2 == 0 && op.ldx % 2 == 0 && op.ldo16 % 2 == 0),
+             "gemm: column sums are only produced by the saved-derivative (dact = 3) bf16 epilogue with even N / leading dimensions");
     B2_CHECK(op.split_k == 1 || (op.accumulate && op.out_f32 && !op.out_bf16 && !op.out_preact && !op.bias && !op.bias2 &&
                                  !op.residual && op.act == 0 && op.dact == 0),
              "gemm: split-K needs a pure fp32 accumulate epilogue");
@@ -139,6 +141,7 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
     d.residual = op.residual; d.ldr = op.ldr;
     d.out_f32 = op.out_f32; d.ldo32 = op.ldo32; d.out_bf16 = op.out_bf16; d.ldo16 = op.ldo16;
     d.accumulate = op.accumulate;
+    d.colsum_out = op.colsum_out; d.colsum_out2 = op.colsum_out2;
     { const char* e = getenv("B200MART_GEMM_DEBUG"); d.debug = e ? atoi(e) : 0; }
     int split = op.split_k;
     if (split > d.kb_total) split = d.kb_total;

@@ -20,10 +20,11 @@ int launch_text_embed_ln(const int64_t* ids, const int64_t* tt, const float* E, 
                          float* mean, float* rstd, int B, int L, int H, int V, int* status, cudaStream_t s);
 int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y32, bf16* y16,
                          float* mean, float* rstd, int M, int H, cudaStream_t s);
-// dx = LN'(dy) [* act'(dact_src)] [+ add];  dgamma += ..., dbeta += ...
+// dx = LN'(dy) [* act'(dact_src)] [+ add];  dgamma += ..., dbeta += ...; dxsum[c] += sum_rows dx[:, c] when given
+// (the bias gradient of the linear layer whose output this LayerNorm normalised)
 int launch_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                          const float* add, const bf16* dact_src, int dact, float* dx32, bf16* dx16, float* dgamma,
-                         float* dbeta, int M, int H, cudaStream_t s);
+                         float* dbeta, float* dxsum, int M, int H, cudaStream_t s);
 int launch_colsum_bf16(const bf16* x, long ld, float* out, int M, int N, cudaStream_t s);  // out[n] += sum_m x[m,n]
 int launch_colsum_f32(const float* x, long ld, float* out, int M, int N, cudaStream_t s);
 // text embedding backward: dE[ids] += d, dtype[tt] += d, dpos[l] += d  (d = gradient wrt the pre-LN sum)

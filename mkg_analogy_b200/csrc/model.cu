@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 #include "../../include/b200mart.h"
 
+#include <stdlib.h>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -71,7 +72,7 @@ struct Workspace {
     // backward scratch
     float *t32a, *t32b, *t32c, *dT; bf16 *t16a, *tF16, *tdqkv16;
     float *v32a, *v32b, *dV; bf16 *v16a, *dV16, *vF16, *vdqkv16;
-    float *dk1, *dv1; float *pbuf, *dsbuf; float* delta;
+    float *dk1, *dv1; float *pbuf, *dsbuf; float *delta, *delta_v;   // delta: text chain, delta_v: vision chain
     bf16* dpatch16;
     size_t bytes = 0;
 };
@@ -91,6 +92,12 @@ struct b200mart_handle {
     int nseg = 0;
     // cached workspace carving
     Workspace ws; void* ws_base = nullptr;
+    // two-chain execution: the vision and text streams of the model are independent below the fusion depth
+    // (modeling_unimo.py:616-640), so each runs on its own CUDA stream, ordered by events where they meet
+    bool split_streams = true;
+    cudaStream_t sV = nullptr, sT = nullptr;
+    std::vector<cudaEvent_t> evpool;
+    size_t ev_used = 0;
     // optional per-category device timing (CUDA events around each launch group; see b200mart_profile_begin/end)
     bool profiling = false;
     struct ProfRec { cudaEvent_t e0, e1; int cat; };
@@ -101,6 +108,9 @@ struct b200mart_handle {
         for (auto& kv : plans) gemm_plan_destroy(kv.second);
         for (auto* p : segs_dev) if (p) cudaFree(p);
         for (auto& r : prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+        for (auto& e : evpool) cudaEventDestroy(e);
+        if (sV) cudaStreamDestroy(sV);
+        if (sT) cudaStreamDestroy(sT);
     }
 };
 
@@ -268,7 +278,8 @@ void carve(const b200mart_handle* h, int B, int L, void* base, Workspace& w) {
     w.v16a = c.take<bf16>(Mv * H); w.dV16 = c.take<bf16>(Mv * H); w.vF16 = c.take<bf16>(Mv * F); w.vdqkv16 = c.take<bf16>(Mv * 3 * H);
     w.dk1 = c.take<float>(Mt * H); w.dv1 = c.take<float>(Mt * H);
     w.pbuf = c.take<float>(Mt * Nv); w.dsbuf = c.take<float>(Mt * Nv);
-    w.delta = c.take<float>((size_t)B * nh * (Nv > (size_t)L ? Nv : (size_t)L));
+    w.delta = c.take<float>((size_t)B * nh * L);
+    w.delta_v = c.take<float>((size_t)B * nh * Nv);
     w.dpatch16 = c.take<bf16>((size_t)B * 2 * P * H);
     w.bytes = c.off + 256;
 }
@@ -296,7 +307,8 @@ int run_gemm(b200mart_handle* h, const GemmOp& op, cudaStream_t s) {
     key[k++] = (long)op.bias; key[k++] = (long)op.bias2; key[k++] = (long)op.out_preact; key[k++] = op.ldp; key[k++] = op.act;
     key[k++] = (long)op.dact_src; key[k++] = op.ldx; key[k++] = op.dact; key[k++] = (long)op.residual; key[k++] = op.ldr;
     key[k++] = (long)op.out_f32; key[k++] = op.ldo32; key[k++] = (long)op.out_bf16; key[k++] = op.ldo16;
-    key[k++] = op.accumulate; key[k++] = op.split_k; key[k++] = op.bn;
+    key[k++] = op.accumulate; key[k++] = op.split_k; key[k++] = op.bn; key[k++] = op.save_grad;
+    key[k++] = (long)op.colsum_out; key[k++] = (long)op.colsum_out2;
     std::string ks(reinterpret_cast<const char*>(key), k * sizeof(long));
     auto it = h->plans.find(ks);
     GemmPlan* plan = nullptr;
@@ -349,11 +361,13 @@ struct Run {
     }
     // dX = dY W  [* act'(dact_src)] [+ residual].  dY (M, N) bf16, W (N, K) -> B operand stored [K=N][N=K] (MN-major)
     int grad_input(int M, int N, int K, const bf16* dY, long w_off, const bf16* dact_src, int dact, const float* residual,
-                   float* out32, bf16* out16) {
+                   float* out32, bf16* out16, long colsum_off = -1, long colsum_off2 = -1) {
         GemmOp op;
         op.M = M; op.N = K; op.K1 = N;
         op.A = dY; op.lda = N; op.B = p16(w_off); op.ldb = K; op.b_mn = 1;
         op.dact_src = dact_src; op.ldx = K; op.dact = dact;
+        if (colsum_off >= 0) op.colsum_out = g32(colsum_off);      // bias gradient of the layer that produced dact_src
+        if (colsum_off2 >= 0) op.colsum_out2 = g32(colsum_off2);
         op.residual = residual; op.ldr = K;
         op.out_f32 = out32; op.ldo32 = K; op.out_bf16 = out16; op.ldo16 = K;
         return run_gemm(h, op, s);
@@ -370,6 +384,50 @@ struct Run {
         return 0;
     }
 };
+
+// ------------------------------------------------------------------ two-chain stream plumbing
+struct Chains {
+    b200mart_handle* h; cudaStream_t main, v, t; bool split;
+    int rc = 0;
+    // event recorded on `on` (nullptr when the chains share one stream: ordering is implicit)
+    cudaEvent_t mark(cudaStream_t on) {
+        if (!split) return nullptr;
+        if (h->ev_used == h->evpool.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { rc = 3; return nullptr; }
+            h->evpool.push_back(e);
+        }
+        cudaEvent_t e = h->evpool[h->ev_used++];
+        if (cudaEventRecord(e, on) != cudaSuccess) rc = 3;
+        return e;
+    }
+    void wait(cudaStream_t who, cudaEvent_t e) {
+        if (split && e && cudaStreamWaitEvent(who, e, 0) != cudaSuccess) rc = 3;
+    }
+};
+
+int chains_begin(b200mart_handle* h, cudaStream_t s, Chains& c) {
+    c.h = h; c.main = s; c.v = s; c.t = s; c.split = false;
+    h->ev_used = 0;
+    if (!h->split_streams) return 0;
+    if (!h->sV) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->sV, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->sT, cudaStreamNonBlocking));
+    }
+    c.v = h->sV; c.t = h->sT; c.split = true;
+    cudaEvent_t e = c.mark(s);
+    c.wait(c.v, e);
+    c.wait(c.t, e);
+    return c.rc ? b200mart_set_err(3, "stream fork failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
+}
+
+int chains_end(Chains& c) {
+    if (c.split) {
+        c.wait(c.main, c.mark(c.v));
+        c.wait(c.main, c.mark(c.t));
+    }
+    return c.rc ? b200mart_set_err(3, "stream join failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
+}
 
 int check_batch(const b200mart_handle* h, const b200mart_batch* b) {
     B2_CHECK(b && b->B > 0 && b->L > 0, "bad batch");
@@ -397,6 +455,7 @@ extern "C" int32_t b200mart_create(const b200mart_model_desc* desc, b200mart_han
     h->Nv = 1 + 2 * h->P;
     h->patch_dim = 3 * d.patch * d.patch;
     h->patch_ld = (int)align_up(h->patch_dim, 8);
+    { const char* e = getenv("B200MART_STREAMS"); if (e && atoi(e) == 0) h->split_streams = false; }
     build_layout(h);
     // AdamW segments (one per parameter, covering its padded extent)
     std::vector<AdamSeg> segs[2];
@@ -467,29 +526,33 @@ extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* 
     Workspace& w = h->ws;
     const ParamLayout& l = h->lay;
     cudaStream_t s = (cudaStream_t)stream;
-    Run r{h, bufs, s};
     CUDA_TRY(cudaMemsetAsync(w.status, 0, 8 * sizeof(int), s));
+    Chains ch;
+    B2_TRY(chains_begin(h, s, ch));
+    const cudaStream_t sv = ch.v, stx = ch.t;          // vision chain / text chain
+    Run rv{h, bufs, sv}, rt{h, bufs, stx};
+    std::vector<cudaEvent_t> ev_tqkv(D, nullptr), ev_vout(D, nullptr);
 
     // ---- vision embeddings: im2col -> patch GEMM -> (+cls, +pos) -> pre-LN     (modeling_unimo.py:119-132, :711)
-    B2_TRY(launch_im2col(batch->pixel_values, w.patches16, B, d.image_size, d.patch, h->patch_ld, s));
+    B2_TRY(launch_im2col(batch->pixel_values, w.patches16, B, d.image_size, d.patch, h->patch_ld, sv));
     {
-        const bf16* wp = r.p16(l.patch_w);
+        const bf16* wp = rv.p16(l.patch_w);
         if (h->patch_ld != h->patch_dim) {   // e.g. ViT-L/14: 588-element rows are not 16-byte multiples -> padded copy
-            B2_TRY(launch_cast_pad_bf16(r.p32(l.patch_w), h->patch_dim, w.wp16, h->patch_ld, H, h->patch_dim, s));
+            B2_TRY(launch_cast_pad_bf16(rv.p32(l.patch_w), h->patch_dim, w.wp16, h->patch_ld, H, h->patch_dim, sv));
             wp = w.wp16;
         }
         GemmOp op;
         op.M = B * 2 * P; op.N = H; op.K1 = h->patch_dim;
         op.A = w.patches16; op.lda = h->patch_ld; op.B = wp; op.ldb = h->patch_ld;
         op.out_f32 = w.patch_out; op.ldo32 = H;
-        B2_TRY(run_gemm(h, op, s));
+        B2_TRY(run_gemm(h, op, sv));
     }
-    B2_TRY(launch_vision_embed_ln(w.patch_out, r.p32(l.cls), r.p32(l.vpos), r.p32(l.preln_w), r.p32(l.preln_b), d.vision_eps,
-                                  w.vx0, w.V32[0], w.vmean0, w.vrstd0, B, P, H, s));
+    B2_TRY(launch_vision_embed_ln(w.patch_out, rv.p32(l.cls), rv.p32(l.vpos), rv.p32(l.preln_w), rv.p32(l.preln_b), d.vision_eps,
+                                  w.vx0, w.V32[0], w.vmean0, w.vrstd0, B, P, H, sv));
     // ---- text embeddings (:152-186)
-    B2_TRY(launch_text_embed_ln(batch->input_ids, batch->token_type_ids, r.p32(l.word), r.p32(l.tpos), r.p32(l.ttype),
-                                r.p32(l.eln_w), r.p32(l.eln_b), d.text_eps, w.tpre, w.T32[0], w.T16[0], w.emean, w.erstd, B, L,
-                                H, d.vocab, w.status, s));
+    B2_TRY(launch_text_embed_ln(batch->input_ids, batch->token_type_ids, rt.p32(l.word), rt.p32(l.tpos), rt.p32(l.ttype),
+                                rt.p32(l.eln_w), rt.p32(l.eln_b), d.text_eps, w.tpre, w.T32[0], w.T16[0], w.emean, w.erstd, B, L,
+                                H, d.vocab, w.status, stx));
 
     for (int i = 0; i < D; ++i) {
         const bool fused = i >= d.fuse_from;
@@ -497,8 +560,8 @@ extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* 
         {
             const VisLayerP& p = l.vis[i];
             VisLayerA& a = w.vl[i];
-            B2_TRY(launch_layernorm_fwd(w.V32[i], r.p32(p.ln1_w), r.p32(p.ln1_b), d.vision_eps, nullptr, a.u16, a.mean1, a.rstd1, Mv, H, s));
-            B2_TRY(r.linear(Mv, 3 * H, H, a.u16, p.qkv_w, p.qkv_b, 0, nullptr, nullptr, nullptr, a.qkv16));
+            B2_TRY(launch_layernorm_fwd(w.V32[i], rv.p32(p.ln1_w), rv.p32(p.ln1_b), d.vision_eps, nullptr, a.u16, a.mean1, a.rstd1, Mv, H, sv));
+            B2_TRY(rv.linear(Mv, 3 * H, H, a.u16, p.qkv_w, p.qkv_b, 0, nullptr, nullptr, nullptr, a.qkv16));
             AttnFwd at{};
             at.q = a.qkv16; at.ldq = 3 * H;
             if (fused) {   // K/V of text layer i-1 prepended (:227-229, :616)
@@ -507,49 +570,54 @@ extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* 
             at.k2 = a.qkv16 + H; at.v2 = a.qkv16 + 2 * H; at.ld2 = 3 * H; at.n2 = Nv;
             at.B = B; at.Lq = Nv; at.nh = nh; at.scale = 0.125f;
             at.out = a.ctx16; at.ldo = H; at.lse = a.lse;
-            { ProfScope ps(h, s, CAT_ATTN); B2_TRY(launch_attention_fwd(at, nullptr, s)); }
-            B2_TRY(r.linear(Mv, H, H, a.ctx16, p.o_w, p.o_b, 0, nullptr, w.V32[i], a.x1, nullptr));
-            B2_TRY(launch_layernorm_fwd(a.x1, r.p32(p.ln2_w), r.p32(p.ln2_b), d.vision_eps, nullptr, a.u2_16, a.mean2, a.rstd2, Mv, H, s));
-            B2_TRY(r.linear(Mv, F, H, a.u2_16, p.fc1_w, p.fc1_b, 2, a.pre16, nullptr, nullptr, a.h16));
-            B2_TRY(r.linear(Mv, H, F, a.h16, p.fc2_w, p.fc2_b, 0, nullptr, a.x1, w.V32[i + 1], nullptr));
+            if (fused) ch.wait(sv, ev_tqkv[i - 1]);     // needs K/V of text layer i-1
+            { ProfScope ps(h, sv, CAT_ATTN); B2_TRY(launch_attention_fwd(at, nullptr, sv)); }
+            B2_TRY(rv.linear(Mv, H, H, a.ctx16, p.o_w, p.o_b, 0, nullptr, w.V32[i], a.x1, nullptr));
+            B2_TRY(launch_layernorm_fwd(a.x1, rv.p32(p.ln2_w), rv.p32(p.ln2_b), d.vision_eps, nullptr, a.u2_16, a.mean2, a.rstd2, Mv, H, sv));
+            B2_TRY(rv.linear(Mv, F, H, a.u2_16, p.fc1_w, p.fc1_b, 2, a.pre16, nullptr, nullptr, a.h16));
+            B2_TRY(rv.linear(Mv, H, F, a.h16, p.fc2_w, p.fc2_b, 0, nullptr, a.x1, w.V32[i + 1], nullptr));
+            if (i + 1 >= d.fuse_from || i + 1 == D) ev_vout[i] = ch.mark(sv);
         }
         // ================= text layer i (BertLayer :540-577)
         {
             const TxtLayerP& p = l.txt[i];
             TxtLayerA& a = w.tl[i];
-            B2_TRY(r.linear(Mt, 3 * H, H, w.T16[i], p.qkv_w, p.qkv_b, 0, nullptr, nullptr, nullptr, a.qkv16));
+            B2_TRY(rt.linear(Mt, 3 * H, H, w.T16[i], p.qkv_w, p.qkv_b, 0, nullptr, nullptr, nullptr, a.qkv16));
+            if (i + 1 >= d.fuse_from && i + 1 < D) ev_tqkv[i] = ch.mark(stx);
             AttnFwd at{};
             at.q = a.qkv16; at.ldq = 3 * H;
             at.k2 = a.qkv16 + H; at.v2 = a.qkv16 + 2 * H; at.ld2 = 3 * H; at.n2 = L;
             at.B = B; at.Lq = L; at.nh = nh; at.scale = 0.125f;
             at.key_mask = batch->attention_mask;
-            if (batch->sep_idx) { at.sep_idx = batch->sep_idx; at.w0 = r.p32(p.aw0); at.w1 = r.p32(p.aw1); }
+            if (batch->sep_idx) { at.sep_idx = batch->sep_idx; at.w0 = rt.p32(p.aw0); at.w1 = rt.p32(p.aw1); }
             at.out = a.ctx16; at.ldo = H; at.lse = a.lse;
-            { ProfScope ps(h, s, CAT_ATTN); B2_TRY(launch_attention_fwd(at, fused ? a.ctx32 : nullptr, s)); }
+            { ProfScope ps(h, stx, CAT_ATTN); B2_TRY(launch_attention_fwd(at, fused ? a.ctx32 : nullptr, stx)); }
+            if (fused) ch.wait(stx, ev_vout[i]);       // needs the vision output of this layer index
             if (fused)   // BertFusion on the context with the vision output of THIS layer index (:373, :627)
-                { ProfScope ps(h, s, CAT_FUSION); B2_TRY(launch_fusion_fwd(a.ctx32, w.V32[i + 1], a.g16, a.flse, B, L, Nv, H, s)); }
-            B2_TRY(r.linear(Mt, H, H, a.ctx16, p.ao_w, p.ao_b, 0, nullptr, w.T32[i], a.apre, nullptr));
-            B2_TRY(launch_layernorm_fwd(a.apre, r.p32(p.aln_w), r.p32(p.aln_b), d.text_eps, a.a32, a.a16, a.amean, a.arstd, Mt, H, s));
+                { ProfScope ps(h, stx, CAT_FUSION); B2_TRY(launch_fusion_fwd(a.ctx32, w.V32[i + 1], a.g16, a.flse, B, L, Nv, H, stx)); }
+            B2_TRY(rt.linear(Mt, H, H, a.ctx16, p.ao_w, p.ao_b, 0, nullptr, w.T32[i], a.apre, nullptr));
+            B2_TRY(launch_layernorm_fwd(a.apre, rt.p32(p.aln_w), rt.p32(p.aln_b), d.text_eps, a.a32, a.a16, a.amean, a.arstd, Mt, H, stx));
             if (fused)
-                B2_TRY(r.linear(Mt, F, H, a.a16, p.i_w, p.i_b, 1, a.ipre16, nullptr, nullptr, a.i16, a.g16, p.f_w, p.f_b));
+                B2_TRY(rt.linear(Mt, F, H, a.a16, p.i_w, p.i_b, 1, a.ipre16, nullptr, nullptr, a.i16, a.g16, p.f_w, p.f_b));
             else
-                B2_TRY(r.linear(Mt, F, H, a.a16, p.i_w, p.i_b, 1, a.ipre16, nullptr, nullptr, a.i16));
-            B2_TRY(r.linear(Mt, H, F, a.i16, p.o_w, p.o_b, 0, nullptr, a.a32, a.opre, nullptr));
-            B2_TRY(launch_layernorm_fwd(a.opre, r.p32(p.oln_w), r.p32(p.oln_b), d.text_eps, w.T32[i + 1], w.T16[i + 1], a.omean, a.orstd, Mt, H, s));
+                B2_TRY(rt.linear(Mt, F, H, a.a16, p.i_w, p.i_b, 1, a.ipre16, nullptr, nullptr, a.i16));
+            B2_TRY(rt.linear(Mt, H, F, a.i16, p.o_w, p.o_b, 0, nullptr, a.a32, a.opre, nullptr));
+            B2_TRY(launch_layernorm_fwd(a.opre, rt.p32(p.oln_w), rt.p32(p.oln_b), d.text_eps, w.T32[i + 1], w.T16[i + 1], a.omean, a.orstd, Mt, H, stx));
         }
     }
     // ---- MLM head transform (:972-976): z = LN(gelu(T W^T + b)).  (text_pooler :748 is never consumed: skipped.)
-    B2_TRY(r.linear(Mt, H, H, w.T16[D], l.tr_w, l.tr_b, 1, w.hpre16, nullptr, w.hact, nullptr));
-    B2_TRY(launch_layernorm_fwd(w.hact, r.p32(l.trln_w), r.p32(l.trln_b), d.text_eps, w.z32, w.z16, w.hmean, w.hrstd, Mt, H, s));
-    if (z_out) CUDA_TRY(cudaMemcpyAsync(z_out, w.z32, sizeof(float) * Mt * H, cudaMemcpyDeviceToDevice, s));
+    B2_TRY(rt.linear(Mt, H, H, w.T16[D], l.tr_w, l.tr_b, 1, w.hpre16, nullptr, w.hact, nullptr));
+    B2_TRY(launch_layernorm_fwd(w.hact, rt.p32(l.trln_w), rt.p32(l.trln_b), d.text_eps, w.z32, w.z16, w.hmean, w.hrstd, Mt, H, stx));
+    if (z_out) CUDA_TRY(cudaMemcpyAsync(z_out, w.z32, sizeof(float) * Mt * H, cudaMemcpyDeviceToDevice, stx));
     if (logits_out) {   // dense compat head: logits = z E^T + b over the whole vocabulary (:958)
         GemmOp op;
         op.M = Mt; op.N = d.vocab; op.K1 = H;
-        op.A = w.z16; op.lda = H; op.B = r.p16(l.word); op.ldb = H;
-        op.bias = r.p32(l.dec_b);
+        op.A = w.z16; op.lda = H; op.B = rt.p16(l.word); op.ldb = H;
+        op.bias = rt.p32(l.dec_b);
         op.out_f32 = logits_out; op.ldo32 = d.vocab;
-        B2_TRY(run_gemm(h, op, s));
+        B2_TRY(run_gemm(h, op, stx));
     }
+    B2_TRY(chains_end(ch));
     return 0;
 }
 
@@ -691,11 +759,17 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
     }
     // ---- head transform backward: z = LN(gelu(T W^T + b))
     B2_TRY(launch_layernorm_bwd(dz, w.hact, w.hmean, w.hrstd, r.p32(l.trln_w), nullptr, w.hpre16, 1, nullptr, w.t16a,
-                                r.g32(l.trln_w), r.g32(l.trln_b), Mt, H, s));
-    B2_TRY(r.grad_weight(Mt, H, H, w.t16a, H, w.T16[D], H, l.tr_w, l.tr_b));
+                                r.g32(l.trln_w), r.g32(l.trln_b), r.g32(l.tr_b), Mt, H, s));
+    B2_TRY(r.grad_weight(Mt, H, H, w.t16a, H, w.T16[D], H, l.tr_w, -1));
     B2_TRY(r.grad_input(Mt, H, H, w.t16a, l.tr_w, nullptr, 0, nullptr, w.dT, nullptr));
 
     const bool any_fusion = D > d.fuse_from;
+    // fork: text chain / vision chain (see b200mart_forward); events order the cross-stream gradient hand-offs
+    Chains ch;
+    B2_TRY(chains_begin(h, s, ch));
+    const cudaStream_t sv = ch.v, stx = ch.t;
+    Run rv{h, bufs, sv}, rt{h, bufs, stx};
+    std::vector<cudaEvent_t> ev_vdone(D + 1, nullptr), ev_tfus(D, nullptr), ev_tattn(D, nullptr);
     for (int i = D - 1; i >= 0; --i) {
         const bool fused = i >= d.fuse_from;
         // ================= text layer i backward
@@ -703,50 +777,58 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             const TxtLayerP& p = l.txt[i];
             TxtLayerA& a = w.tl[i];
             // output LayerNorm
-            B2_TRY(launch_layernorm_bwd(w.dT, a.opre, a.omean, a.orstd, r.p32(p.oln_w), nullptr, nullptr, 0, w.t32a, w.t16a,
-                                        r.g32(p.oln_w), r.g32(p.oln_b), Mt, H, s));
-            B2_TRY(r.grad_weight(Mt, H, F, w.t16a, H, a.i16, F, p.o_w, p.o_b));
-            B2_TRY(r.grad_input(Mt, H, F, w.t16a, p.o_w, a.ipre16, 3, nullptr, nullptr, w.tF16));     // d(pre-GELU)
-            B2_TRY(r.grad_weight(Mt, F, H, w.tF16, F, a.a16, H, p.i_w, p.i_b));
-            if (fused) B2_TRY(r.grad_weight(Mt, F, H, w.tF16, F, a.g16, H, p.f_w, p.f_b));
-            B2_TRY(r.grad_input(Mt, F, H, w.tF16, p.i_w, nullptr, 0, w.t32a, w.t32b, nullptr));        // d a32 (incl. residual)
-            if (fused) B2_TRY(r.grad_input(Mt, F, H, w.tF16, p.f_w, nullptr, 0, nullptr, w.t32c, nullptr));  // d fusion output
+            B2_TRY(launch_layernorm_bwd(w.dT, a.opre, a.omean, a.orstd, rt.p32(p.oln_w), nullptr, nullptr, 0, w.t32a, w.t16a,
+                                        rt.g32(p.oln_w), rt.g32(p.oln_b), rt.g32(p.o_b), Mt, H, stx));
+            B2_TRY(rt.grad_weight(Mt, H, F, w.t16a, H, a.i16, F, p.o_w, -1));
+            // d(pre-GELU) = (dY Wout) * gelu'(pre); its column sums are the intermediate (and fusion_dense) bias gradients
+            B2_TRY(rt.grad_input(Mt, H, F, w.t16a, p.o_w, a.ipre16, 3, nullptr, nullptr, w.tF16, p.i_b, fused ? p.f_b : -1));
+            B2_TRY(rt.grad_weight(Mt, F, H, w.tF16, F, a.a16, H, p.i_w, -1));
+            if (fused) B2_TRY(rt.grad_weight(Mt, F, H, w.tF16, F, a.g16, H, p.f_w, -1));
+            B2_TRY(rt.grad_input(Mt, F, H, w.tF16, p.i_w, nullptr, 0, w.t32a, w.t32b, nullptr));        // d a32 (incl. residual)
+            if (fused) B2_TRY(rt.grad_input(Mt, F, H, w.tF16, p.f_w, nullptr, 0, nullptr, w.t32c, nullptr));  // d fusion output
             // attention-output LayerNorm
-            B2_TRY(launch_layernorm_bwd(w.t32b, a.apre, a.amean, a.arstd, r.p32(p.aln_w), nullptr, nullptr, 0, w.t32a, w.t16a,
-                                        r.g32(p.aln_w), r.g32(p.aln_b), Mt, H, s));
-            B2_TRY(r.grad_weight(Mt, H, H, w.t16a, H, a.ctx16, H, p.ao_w, p.ao_b));
-            B2_TRY(r.grad_input(Mt, H, H, w.t16a, p.ao_w, nullptr, 0, nullptr, w.t32b, nullptr));      // d ctx
+            B2_TRY(launch_layernorm_bwd(w.t32b, a.apre, a.amean, a.arstd, rt.p32(p.aln_w), nullptr, nullptr, 0, w.t32a, w.t16a,
+                                        rt.g32(p.aln_w), rt.g32(p.aln_b), rt.g32(p.ao_b), Mt, H, stx));
+            B2_TRY(rt.grad_weight(Mt, H, H, w.t16a, H, a.ctx16, H, p.ao_w, -1));
+            B2_TRY(rt.grad_input(Mt, H, H, w.t16a, p.ao_w, nullptr, 0, nullptr, w.t32b, nullptr));      // d ctx
+            // dV (gradient wrt the vision output of layer i) and dk1/dv1 come from vision layer i+1's backward
+            if (i + 1 < D && i + 1 >= d.fuse_from - 0 && (fused || i + 1 >= d.fuse_from)) ch.wait(stx, ev_vdone[i + 1]);
             if (fused) {
-                { ProfScope ps(h, s, CAT_FUSION); B2_TRY(launch_fusion_bwd_rows(w.t32c, a.ctx32, w.V32[i + 1], a.flse, w.pbuf, w.dsbuf, w.t32b, B, L, Nv, H, s)); }
-                { ProfScope ps(h, s, CAT_FUSION); B2_TRY(launch_fusion_bwd_keys(w.t32c, a.ctx32, w.pbuf, w.dsbuf, (i == D - 1) ? nullptr : w.dV, w.dV, w.dV16, B, L, Nv, H, s)); }
+                { ProfScope ps(h, stx, CAT_FUSION); B2_TRY(launch_fusion_bwd_rows(w.t32c, a.ctx32, w.V32[i + 1], a.flse, w.pbuf, w.dsbuf, w.t32b, B, L, Nv, H, stx)); }
+                { ProfScope ps(h, stx, CAT_FUSION); B2_TRY(launch_fusion_bwd_keys(w.t32c, a.ctx32, w.pbuf, w.dsbuf, (i == D - 1) ? nullptr : w.dV, w.dV, w.dV16, B, L, Nv, H, stx)); }
             }
+            if (fused) ev_tfus[i] = ch.mark(stx);      // dV / dV16 now include this layer's fusion contribution
             AttnBwd ab{};
             AttnFwd& at = ab.f;
             at.q = a.qkv16; at.ldq = 3 * H;
             at.k2 = a.qkv16 + H; at.v2 = a.qkv16 + 2 * H; at.ld2 = 3 * H; at.n2 = L;
             at.B = B; at.Lq = L; at.nh = nh; at.scale = 0.125f;
             at.key_mask = batch->attention_mask;
-            if (batch->sep_idx) { at.sep_idx = batch->sep_idx; at.w0 = r.p32(p.aw0); at.w1 = r.p32(p.aw1); ab.dw0 = r.g32(p.aw0); ab.dw1 = r.g32(p.aw1); }
+            if (batch->sep_idx) { at.sep_idx = batch->sep_idx; at.w0 = rt.p32(p.aw0); at.w1 = rt.p32(p.aw1); ab.dw0 = rt.g32(p.aw0); ab.dw1 = rt.g32(p.aw1); }
             at.lse = a.lse;
             ab.dout = w.t32b; ab.lddo = H;
             ab.dq = w.tdqkv16; ab.dk2 = w.tdqkv16 + H; ab.dv2 = w.tdqkv16 + 2 * H; ab.ldd = 3 * H;
             if (i + 1 < D && i + 1 >= d.fuse_from) { ab.dk2_add = w.dk1; ab.dv2_add = w.dv1; ab.ldadd = H; }   // from vision layer i+1
-            { ProfScope ps(h, s, CAT_ATTN); B2_TRY(launch_attention_bwd(ab, a.ctx16, H, w.delta, s)); }
-            B2_TRY(r.grad_weight(Mt, 3 * H, H, w.tdqkv16, 3 * H, w.T16[i], H, p.qkv_w, p.qkv_b));
-            B2_TRY(r.grad_input(Mt, 3 * H, H, w.tdqkv16, p.qkv_w, nullptr, 0, w.t32a, w.dT, nullptr));  // d T^i
+            { ProfScope ps(h, stx, CAT_ATTN); B2_TRY(launch_attention_bwd(ab, a.ctx16, H, w.delta, stx)); }
+            if (ab.dk2_add) ev_tattn[i] = ch.mark(stx);   // dk1/dv1 consumed: vision layer i may overwrite them
+            B2_TRY(rt.grad_weight(Mt, 3 * H, H, w.tdqkv16, 3 * H, w.T16[i], H, p.qkv_w, p.qkv_b));
+            B2_TRY(rt.grad_input(Mt, 3 * H, H, w.tdqkv16, p.qkv_w, nullptr, 0, w.t32a, w.dT, nullptr));  // d T^i
         }
         // ================= vision layer i backward (only reached by gradient through the fusion / KV-prefix paths)
         if (any_fusion) {
             const VisLayerP& p = l.vis[i];
             VisLayerA& a = w.vl[i];
-            B2_TRY(r.grad_weight(Mv, H, F, w.dV16, H, a.h16, F, p.fc2_w, p.fc2_b));
-            B2_TRY(r.grad_input(Mv, H, F, w.dV16, p.fc2_w, a.pre16, 3, nullptr, nullptr, w.vF16));
-            B2_TRY(r.grad_weight(Mv, F, H, w.vF16, F, a.u2_16, H, p.fc1_w, p.fc1_b));
-            B2_TRY(r.grad_input(Mv, F, H, w.vF16, p.fc1_w, nullptr, 0, nullptr, w.v32a, nullptr));
-            B2_TRY(launch_layernorm_bwd(w.v32a, a.x1, a.mean2, a.rstd2, r.p32(p.ln2_w), w.dV, nullptr, 0, w.v32b, w.v16a,
-                                        r.g32(p.ln2_w), r.g32(p.ln2_b), Mv, H, s));
-            B2_TRY(r.grad_weight(Mv, H, H, w.v16a, H, a.ctx16, H, p.o_w, p.o_b));
-            B2_TRY(r.grad_input(Mv, H, H, w.v16a, p.o_w, nullptr, 0, nullptr, w.v32a, nullptr));
+            if (fused) ch.wait(sv, ev_tfus[i]);
+            // fc2 bias gradient = column sums of dV: fused into the LayerNorm-1 backward of layer i+1 when no text-layer
+            // fusion adds into dV afterwards (i < fuse_from), a column-sum pass otherwise
+            B2_TRY(rv.grad_weight(Mv, H, F, w.dV16, H, a.h16, F, p.fc2_w, fused ? p.fc2_b : -1));
+            B2_TRY(rv.grad_input(Mv, H, F, w.dV16, p.fc2_w, a.pre16, 3, nullptr, nullptr, w.vF16, p.fc1_b));
+            B2_TRY(rv.grad_weight(Mv, F, H, w.vF16, F, a.u2_16, H, p.fc1_w, -1));
+            B2_TRY(rv.grad_input(Mv, F, H, w.vF16, p.fc1_w, nullptr, 0, nullptr, w.v32a, nullptr));
+            B2_TRY(launch_layernorm_bwd(w.v32a, a.x1, a.mean2, a.rstd2, rv.p32(p.ln2_w), w.dV, nullptr, 0, w.v32b, w.v16a,
+                                        rv.g32(p.ln2_w), rv.g32(p.ln2_b), rv.g32(p.o_b), Mv, H, sv));
+            B2_TRY(rv.grad_weight(Mv, H, H, w.v16a, H, a.ctx16, H, p.o_w, -1));
+            B2_TRY(rv.grad_input(Mv, H, H, w.v16a, p.o_w, nullptr, 0, nullptr, w.v32a, nullptr));
             AttnBwd ab{};
             AttnFwd& at = ab.f;
             at.q = a.qkv16; at.ldq = 3 * H;
@@ -756,24 +838,27 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             at.lse = a.lse;
             ab.dout = w.v32a; ab.lddo = H;
             ab.dq = w.vdqkv16; ab.dk2 = w.vdqkv16 + H; ab.dv2 = w.vdqkv16 + 2 * H; ab.ldd = 3 * H;
-            if (fused) { ab.dk1 = w.dk1; ab.dv1 = w.dv1; ab.ldd1 = H; }
-            { ProfScope ps(h, s, CAT_ATTN); B2_TRY(launch_attention_bwd(ab, a.ctx16, H, w.delta, s)); }
-            B2_TRY(r.grad_weight(Mv, 3 * H, H, w.vdqkv16, 3 * H, a.u16, H, p.qkv_w, p.qkv_b));
-            B2_TRY(r.grad_input(Mv, 3 * H, H, w.vdqkv16, p.qkv_w, nullptr, 0, nullptr, w.v32a, nullptr));
-            B2_TRY(launch_layernorm_bwd(w.v32a, w.V32[i], a.mean1, a.rstd1, r.p32(p.ln1_w), w.v32b, nullptr, 0, w.dV, w.dV16,
-                                        r.g32(p.ln1_w), r.g32(p.ln1_b), Mv, H, s));
+            if (fused) { ab.dk1 = w.dk1; ab.dv1 = w.dv1; ab.ldd1 = H; ch.wait(sv, ev_tattn[i]); }
+            { ProfScope ps(h, sv, CAT_ATTN); B2_TRY(launch_attention_bwd(ab, a.ctx16, H, w.delta_v, sv)); }
+            B2_TRY(rv.grad_weight(Mv, 3 * H, H, w.vdqkv16, 3 * H, a.u16, H, p.qkv_w, p.qkv_b));
+            B2_TRY(rv.grad_input(Mv, 3 * H, H, w.vdqkv16, p.qkv_w, nullptr, 0, nullptr, w.v32a, nullptr));
+            B2_TRY(launch_layernorm_bwd(w.v32a, w.V32[i], a.mean1, a.rstd1, rv.p32(p.ln1_w), w.v32b, nullptr, 0, w.dV, w.dV16,
+                                        rv.g32(p.ln1_w), rv.g32(p.ln1_b),
+                                        (i >= 1 && i - 1 < d.fuse_from) ? rv.g32(l.vis[i - 1].fc2_b) : nullptr, Mv, H, sv));
+            ev_vdone[i] = ch.mark(sv);
         }
     }
     // ---- embeddings
-    B2_TRY(launch_layernorm_bwd(w.dT, w.tpre, w.emean, w.erstd, r.p32(l.eln_w), nullptr, nullptr, 0, w.t32a, nullptr,
-                                r.g32(l.eln_w), r.g32(l.eln_b), Mt, H, s));
-    B2_TRY(launch_text_embed_bwd(w.t32a, batch->input_ids, batch->token_type_ids, r.g32(l.word), r.g32(l.tpos), r.g32(l.ttype), B, L, H, s));
+    B2_TRY(launch_layernorm_bwd(w.dT, w.tpre, w.emean, w.erstd, rt.p32(l.eln_w), nullptr, nullptr, 0, w.t32a, nullptr,
+                                rt.g32(l.eln_w), rt.g32(l.eln_b), nullptr, Mt, H, stx));
+    B2_TRY(launch_text_embed_bwd(w.t32a, batch->input_ids, batch->token_type_ids, rt.g32(l.word), rt.g32(l.tpos), rt.g32(l.ttype), B, L, H, stx));
     if (any_fusion) {
-        B2_TRY(launch_layernorm_bwd(w.dV, w.vx0, w.vmean0, w.vrstd0, r.p32(l.preln_w), nullptr, nullptr, 0, w.v32a, nullptr,
-                                    r.g32(l.preln_w), r.g32(l.preln_b), Mv, H, s));
-        B2_TRY(launch_vision_embed_bwd(w.v32a, r.g32(l.cls), r.g32(l.vpos), w.dpatch16, B, P, H, s));
-        B2_TRY(r.grad_weight(B * 2 * P, H, h->patch_dim, w.dpatch16, H, w.patches16, h->patch_ld, l.patch_w, -1));
+        B2_TRY(launch_layernorm_bwd(w.dV, w.vx0, w.vmean0, w.vrstd0, rv.p32(l.preln_w), nullptr, nullptr, 0, w.v32a, nullptr,
+                                    rv.g32(l.preln_w), rv.g32(l.preln_b), nullptr, Mv, H, sv));
+        B2_TRY(launch_vision_embed_bwd(w.v32a, rv.g32(l.cls), rv.g32(l.vpos), w.dpatch16, B, P, H, sv));
+        B2_TRY(rv.grad_weight(B * 2 * P, H, h->patch_dim, w.dpatch16, H, w.patches16, h->patch_ld, l.patch_w, -1));
     }
+    B2_TRY(chains_end(ch));
     return 0;
 }
 
@@ -876,7 +961,7 @@ extern "C" int32_t b200mart_layernorm_bwd(const float* dy, const float* x, const
                                           const float* add, float* dx32, void* dx16, float* dgamma, float* dbeta, int32_t M, int32_t H,
                                           void* stream) {
     B2_CHECK(dy && x && mean && rstd && gamma && dgamma && dbeta, "layernorm_bwd: null argument");
-    return launch_layernorm_bwd(dy, x, mean, rstd, gamma, add, nullptr, 0, dx32, (bf16*)dx16, dgamma, dbeta, M, H, (cudaStream_t)stream);
+    return launch_layernorm_bwd(dy, x, mean, rstd, gamma, add, nullptr, 0, dx32, (bf16*)dx16, dgamma, dbeta, nullptr, M, H, (cudaStream_t)stream);
 }
 
 extern "C" int32_t b200mart_ls_ce(const float* logits, int32_t B, int32_t C, const int64_t* label, float eps, float* loss, float* dlogits,
