@@ -100,6 +100,11 @@ int32_t b200mart_param_count(const b200mart_handle* h);
 int64_t b200mart_param_total(const b200mart_handle* h);              /* elements of the flat buffers */
 int32_t b200mart_param_info(const b200mart_handle* h, int32_t index, const char** name, int64_t* offset,
                             int32_t* ndim, int64_t shape[4], int32_t* decay, int32_t* unused_in_finetune);
+/* Flat extent [begin, end) holding every parameter of layer index `layer` (vision layer + text layer): the unit of the
+ * overlapped data-parallel gradient exchange (see layer_events of b200mart_backward). */
+int32_t b200mart_layer_extent(const b200mart_handle* h, int32_t layer, int64_t* begin, int64_t* end);
+/* Runtime options: "streams" (default 1) runs the vision and text chains on two internal CUDA streams. */
+int32_t b200mart_set_option(b200mart_handle* h, const char* name, int32_t value);
 /* params16[i] = bf16(params32[i]) over the whole flat buffer */
 int32_t b200mart_cast_params(const b200mart_handle* h, const float* params32, void* params16, void* stream);
 
@@ -163,10 +168,13 @@ int32_t b200mart_head_loss(b200mart_handle* h, const b200mart_buffers* bufs, con
 /* Backward of b200mart_forward (what torch autograd does for the reference graph).  The gradient wrt
  * trans_hidden_states is the one left by b200mart_head_loss, plus dz_extra (B, L, hidden) fp32 when given
  * (use_head_grad = 0: dz_extra alone).  dlogits (B, L, vocab) fp32, when given, is the gradient of the dense
- * compat logits; dlogits_scratch must then hold B*L*roundup(vocab, 8) bf16.  Accumulates into grads32. */
+ * compat logits; dlogits_scratch must then hold B*L*roundup(vocab, 8) bf16.  Accumulates into grads32.
+ * layer_events: NULL, or 2*layers cudaEvent_t handles; events [2i] and [2i+1] are recorded (on the library's internal
+ * streams) when layer i's parameter gradients are final, so that the caller can start that layer's gradient all-reduce
+ * on another stream while the layers below are still running (what DDP's bucket hooks do for the reference). */
 int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers* bufs, const b200mart_batch* batch,
                           int32_t use_head_grad, const float* dz_extra, const float* dlogits, void* dlogits_scratch,
-                          void* stream);
+                          void* const* layer_events, void* stream);
 
 /* torch.optim.AdamW step as configured at transformer.py:224-241 over the flat buffers, refreshing the bf16
  * mirror.  `step` is 1-based.  Parameters the reference never gives a gradient (text_pooler, vision_post_layernorm,

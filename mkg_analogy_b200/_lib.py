@@ -98,7 +98,9 @@ SYMBOLS = {
     "b200mart_workspace_bytes": (i64, [vp, i32, i32]),
     "b200mart_forward": (i32, [vp, C.POINTER(Buffers), C.POINTER(Batch), vp, vp, vp]),
     "b200mart_head_loss": (i32, [vp, C.POINTER(Buffers), C.POINTER(Batch), C.POINTER(Head), vp, vp, vp, i32, vp]),
-    "b200mart_backward": (i32, [vp, C.POINTER(Buffers), C.POINTER(Batch), i32, vp, vp, vp, vp]),
+    "b200mart_backward": (i32, [vp, C.POINTER(Buffers), C.POINTER(Batch), i32, vp, vp, vp, C.POINTER(vp), vp]),
+    "b200mart_layer_extent": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i64)]),
+    "b200mart_set_option": (i32, [vp, C.c_char_p, i32]),
     "b200mart_adamw": (i32, [vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, i32, vp]),
     "b200mart_status": (i32, [vp, C.POINTER(Buffers), vp, C.POINTER(i32)]),
     "b200mart_attention_fwd": (i32, [C.POINTER(AttnDesc), vp]),

@@ -86,6 +86,7 @@ struct b200mart_handle {
     int P = 0, Nv = 0, patch_dim = 0, patch_ld = 0;   // patch_ld: patch_dim rounded up to 8 (16-byte bf16 rows for TMA)
     std::vector<PInfo> params;
     ParamLayout lay;
+    std::vector<long> layer_begin, layer_end;   // flat extent of layer i's parameters (vision + text)
     std::unordered_map<std::string, GemmPlan*> plans;
     AdamSeg* segs_dev[2] = {nullptr, nullptr};   // [0] fine-tune, [1] pre-train (uploaded on first use)
     std::vector<AdamSeg> segs_host[2];
@@ -168,7 +169,11 @@ void build_layout(b200mart_handle* h) {
     l.eln_w = add_param(h, "unimo.text_embeddings.LayerNorm.weight", {H});
     l.eln_b = add_param(h, "unimo.text_embeddings.LayerNorm.bias", {H});
     char buf[160];
+    // one contiguous extent per layer index (vision layer i, then text layer i): the gradient exchange of a layer
+    // can start as soon as that layer's backward has run on both chains
     for (int i = 0; i < d.layers; ++i) {
+        h->layer_begin.push_back(l.total);
+        {
         VisLayerP v;
         auto nm = [&](const char* s) { snprintf(buf, sizeof(buf), "unimo.encoder.vision_layers.%d.%s", i, s); return std::string(buf); };
         v.qkv_w = add_param(h, nm("self_attn.q_proj.weight"), {H, H});
@@ -188,8 +193,8 @@ void build_layout(b200mart_handle* h) {
         v.ln2_w = add_param(h, nm("layer_norm2.weight"), {H});
         v.ln2_b = add_param(h, nm("layer_norm2.bias"), {H});
         l.vis.push_back(v);
-    }
-    for (int i = 0; i < d.layers; ++i) {
+        }
+        {
         TxtLayerP t;
         auto nm = [&](const char* s) { snprintf(buf, sizeof(buf), "unimo.encoder.text_layer.%d.%s", i, s); return std::string(buf); };
         t.qkv_w = add_param(h, nm("attention.self.query.weight"), {H, H});
@@ -214,6 +219,8 @@ void build_layout(b200mart_handle* h) {
         t.oln_w = add_param(h, nm("output.LayerNorm.weight"), {H});
         t.oln_b = add_param(h, nm("output.LayerNorm.bias"), {H});
         l.txt.push_back(t);
+        }
+        h->layer_end.push_back(l.total);
     }
     l.pool_w = add_param(h, "unimo.text_pooler.dense.weight", {H, H});
     l.pool_b = add_param(h, "unimo.text_pooler.dense.bias", {H});
@@ -493,6 +500,19 @@ extern "C" int32_t b200mart_param_info(const b200mart_handle* h, int32_t i, cons
     return 0;
 }
 
+extern "C" int32_t b200mart_layer_extent(const b200mart_handle* h, int32_t layer, int64_t* begin, int64_t* end) {
+    B2_CHECK(h && begin && end && layer >= 0 && layer < (int)h->layer_begin.size(), "layer_extent: layer %d out of range", layer);
+    *begin = h->layer_begin[layer];
+    *end = h->layer_end[layer];
+    return 0;
+}
+
+extern "C" int32_t b200mart_set_option(b200mart_handle* h, const char* name, int32_t value) {
+    B2_CHECK(h && name, "set_option: null argument");
+    if (strcmp(name, "streams") == 0) { h->split_streams = value != 0; return 0; }
+    return b200mart_set_err(1, "set_option: unknown option '%s'", name);
+}
+
 extern "C" int32_t b200mart_cast_params(const b200mart_handle* h, const float* p32, void* p16, void* stream) {
     B2_CHECK(h && p32 && p16, "cast_params: null argument");
     return launch_cast_bf16(p32, reinterpret_cast<bf16*>(p16), h->lay.total, (cudaStream_t)stream);
@@ -719,7 +739,7 @@ extern "C" int32_t b200mart_head_loss(b200mart_handle* h, const b200mart_buffers
 // --------------------------------------------------------------------------------------- backward
 extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers* bufs, const b200mart_batch* batch,
                                      int32_t use_head_grad, const float* dz_extra, const float* dlogits, void* dlogits_scratch,
-                                     void* stream) {
+                                     void* const* layer_events, void* stream) {
     B2_CHECK(h && bufs && bufs->params32 && bufs->params16 && bufs->grads32, "backward: null handle / buffers");
     B2_TRY(check_batch(h, batch));
     B2_CHECK(h->ws_base == bufs->workspace && h->ws.B == batch->B && h->ws.L == batch->L, "backward: run forward on this batch first");
@@ -846,6 +866,10 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
                                         rv.g32(p.ln1_w), rv.g32(p.ln1_b),
                                         (i >= 1 && i - 1 < d.fuse_from) ? rv.g32(l.vis[i - 1].fc2_b) : nullptr, Mv, H, sv));
             ev_vdone[i] = ch.mark(sv);
+        }
+        if (layer_events) {   // layer i's gradients are final once both chains pass this point
+            CUDA_TRY(cudaEventRecord((cudaEvent_t)layer_events[2 * i], stx));
+            CUDA_TRY(cudaEventRecord((cudaEvent_t)layer_events[2 * i + 1], any_fusion ? sv : stx));
         }
     }
     // ---- embeddings

@@ -232,7 +232,20 @@ class Engine:
                                              _lib.ptr(ranks), int(compute_grad), _lib.cur_stream()))
         return loss, ml, ranks
 
-    def backward(self, batch, use_head_grad=True, dz=None, dlogits=None):
+    def layer_extents(self):
+        """[(begin, end)] flat extents of each layer index's parameters (vision + text layer)."""
+        out = []
+        for i in range(self.cfg.layers):
+            b, e = _lib.i64(), _lib.i64()
+            _lib.check(self.l.b200mart_layer_extent(self.h, i, C.byref(b), C.byref(e)))
+            out.append((b.value, e.value))
+        return out
+
+    def set_option(self, name, value):
+        _lib.check(self.l.b200mart_set_option(self.h, name.encode(), int(value)))
+
+    def backward(self, batch, use_head_grad=True, dz=None, dlogits=None, layer_events=None):
+        """layer_events: optional list of 2*layers torch.cuda.Event (already created by a record()); see b200mart.h."""
         cb = self._batch(batch)
         bufs = self._bufs(cb.B, cb.L)
         scratch = None
@@ -242,8 +255,12 @@ class Engine:
             dlogits = dlogits.contiguous()
         if dz is not None:
             dz = dz.contiguous()
+        evs = None
+        if layer_events is not None:
+            assert len(layer_events) == 2 * self.cfg.layers
+            evs = (_lib.vp * len(layer_events))(*[e.cuda_event for e in layer_events])
         _lib.check(self.l.b200mart_backward(self.h, C.byref(bufs), C.byref(cb), int(use_head_grad), _lib.ptr(dz),
-                                            _lib.ptr(dlogits), _lib.ptr(scratch), _lib.cur_stream()))
+                                            _lib.ptr(dlogits), _lib.ptr(scratch), evs, _lib.cur_stream()))
 
     def adamw(self, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, pretrain=False):
         self._need_cuda()

@@ -81,7 +81,7 @@ def init_weights_(engine: Engine, seed=0):
 class MartTrainer:
     def __init__(self, cfg: MKGformerConfig, vocab: VocabLayout, *, pretrain=False, lr=5e-5, weight_decay=0.01,
                  warmup_ratio=0.1, total_steps=1000, alpha=0.43, label_smoothing=0.1, device=None, process_group=None,
-                 grad_buckets=8):
+                 grad_buckets=8, overlap_comm=True):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.cfg, self.vocab, self.pretrain = cfg, vocab, bool(pretrain)
@@ -97,6 +97,15 @@ class MartTrainer:
             self.world = torch.distributed.get_world_size(process_group)
         self.grad_buckets = grad_buckets
         self._dev_batch = None
+        # overlapped exchange: per-layer "gradients final" events recorded by the library, all-reduces on a side stream
+        self.overlap_comm = bool(overlap_comm) and self.world > 1
+        self._comm_stream = self._layer_events = None
+        if self.overlap_comm:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+            self._layer_events = [torch.cuda.Event() for _ in range(2 * cfg.layers)]
+            for e in self._layer_events:
+                e.record()                       # materialise the CUDA event handles
+            self._extents = self.engine.layer_extents()
 
     # ------------------------------------------------------------------ pieces
     def _head(self, batch):
@@ -123,6 +132,29 @@ class MartTrainer:
             return
         allreduce_mean_(self.engine.grads32, self.pg, self.grad_buckets)
 
+    def _backward_overlapped(self, mb):
+        """Backward with the gradient exchange of layer i started as soon as layer i's backward has run on both chains
+        (layers are walked top-down, so the exchange of layers D-1..1 hides behind the backward of the layers below);
+        embeddings / head gradients, final only at the end, go last.  One NCCL mean all-reduce per layer extent
+        (about 66 MB at base size) on a side stream; the optimizer step waits for all of them."""
+        import torch.distributed as dist
+        eng, g = self.engine, self.engine.grads32
+        main, comm = torch.cuda.current_stream(), self._comm_stream
+        eng.backward(mb, layer_events=self._layer_events)
+        with torch.cuda.stream(comm):
+            for i in reversed(range(self.cfg.layers)):
+                comm.wait_event(self._layer_events[2 * i])
+                comm.wait_event(self._layer_events[2 * i + 1])
+                b, e = self._extents[i]
+                dist.all_reduce(g[b:e], op=dist.ReduceOp.AVG, group=self.pg)
+            comm.wait_stream(main)               # the whole backward (embeddings included) is ordered before this point
+            lo, hi = self._extents[0][0], self._extents[-1][1]
+            if lo > 0:
+                dist.all_reduce(g[:lo], op=dist.ReduceOp.AVG, group=self.pg)
+            if hi < g.numel():
+                dist.all_reduce(g[hi:], op=dist.ReduceOp.AVG, group=self.pg)
+        main.wait_stream(comm)
+
     # ------------------------------------------------------------------ public API
     def train_step(self, batch):
         """One optimizer step on a device-resident batch. Returns the loss as a device tensor (1,)."""
@@ -131,8 +163,11 @@ class MartTrainer:
         eng.zero_grad()
         eng.forward(mb, want_z=False)
         loss, _, _ = eng.head_loss(mb, self._head(batch), compute_grad=True)
-        eng.backward(mb)
-        self.allreduce_grads()
+        if self.overlap_comm:
+            self._backward_overlapped(mb)
+        else:
+            eng.backward(mb)
+            self.allreduce_grads()
         lr = linear_warmup_lr(self.steps_done, self.total_steps, self.lr, self.warmup_ratio)
         self.steps_done += 1
         eng.adamw(self.steps_done, lr, weight_decay=self.weight_decay, pretrain=self.pretrain)

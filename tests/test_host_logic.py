@@ -190,3 +190,30 @@ def test_data_parallel_mean_of_shards_is_global_gradient_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err <= 1e-5 * scale + 1e-7, (err, scale)
+
+
+def test_layer_extents_partition_the_encoder():
+    """b200mart_layer_extent: contiguous, ordered, disjoint; exactly the encoder-layer parameters fall inside."""
+    import ctypes as C
+    from mkg_analogy_b200 import _lib
+    from mkg_analogy_b200.config import BASE
+    from mkg_analogy_b200.engine import _model_desc, _read_layout
+    l = _lib.lib()
+    h = _lib.vp()
+    d = _model_desc(BASE)
+    _lib.check(l.b200mart_create(C.byref(d), C.byref(h)))
+    infos, total = _read_layout(l, h)
+    ext = []
+    for i in range(BASE.layers):
+        b, e = _lib.i64(), _lib.i64()
+        _lib.check(l.b200mart_layer_extent(h, i, C.byref(b), C.byref(e)))
+        ext.append((b.value, e.value))
+    l.b200mart_destroy(h)
+    assert all(ext[i][1] == ext[i + 1][0] for i in range(len(ext) - 1)) and 0 < ext[0][0] and ext[-1][1] < total
+    for p in infos:
+        inside = [i for i, (b, e) in enumerate(ext) if b <= p.offset < e]
+        if ".encoder." in p.name:
+            layer = int(p.name.split(".")[3])
+            assert inside == [layer], p.name
+        else:
+            assert inside == [], p.name
