@@ -6,7 +6,8 @@
 One "step" = one optimizer step on one 32-example synthetic MARS-shaped batch per GPU (224x224 image pair, 64 text
 tokens, 2,063-entity score head over the 42,007-token vocabulary): forward, label-smoothed CE + relaxation loss on the
 [MASK] rows, backward, (N>1: NCCL all-reduce of the flat fp32 gradient buffer), AdamW.  Arithmetic: bf16 tensor-core
-operands, fp32 accumulation / residual streams / LayerNorm / softmax / loss / master weights; dropout p = 0.
+operands, fp32 accumulation / residual streams / LayerNorm / softmax / loss / master weights; training-mode dropout
+(p = 0.1 at the four BERT-stream sites) on.
 
 Prints ONE JSON line (rank 0): value = whole-job examples/s with inputs resident in HBM (CUDA events, max over ranks);
 e2e = the same step through MartTrainer.train_step_host with pinned host inputs (H2D + loss D2H inside the timed region);
@@ -39,7 +40,7 @@ def config_dict(n_gpus):
             "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * n_gpus, "seq_len": SEQ_LEN, "image": "2x3x224x224",
             "score_head": "2063 analogy entities of a 42007-token vocab", "params_M": 234.7,
             "parallelism": f"dp{n_gpus}" + ("" if n_gpus == 1 else " (flat fp32 gradient mean all-reduce per layer extent, overlapped with backward)"),
-            "dropout": 0.0,
+            "dropout": "hidden 0.1 / attention 0.1 (BERT stream, as the reference trains)",
             "l2": "per-step working set (0.47 GB bf16 weights + >1 GB activations) exceeds the 126 MB L2; 4 rotating batches"}
 
 

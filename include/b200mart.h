@@ -103,8 +103,15 @@ int32_t b200mart_param_info(const b200mart_handle* h, int32_t index, const char*
 /* Flat extent [begin, end) holding every parameter of layer index `layer` (vision layer + text layer): the unit of the
  * overlapped data-parallel gradient exchange (see layer_events of b200mart_backward). */
 int32_t b200mart_layer_extent(const b200mart_handle* h, int32_t layer, int64_t* begin, int64_t* end);
-/* Runtime options: "streams" (default 1) runs the vision and text chains on two internal CUDA streams. */
+/* Runtime options: "streams" (default 1) runs the vision and text chains on two internal CUDA streams;
+ * "training" (default 0) enables dropout in b200mart_forward (nn.Module.train()/eval() of the reference). */
 int32_t b200mart_set_option(b200mart_handle* h, const char* name, int32_t value);
+/* Dropout of the BERT stream (modeling_unimo.py:185 embeddings, :362 attention probabilities, :389 / :476 sub-layer
+ * outputs; the CLIP stream has none): hidden_dropout_prob, attention_probs_dropout_prob (reference: 0.1 / 0.1) and a seed.
+ * Masks are a stateless function of (seed, forward-call counter, site, element index): backward regenerates them. */
+int32_t b200mart_set_dropout(b200mart_handle* h, float p_hidden, float p_attn, uint32_t seed);
+/* per-forward seed of the most recent b200mart_forward (tests rebuild the masks from it) */
+uint32_t b200mart_last_dropout_seed(const b200mart_handle* h);
 /* params16[i] = bf16(params32[i]) over the whole flat buffer */
 int32_t b200mart_cast_params(const b200mart_handle* h, const float* params32, void* params16, void* stream);
 
@@ -130,7 +137,7 @@ typedef struct b200mart_batch {
     const int64_t* sep_idx;         /* (B, 6) or NULL: no adaptive scaling (pre-training) */
 } b200mart_batch;
 
-/* UnimoForMaskedLM.forward (modeling_unimo.py:848-893) in eval-mode arithmetic (dropout p = 0).
+/* UnimoForMaskedLM.forward (modeling_unimo.py:848-893); dropout only with the "training" option (see above).
  *   z_out      (B, L, hidden) fp32: trans_hidden_states = model_output[1]              (may be NULL)
  *   logits_out (B, L, vocab)  fp32: model_output[0].logits, the dense "compat" head    (may be NULL)
  * Activations needed by b200mart_backward stay in the workspace until the next forward. */

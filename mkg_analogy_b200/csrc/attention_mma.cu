@@ -237,9 +237,14 @@ attn_fwd_mma(const AttnFwd a, float* __restrict__ out32) {
             for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float p = __expf(s[nt][e] - mrun[e >> 1]);
-                    s[nt][e] = p;
+                    float p = __expf(s[nt][e] - mrun[e >> 1]);
                     lrun[e >> 1] += p;
+                    if (a.drop.thresh) {   // dropout on the normalised probabilities (:362): the row sum stays undropped
+                        const int col = kc + nt * 8 + 2 * t + (e & 1);
+                        const int row = r0 + g + 8 * (e >> 1);
+                        p *= drop_mult(a.drop, (uint32_t)((((long)b * a.nh + h) * a.Lq + row) * n + col));
+                    }
+                    s[nt][e] = p;
                 }
                 o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0]; o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
             }
@@ -323,7 +328,9 @@ attn_bwd_rows_mma(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx, fl
                     const float f = afactor(ad, row, j2);
                     const float sraw = s[nt][e] * a.scale;
                     const float p = (row < a.Lq) ? __expf(sraw * f + madd[col] - lse[e >> 1]) : 0.f;
-                    const float ds = p * (dp[nt][e] - dl[e >> 1]);
+                    float dpe = dp[nt][e];
+                    if (a.drop.thresh) dpe *= drop_mult(a.drop, (uint32_t)((((long)b * a.nh + h) * a.Lq + row) * n + col));
+                    const float ds = p * (dpe - dl[e >> 1]);
                     if (ad.split >= 0 && j2 >= ad.split && col < n) {
                         if (row < ad.split) dw0 = fmaf(ds, sraw, dw0); else dw1 = fmaf(ds, sraw, dw1);
                     }
@@ -430,8 +437,11 @@ attn_bwd_keys_mma(const AttnBwd gr, const float* __restrict__ delta) {
                     const int hh = e >> 1;                            // key row g / g+8
                     const float f = afactor(ad, r, j2v[hh]);
                     const float p = (r < Lq) ? __expf(st[nt][e] * a.scale * f + madd[hh] - lse_s[r]) : 0.f;
-                    const float ds = p * (dpt[nt][e] - dl_s[r]);
-                    dpt[nt][e] = p;           // P^T
+                    float mult = 1.f;
+                    if (a.drop.thresh)
+                        mult = drop_mult(a.drop, (uint32_t)((((long)b * a.nh + h) * Lq + r) * n + (j0 + g + 8 * hh)));
+                    const float ds = p * (dpt[nt][e] * mult - dl_s[r]);
+                    dpt[nt][e] = p * mult;    // dropped P^T
                     st[nt][e] = ds * f;       // dS^T * f
                 }
             }

@@ -42,8 +42,35 @@ extern unsigned long long g_b200mart_launches;
         if (_r != 0) return _r;                                                            \
     } while (0)
 
+// ---------------------------------------------------------------- dropout (counter-based, stateless)
+// keep(element) = hash32(index ^ site_seed) >= thresh, thresh = p * 2^32; kept values are scaled by 1 / (1 - p).  The mask
+// of a site is a pure function of (seed, site, element index), so backward regenerates it instead of storing it.
+// Sites of the BERT stream (MarT/models/modeling_unimo.py:185, :362, :389, :476): 0 = embeddings; per text layer i:
+// 1 + 3 i = attention probabilities, 2 + 3 i = attention-output dense, 3 + 3 i = FFN-output dense.
+struct DropCfg {
+    uint32_t site_seed;
+    uint32_t thresh;   // 0 = dropout off
+    float scale;
+};
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+inline DropCfg make_drop(float p, uint32_t seed, int site) {
+    DropCfg d;
+    d.site_seed = hash32(seed + 0x9E3779B9U * (uint32_t)(site + 1));
+    d.thresh = (p > 0.f) ? (uint32_t)((double)p * 4294967296.0) : 0u;
+    d.scale = (p > 0.f) ? 1.0f / (1.0f - p) : 1.0f;
+    return d;
+}
+
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
+// multiplier of element `idx` at a dropout site: 0 (dropped) or 1 / (1 - p)
+__device__ __forceinline__ float drop_mult(const DropCfg& d, uint32_t idx) {
+    return (hash32(idx ^ d.site_seed) >= d.thresh) ? d.scale : 0.f;
+}
+
 
 // Spin limit for every mbarrier wait: a protocol bug must trap (CUDA error on the host)
 // instead of hanging the GPU box.

@@ -82,7 +82,8 @@ __global__ void im2col_kernel(const float* __restrict__ px, bf16* __restrict__ o
 // ---------------------------------------------------------------- LayerNorm core (warp per row)
 template <bool WRITE_STATS>
 __device__ __forceinline__ void ln_row(float4 (&v)[MAXV], int nv, int H, const float* gamma, const float* beta, float eps,
-                                       float* y32, bf16* y16, float* mean_out, float* rstd_out, int lane) {
+                                       float* y32, bf16* y16, float* mean_out, float* rstd_out, int lane,
+                                       DropCfg drop = DropCfg{0u, 0u, 1.f}, uint32_t row_idx0 = 0u) {
     float s = 0.f;
 #pragma unroll
     for (int t = 0; t < MAXV; ++t)
@@ -107,6 +108,10 @@ __device__ __forceinline__ void ln_row(float4 (&v)[MAXV], int nv, int H, const f
             o.y = (v[t].y - mean) * rstd * g.y + b.y;
             o.z = (v[t].z - mean) * rstd * g.z + b.z;
             o.w = (v[t].w - mean) * rstd * g.w + b.w;
+            if (drop.thresh) {   // dropout on the normalised output (BertEmbeddings :185); element index = row * H + col
+                o.x *= drop_mult(drop, row_idx0 + col); o.y *= drop_mult(drop, row_idx0 + col + 1);
+                o.z *= drop_mult(drop, row_idx0 + col + 2); o.w *= drop_mult(drop, row_idx0 + col + 3);
+            }
             if (y32) st4(y32 + col, o);
             if (y16) st4_bf16(y16 + col, o);
         }
@@ -156,7 +161,7 @@ __global__ void text_embed_ln_kernel(const int64_t* __restrict__ ids, const int6
                                      const float* __restrict__ E, const float* __restrict__ pos,
                                      const float* __restrict__ type, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float eps, float* pre, float* out32, bf16* out16,
-                                     float* mean, float* rstd, int B, int L, int H, int V, int* status) {
+                                     float* mean, float* rstd, int B, int L, int H, int V, int* status, DropCfg drop) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= B * L) return;
@@ -175,7 +180,8 @@ __global__ void text_embed_ln_kernel(const int64_t* __restrict__ ids, const int6
             v[k] = make_float4(a.x + t.x + p.x, a.y + t.y + p.y, a.z + t.z + p.z, a.w + t.w + p.w);
             st4(pre + (long)row * H + col, v[k]);
         }
-    ln_row<true>(v, nv, H, gamma, beta, eps, out32 + (long)row * H, out16 + (long)row * H, mean + row, rstd + row, lane);
+    ln_row<true>(v, nv, H, gamma, beta, eps, out32 + (long)row * H, out16 + (long)row * H, mean + row, rstd + row, lane, drop,
+                 (uint32_t)row * (uint32_t)H);
 }
 
 // LayerNorm backward. Each warp walks rows r = warp_id, warp_id + nwarps, ...; dgamma/dbeta (and, optionally, the column
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ add,
                      const bf16* __restrict__ dact_src, int dact, float* dx32, bf16* dx16, float* dgamma, float* dbeta,
-                     float* dxsum, int M, int H) {
+                     float* dxsum, int M, int H, DropCfg dy_drop, DropCfg dx16_drop) {
     extern __shared__ float red[];  // [warps][H] x (2 or 3)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int nv = H / 128;
@@ -207,6 +213,11 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
             if (t < nv) {
                 const long off = (long)row * H + lane * 4 + t * 128;
                 d[t] = ld4(dy + off);
+                if (dy_drop.thresh) {   // this LayerNorm's output went through dropout: dy arrives wrt the dropped output
+                    const uint32_t e = (uint32_t)off;
+                    d[t].x *= drop_mult(dy_drop, e); d[t].y *= drop_mult(dy_drop, e + 1);
+                    d[t].z *= drop_mult(dy_drop, e + 2); d[t].w *= drop_mult(dy_drop, e + 3);
+                }
                 float4 xv = ld4(x + off);
                 xh[t] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
                 ab[t].x += d[t].x; ab[t].y += d[t].y; ab[t].z += d[t].z; ab[t].w += d[t].w;
@@ -240,8 +251,13 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                     float4 a = ld4(add + off);
                     o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
                 }
+                if (dx32) st4(dx32 + off, o);      // full gradient: the residual path
+                if (dx16_drop.thresh) {            // the dense branch fed this LayerNorm through dropout: mask its gradient
+                    const uint32_t e = (uint32_t)off;
+                    o.x *= drop_mult(dx16_drop, e); o.y *= drop_mult(dx16_drop, e + 1);
+                    o.z *= drop_mult(dx16_drop, e + 2); o.w *= drop_mult(dx16_drop, e + 3);
+                }
                 if (COLSUM) { ac[t].x += o.x; ac[t].y += o.y; ac[t].z += o.z; ac[t].w += o.w; }
-                if (dx32) st4(dx32 + off, o);
                 if (dx16) st4_bf16(dx16 + off, o);
             }
     }
@@ -430,10 +446,10 @@ int launch_vision_embed_ln(const float* patch_out, const float* cls, const float
 }
 int launch_text_embed_ln(const int64_t* ids, const int64_t* tt, const float* E, const float* pos, const float* type,
                          const float* gamma, const float* beta, float eps, float* pre, float* out_f32, bf16* out_bf16,
-                         float* mean, float* rstd, int B, int L, int H, int V, int* status, cudaStream_t s) {
+                         float* mean, float* rstd, int B, int L, int H, int V, int* status, DropCfg drop, cudaStream_t s) {
     B2_TRY(check_h(H));
     text_embed_ln_kernel<<<(B * L + 3) / 4, 128, 0, s>>>(ids, tt, E, pos, type, gamma, beta, eps, pre, out_f32, out_bf16,
-                                                        mean, rstd, B, L, H, V, status);
+                                                        mean, rstd, B, L, H, V, status, drop);
     B2_LAUNCHED();
     return 0;
 }
@@ -446,7 +462,7 @@ int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
 }
 int launch_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                          const float* add, const bf16* dact_src, int dact, float* dx32, bf16* dx16, float* dgamma,
-                         float* dbeta, float* dxsum, int M, int H, cudaStream_t s) {
+                         float* dbeta, float* dxsum, int M, int H, cudaStream_t s, DropCfg dy_drop, DropCfg dx16_drop) {
     B2_TRY(check_h(H));
     const int nw = 8;
     int blocks = (M + nw - 1) / nw;
@@ -455,11 +471,11 @@ int launch_layernorm_bwd(const float* dy, const float* x, const float* mean, con
     if (dxsum) {
         CUDA_TRY(cudaFuncSetAttribute((const void*)layernorm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         layernorm_bwd_kernel<true><<<blocks, nw * 32, smem, s>>>(dy, x, mean, rstd, gamma, add, dact_src, dact_src ? dact : 0, dx32,
-                                                               dx16, dgamma, dbeta, dxsum, M, H);
+                                                               dx16, dgamma, dbeta, dxsum, M, H, dy_drop, dx16_drop);
     } else {
         CUDA_TRY(cudaFuncSetAttribute((const void*)layernorm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         layernorm_bwd_kernel<false><<<blocks, nw * 32, smem, s>>>(dy, x, mean, rstd, gamma, add, dact_src, dact_src ? dact : 0, dx32,
-                                                                dx16, dgamma, dbeta, nullptr, M, H);
+                                                                dx16, dgamma, dbeta, nullptr, M, H, dy_drop, dx16_drop);
     }
     B2_LAUNCHED();
     return 0;

@@ -25,6 +25,7 @@ struct GemmOp {
     int act = 0;                          // 0 none, 1 gelu(erf), 2 quick_gelu
     int save_grad = 0;                    // out_preact receives act'(pre-activation) instead of the pre-activation
     const bf16* dact_src = nullptr; long ldx = 0; int dact = 0;  // *= act'(dact_src[m,n]) (backward); dact = 3: dact_src already holds act'
+    DropCfg drop = DropCfg{0u, 0u, 1.f};  // dropout applied to the value before the residual add (element index m*N+n)
     const float* residual = nullptr; long ldr = 0;   // + residual[m,n] (fp32)
     float* out_f32 = nullptr; long ldo32 = 0;
     bf16* out_bf16 = nullptr; long ldo16 = 0;
@@ -41,6 +42,7 @@ struct GemmPlan;  // opaque: encoded tensor maps + launch geometry
 // operand pointers stay valid.
 int gemm_plan_create(const GemmOp& op, GemmPlan** out);
 void gemm_plan_destroy(GemmPlan* p);
-int gemm_plan_launch(const GemmPlan* p, cudaStream_t stream);
+// drop: optional override of the plan's dropout configuration (same on/off state, fresh seed)
+int gemm_plan_launch(const GemmPlan* p, cudaStream_t stream, const DropCfg* drop = nullptr);
 // flops of one launch (2*M*N*K)
 double gemm_plan_flops(const GemmPlan* p);

@@ -50,6 +50,7 @@ struct GemmDev {
     float* out_f32; long ldo32;
     bf16* out_bf16; long ldo16;
     int accumulate;
+    DropCfg drop;                            // dropout on (acc*alpha + bias) before the residual add (EPI_RES / GENERIC)
     float* colsum_out; float* colsum_out2;   // EPI_DACT: += column sums of the output (bias gradient of the producing layer)
     int debug;   // B200MART_GEMM_DEBUG bitmask (bring-up only): 1 no epilogue global access, 2 no TMA, 4 no MMA
 };
@@ -127,7 +128,13 @@ __device__ __forceinline__ void epilogue_row(const GemmDev& p, const float* stg,
         *reinterpret_cast<uint32_t*>(p.out_preact + row * p.ldp + col) = p.save_grad ? pack_bf16x2(d0, d1) : pack_bf16x2(v0, v1);
         *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(y0, y1);
     } else if (EPI == EPI_RES) {
-        const float o0 = v0 + rs.x, o1 = v1 + rs.y;
+        float d0 = v0, d1 = v1;
+        if (p.drop.thresh) {   // BertSelfOutput :389 / BertOutput :476: dropout(dense(x)) + residual
+            const uint32_t e = (uint32_t)row * (uint32_t)p.N + (uint32_t)col;
+            d0 *= drop_mult(p.drop, e);
+            d1 *= drop_mult(p.drop, e + 1);
+        }
+        const float o0 = d0 + rs.x, o1 = d1 + rs.y;
         *reinterpret_cast<float2*>(p.out_f32 + row * p.ldo32 + col) = make_float2(o0, o1);
         if (p.out_bf16) *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(o0, o1);
     } else if (EPI == EPI_F32) {
@@ -188,6 +195,7 @@ __device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* st
                     const float x = __bfloat162float(p.dact_src[row * p.ldx + col]);
                     v *= (p.dact == 3) ? x : act_grad(p.dact, x);
                 }
+                if (p.drop.thresh) v *= drop_mult(p.drop, (uint32_t)row * (uint32_t)p.N + (uint32_t)col);
                 if (p.residual) v += p.residual[row * p.ldr + col];
                 if (p.out_f32) {
                     if (p.accumulate) atomicAdd(p.out_f32 + row * p.ldo32 + col, v);

@@ -94,9 +94,10 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
         else if (!op.accumulate && !has_dact && !op.out_preact && op.act == 0 && !op.bias2 && op.residual && op.out_f32)
             epi = EPI_RES;
         else if (!op.accumulate && !has_dact && !op.out_preact && op.act == 0 && !op.bias2 && !op.residual && op.out_f32 &&
-                 !op.out_bf16)
+                 !op.out_bf16 && !op.drop.thresh)
             epi = EPI_F32;
-        else if (!op.accumulate && !has_dact && !op.out_preact && op.act == 0 && !op.residual && op.out_bf16 && !op.out_f32)
+        else if (!op.accumulate && !has_dact && !op.out_preact && op.act == 0 && !op.residual && op.out_bf16 && !op.out_f32 &&
+                 !op.drop.thresh)
             epi = EPI_BF16;
     }
     if (!has_specialised(op.a_mn, op.b_mn, epi)) epi = EPI_GENERIC;
@@ -142,6 +143,7 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
     d.out_f32 = op.out_f32; d.ldo32 = op.ldo32; d.out_bf16 = op.out_bf16; d.ldo16 = op.ldo16;
     d.accumulate = op.accumulate;
     d.colsum_out = op.colsum_out; d.colsum_out2 = op.colsum_out2;
+    d.drop = op.drop;
     { const char* e = getenv("B200MART_GEMM_DEBUG"); d.debug = e ? atoi(e) : 0; }
     int split = op.split_k;
     if (split > d.kb_total) split = d.kb_total;
@@ -170,8 +172,14 @@ void gemm_plan_destroy(GemmPlan* p) { delete p; }
 
 double gemm_plan_flops(const GemmPlan* p) { return p->flops; }
 
-int gemm_plan_launch(const GemmPlan* p, cudaStream_t stream) {
-    p->kernel<<<p->grid, GEMM_THREADS, p->smem, stream>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, p->dev);
+int gemm_plan_launch(const GemmPlan* p, cudaStream_t stream, const DropCfg* drop) {
+    if (drop) {   // per-step dropout seed: the plan (tensor maps, geometry) is reused, only the mask seed changes
+        GemmDev dev = p->dev;
+        dev.drop = *drop;
+        p->kernel<<<p->grid, GEMM_THREADS, p->smem, stream>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, dev);
+    } else {
+        p->kernel<<<p->grid, GEMM_THREADS, p->smem, stream>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, p->dev);
+    }
     B2_LAUNCHED();
     return 0;
 }

@@ -17,14 +17,17 @@ int launch_vision_embed_ln(const float* patch_out, const float* cls, const float
 // BertEmbeddings (modeling_unimo.py:152-186), dropout p = 0
 int launch_text_embed_ln(const int64_t* ids, const int64_t* tt, const float* E, const float* pos, const float* type,
                          const float* gamma, const float* beta, float eps, float* pre, float* out_f32, bf16* out_bf16,
-                         float* mean, float* rstd, int B, int L, int H, int V, int* status, cudaStream_t s);
+                         float* mean, float* rstd, int B, int L, int H, int V, int* status, DropCfg drop, cudaStream_t s);
 int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y32, bf16* y16,
                          float* mean, float* rstd, int M, int H, cudaStream_t s);
 // dx = LN'(dy) [* act'(dact_src)] [+ add];  dgamma += ..., dbeta += ...; dxsum[c] += sum_rows dx[:, c] when given
 // (the bias gradient of the linear layer whose output this LayerNorm normalised)
 int launch_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                          const float* add, const bf16* dact_src, int dact, float* dx32, bf16* dx16, float* dgamma,
-                         float* dbeta, float* dxsum, int M, int H, cudaStream_t s);
+                         float* dbeta, float* dxsum, int M, int H, cudaStream_t s, DropCfg dy_drop = DropCfg{0u, 0u, 1.f},
+                         DropCfg dx16_drop = DropCfg{0u, 0u, 1.f});
+// dy_drop: dy is the gradient wrt a DROPPED copy of this LayerNorm's output (element index row*H+col);
+// dx16_drop: dx16 (and dxsum) additionally carry the dropout mask of the dense branch that fed the LayerNorm input
 int launch_colsum_bf16(const bf16* x, long ld, float* out, int M, int N, cudaStream_t s);  // out[n] += sum_m x[m,n]
 int launch_colsum_f32(const float* x, long ld, float* out, int M, int N, cudaStream_t s);
 // text embedding backward: dE[ids] += d, dtype[tt] += d, dpos[l] += d  (d = gradient wrt the pre-LN sum)
@@ -45,6 +48,7 @@ int launch_adamw(float* p, const float* g, float* m, float* v, bf16* p16, const 
 
 // ---- attention_mma.cu (self-attention) / attention.cu (fusion)
 struct AttnFwd {
+    DropCfg drop;                 // dropout on the attention probabilities (thresh 0 = off); element ((b*nh+h)*Lq+r)*n+c
     // Q rows: [B*Lq] rows of q (ldq), head h at column h*64. Keys: optional prefix source (n1 keys per sample) then own (n2).
     const bf16* q; long ldq;
     const bf16* k1; const bf16* v1; long ld1; int n1;   // prefix (text K/V for the vision stream), may be null

@@ -93,6 +93,12 @@ struct b200mart_handle {
     int nseg = 0;
     // cached workspace carving
     Workspace ws; void* ws_base = nullptr;
+    // dropout (BERT stream; reference p = 0.1 in training): masks are regenerated from (seed, site, element) in backward
+    bool training = false;
+    float p_hidden = 0.f, p_attn = 0.f;
+    uint32_t seed0 = 0, cur_seed = 0;
+    unsigned long long fwd_count = 0;
+    float cur_ph = 0.f, cur_pa = 0.f;          // probabilities in effect for the forward whose activations are saved
     // two-chain execution: the vision and text streams of the model are independent below the fusion depth
     // (modeling_unimo.py:616-640), so each runs on its own CUDA stream, ordered by events where they meet
     bool split_streams = true;
@@ -315,7 +321,7 @@ int run_gemm(b200mart_handle* h, const GemmOp& op, cudaStream_t s) {
     key[k++] = (long)op.dact_src; key[k++] = op.ldx; key[k++] = op.dact; key[k++] = (long)op.residual; key[k++] = op.ldr;
     key[k++] = (long)op.out_f32; key[k++] = op.ldo32; key[k++] = (long)op.out_bf16; key[k++] = op.ldo16;
     key[k++] = op.accumulate; key[k++] = op.split_k; key[k++] = op.bn; key[k++] = op.save_grad;
-    key[k++] = (long)op.colsum_out; key[k++] = (long)op.colsum_out2;
+    key[k++] = (long)op.colsum_out; key[k++] = (long)op.colsum_out2; key[k++] = op.drop.thresh;
     std::string ks(reinterpret_cast<const char*>(key), k * sizeof(long));
     auto it = h->plans.find(ks);
     GemmPlan* plan = nullptr;
@@ -331,7 +337,7 @@ int run_gemm(b200mart_handle* h, const GemmOp& op, cudaStream_t s) {
     }
     ProfScope ps(h, s, CAT_GEMM);
     if (h->profiling) h->prof_flops += gemm_plan_flops(plan);
-    return gemm_plan_launch(plan, s);
+    return gemm_plan_launch(plan, s, op.drop.thresh ? &op.drop : nullptr);
 }
 
 // split-K factor for weight-gradient GEMMs so that the grid covers the machine (148 SMs)
@@ -347,6 +353,7 @@ struct Run {
     b200mart_handle* h;
     const b200mart_buffers* bufs;
     cudaStream_t s;
+    DropCfg drop_next = DropCfg{0u, 0u, 1.f};   // consumed by the next linear(): dropout before its residual add
     const float* p32(long off) const { return bufs->params32 + off; }
     const bf16* p16(long off) const { return reinterpret_cast<const bf16*>(bufs->params16) + off; }
     float* g32(long off) const { return bufs->grads32 + off; }
@@ -363,6 +370,8 @@ struct Run {
         // bf16-output activations save act'(pre) for backward (cheap multiply there); the fp32-output head saves pre itself
         op.save_grad = (preact != nullptr && out32 == nullptr && act != 0) ? 1 : 0;
         op.residual = residual; op.ldr = N;
+        op.drop = drop_next;
+        drop_next = DropCfg{0u, 0u, 1.f};
         op.out_f32 = out32; op.ldo32 = N; op.out_bf16 = out16; op.ldo16 = N;
         return run_gemm(h, op, s);
     }
@@ -510,8 +519,17 @@ extern "C" int32_t b200mart_layer_extent(const b200mart_handle* h, int32_t layer
 extern "C" int32_t b200mart_set_option(b200mart_handle* h, const char* name, int32_t value) {
     B2_CHECK(h && name, "set_option: null argument");
     if (strcmp(name, "streams") == 0) { h->split_streams = value != 0; return 0; }
+    if (strcmp(name, "training") == 0) { h->training = value != 0; return 0; }
     return b200mart_set_err(1, "set_option: unknown option '%s'", name);
 }
+
+extern "C" int32_t b200mart_set_dropout(b200mart_handle* h, float p_hidden, float p_attn, uint32_t seed) {
+    B2_CHECK(h && p_hidden >= 0.f && p_hidden < 1.f && p_attn >= 0.f && p_attn < 1.f, "set_dropout: probabilities must be in [0, 1)");
+    h->p_hidden = p_hidden; h->p_attn = p_attn; h->seed0 = seed;
+    return 0;
+}
+
+extern "C" uint32_t b200mart_last_dropout_seed(const b200mart_handle* h) { return h ? h->cur_seed : 0u; }
 
 extern "C" int32_t b200mart_cast_params(const b200mart_handle* h, const float* p32, void* p16, void* stream) {
     B2_CHECK(h && p32 && p16, "cast_params: null argument");
@@ -552,6 +570,13 @@ extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* 
     const cudaStream_t sv = ch.v, stx = ch.t;          // vision chain / text chain
     Run rv{h, bufs, sv}, rt{h, bufs, stx};
     std::vector<cudaEvent_t> ev_tqkv(D, nullptr), ev_vout(D, nullptr);
+    // dropout state of THIS forward (backward regenerates the same masks)
+    h->cur_ph = h->training ? h->p_hidden : 0.f;
+    h->cur_pa = h->training ? h->p_attn : 0.f;
+    ++h->fwd_count;
+    h->cur_seed = hash32(h->seed0 ^ hash32((uint32_t)h->fwd_count) ^ (uint32_t)(h->fwd_count >> 32));
+    const float ph = h->cur_ph, pa = h->cur_pa;
+    const uint32_t seed = h->cur_seed;
 
     // ---- vision embeddings: im2col -> patch GEMM -> (+cls, +pos) -> pre-LN     (modeling_unimo.py:119-132, :711)
     B2_TRY(launch_im2col(batch->pixel_values, w.patches16, B, d.image_size, d.patch, h->patch_ld, sv));
@@ -572,7 +597,7 @@ extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* 
     // ---- text embeddings (:152-186)
     B2_TRY(launch_text_embed_ln(batch->input_ids, batch->token_type_ids, rt.p32(l.word), rt.p32(l.tpos), rt.p32(l.ttype),
                                 rt.p32(l.eln_w), rt.p32(l.eln_b), d.text_eps, w.tpre, w.T32[0], w.T16[0], w.emean, w.erstd, B, L,
-                                H, d.vocab, w.status, stx));
+                                H, d.vocab, w.status, make_drop(ph, seed, 0), stx));
 
     for (int i = 0; i < D; ++i) {
         const bool fused = i >= d.fuse_from;
@@ -611,16 +636,19 @@ extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* 
             at.key_mask = batch->attention_mask;
             if (batch->sep_idx) { at.sep_idx = batch->sep_idx; at.w0 = rt.p32(p.aw0); at.w1 = rt.p32(p.aw1); }
             at.out = a.ctx16; at.ldo = H; at.lse = a.lse;
+            at.drop = make_drop(pa, seed, 1 + 3 * i);
             { ProfScope ps(h, stx, CAT_ATTN); B2_TRY(launch_attention_fwd(at, fused ? a.ctx32 : nullptr, stx)); }
             if (fused) ch.wait(stx, ev_vout[i]);       // needs the vision output of this layer index
             if (fused)   // BertFusion on the context with the vision output of THIS layer index (:373, :627)
                 { ProfScope ps(h, stx, CAT_FUSION); B2_TRY(launch_fusion_fwd(a.ctx32, w.V32[i + 1], a.g16, a.flse, B, L, Nv, H, stx)); }
+            rt.drop_next = make_drop(ph, seed, 2 + 3 * i);
             B2_TRY(rt.linear(Mt, H, H, a.ctx16, p.ao_w, p.ao_b, 0, nullptr, w.T32[i], a.apre, nullptr));
             B2_TRY(launch_layernorm_fwd(a.apre, rt.p32(p.aln_w), rt.p32(p.aln_b), d.text_eps, a.a32, a.a16, a.amean, a.arstd, Mt, H, stx));
             if (fused)
                 B2_TRY(rt.linear(Mt, F, H, a.a16, p.i_w, p.i_b, 1, a.ipre16, nullptr, nullptr, a.i16, a.g16, p.f_w, p.f_b));
             else
                 B2_TRY(rt.linear(Mt, F, H, a.a16, p.i_w, p.i_b, 1, a.ipre16, nullptr, nullptr, a.i16));
+            rt.drop_next = make_drop(ph, seed, 3 + 3 * i);
             B2_TRY(rt.linear(Mt, H, F, a.i16, p.o_w, p.o_b, 0, nullptr, a.a32, a.opre, nullptr));
             B2_TRY(launch_layernorm_fwd(a.opre, rt.p32(p.oln_w), rt.p32(p.oln_b), d.text_eps, w.T32[i + 1], w.T16[i + 1], a.omean, a.orstd, Mt, H, stx));
         }
@@ -790,6 +818,9 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
     const cudaStream_t sv = ch.v, stx = ch.t;
     Run rv{h, bufs, sv}, rt{h, bufs, stx};
     std::vector<cudaEvent_t> ev_vdone(D + 1, nullptr), ev_tfus(D, nullptr), ev_tattn(D, nullptr);
+    const float ph = h->cur_ph, pa = h->cur_pa;      // dropout of the forward whose activations are in the workspace
+    const uint32_t seed = h->cur_seed;
+    const DropCfg nodrop{0u, 0u, 1.f};
     for (int i = D - 1; i >= 0; --i) {
         const bool fused = i >= d.fuse_from;
         // ================= text layer i backward
@@ -798,7 +829,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             TxtLayerA& a = w.tl[i];
             // output LayerNorm
             B2_TRY(launch_layernorm_bwd(w.dT, a.opre, a.omean, a.orstd, rt.p32(p.oln_w), nullptr, nullptr, 0, w.t32a, w.t16a,
-                                        rt.g32(p.oln_w), rt.g32(p.oln_b), rt.g32(p.o_b), Mt, H, stx));
+                                        rt.g32(p.oln_w), rt.g32(p.oln_b), rt.g32(p.o_b), Mt, H, stx, nodrop, make_drop(ph, seed, 3 + 3 * i)));
             B2_TRY(rt.grad_weight(Mt, H, F, w.t16a, H, a.i16, F, p.o_w, -1));
             // d(pre-GELU) = (dY Wout) * gelu'(pre); its column sums are the intermediate (and fusion_dense) bias gradients
             B2_TRY(rt.grad_input(Mt, H, F, w.t16a, p.o_w, a.ipre16, 3, nullptr, nullptr, w.tF16, p.i_b, fused ? p.f_b : -1));
@@ -808,7 +839,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             if (fused) B2_TRY(rt.grad_input(Mt, F, H, w.tF16, p.f_w, nullptr, 0, nullptr, w.t32c, nullptr));  // d fusion output
             // attention-output LayerNorm
             B2_TRY(launch_layernorm_bwd(w.t32b, a.apre, a.amean, a.arstd, rt.p32(p.aln_w), nullptr, nullptr, 0, w.t32a, w.t16a,
-                                        rt.g32(p.aln_w), rt.g32(p.aln_b), rt.g32(p.ao_b), Mt, H, stx));
+                                        rt.g32(p.aln_w), rt.g32(p.aln_b), rt.g32(p.ao_b), Mt, H, stx, nodrop, make_drop(ph, seed, 2 + 3 * i)));
             B2_TRY(rt.grad_weight(Mt, H, H, w.t16a, H, a.ctx16, H, p.ao_w, -1));
             B2_TRY(rt.grad_input(Mt, H, H, w.t16a, p.ao_w, nullptr, 0, nullptr, w.t32b, nullptr));      // d ctx
             // dV (gradient wrt the vision output of layer i) and dk1/dv1 come from vision layer i+1's backward
@@ -826,6 +857,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             at.key_mask = batch->attention_mask;
             if (batch->sep_idx) { at.sep_idx = batch->sep_idx; at.w0 = rt.p32(p.aw0); at.w1 = rt.p32(p.aw1); ab.dw0 = rt.g32(p.aw0); ab.dw1 = rt.g32(p.aw1); }
             at.lse = a.lse;
+            at.drop = make_drop(pa, seed, 1 + 3 * i);
             ab.dout = w.t32b; ab.lddo = H;
             ab.dq = w.tdqkv16; ab.dk2 = w.tdqkv16 + H; ab.dv2 = w.tdqkv16 + 2 * H; ab.ldd = 3 * H;
             if (i + 1 < D && i + 1 >= d.fuse_from) { ab.dk2_add = w.dk1; ab.dv2_add = w.dv1; ab.ldadd = H; }   // from vision layer i+1
@@ -874,7 +906,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
     }
     // ---- embeddings
     B2_TRY(launch_layernorm_bwd(w.dT, w.tpre, w.emean, w.erstd, rt.p32(l.eln_w), nullptr, nullptr, 0, w.t32a, nullptr,
-                                rt.g32(l.eln_w), rt.g32(l.eln_b), nullptr, Mt, H, stx));
+                                rt.g32(l.eln_w), rt.g32(l.eln_b), nullptr, Mt, H, stx, make_drop(ph, seed, 0), nodrop));
     B2_TRY(launch_text_embed_bwd(w.t32a, batch->input_ids, batch->token_type_ids, rt.g32(l.word), rt.g32(l.tpos), rt.g32(l.ttype), B, L, H, stx));
     if (any_fusion) {
         B2_TRY(launch_layernorm_bwd(w.dV, w.vx0, w.vmean0, w.vrstd0, rv.p32(l.preln_w), nullptr, nullptr, 0, w.v32a, nullptr,

@@ -241,6 +241,17 @@ class Engine:
             out.append((b.value, e.value))
         return out
 
+    def set_dropout(self, p_hidden, p_attn, seed=0):
+        _lib.check(self.l.b200mart_set_dropout(self.h, float(p_hidden), float(p_attn), int(seed) & 0xFFFFFFFF))
+
+    def train(self, mode=True):
+        """nn.Module.train()/eval(): dropout on/off for the following forward calls."""
+        self.set_option("training", 1 if mode else 0)
+
+    def last_dropout_seed(self):
+        """Per-forward seed of the most recent forward (tests rebuild the masks from it)."""
+        return int(self.l.b200mart_last_dropout_seed(self.h))
+
     def set_option(self, name, value):
         _lib.check(self.l.b200mart_set_option(self.h, name.encode(), int(value)))
 

@@ -63,6 +63,7 @@ def make_fused_litmodel(base_cls):
             m, eng = self.model, self.model.engine
             mb = self._inputs(batch)
             eng.mirror_stale = True                        # a torch optimizer may have stepped the fp32 masters
+            eng.train(True)
             m._prepare_grads()
             eng.forward(mb, want_z=False)
             loss, _, _ = eng.head_loss(mb, self._head(label, extra), compute_grad=True)
@@ -75,6 +76,7 @@ def make_fused_litmodel(base_cls):
             eng = self.model.engine
             mb = self._inputs(batch)
             eng.mirror_stale = True
+            eng.train(False)
             eng.forward(mb, want_z=False)
             _, _, ranks = eng.head_loss(mb, self._head(label, extra), compute_grad=False, want_ranks=True)
             ranks = ranks.cpu().numpy()

@@ -9,7 +9,8 @@ the 2-tuple `(MaskedLMOutput-like with .logits (B, L, V), trans_hidden_states (B
 while every FLOP runs in libb200mart.so on the GPU.  Parameters are ordinary `nn.Parameter`s that are *views* of the
 engine's flat fp32 buffer; their `.grad`s are views of the flat gradient buffer.
 
-Arithmetic is the reference's eval-mode graph (dropout p = 0) in bf16-operand / fp32-accumulate precision.
+Arithmetic: bf16 tensor-core operands, fp32 accumulation; `module.train()` enables the BERT stream's dropout (reference
+p = 0.1; stateless hash masks, so the random stream differs from torch's), `module.eval()` is the deterministic graph.
 """
 from dataclasses import dataclass
 from typing import Optional
@@ -124,6 +125,7 @@ class MKGformerKGC(nn.Module):
         self.unimo.vision_embeddings.register_buffer("position_ids", torch.arange(cfg.patches + 1, device=device).expand((1, -1)))
         self._anchor = torch.zeros((), device=device, requires_grad=True)
         self.engine.mirror_stale = True
+        self.engine.set_dropout(cfg.hidden_dropout, cfg.attn_dropout, int(torch.initial_seed()) & 0x7FFFFFFF)
 
     def _init_tensor(self, name, v):
         if "LayerNorm.weight" in name or "layer_norm1.weight" in name or "layer_norm2.weight" in name or \
@@ -237,6 +239,8 @@ class MKGformerKGC(nn.Module):
         if sep_idx is not None:
             batch["sep_idx"] = sep_idx.to(dev).contiguous()
         self.engine.mirror_stale = True     # parameters may have been updated by a torch optimizer since the last call
+        if self.engine.device.type == "cuda":
+            self.engine.train(self.training)    # module.train() / .eval() -> dropout of the BERT stream on / off
         if torch.is_grad_enabled():
             logits, z = _ForwardFn.apply(self._anchor, self, batch, output_logits)
         else:

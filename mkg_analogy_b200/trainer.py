@@ -81,7 +81,7 @@ def init_weights_(engine: Engine, seed=0):
 class MartTrainer:
     def __init__(self, cfg: MKGformerConfig, vocab: VocabLayout, *, pretrain=False, lr=5e-5, weight_decay=0.01,
                  warmup_ratio=0.1, total_steps=1000, alpha=0.43, label_smoothing=0.1, device=None, process_group=None,
-                 grad_buckets=8, overlap_comm=True):
+                 grad_buckets=8, overlap_comm=True, dropout=True, seed=0):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.cfg, self.vocab, self.pretrain = cfg, vocab, bool(pretrain)
@@ -97,6 +97,11 @@ class MartTrainer:
             self.world = torch.distributed.get_world_size(process_group)
         self.grad_buckets = grad_buckets
         self._dev_batch = None
+        # training-mode dropout of the BERT stream (reference: hidden 0.1, attention 0.1); per-rank seed
+        self.dropout = bool(dropout)
+        rank = torch.distributed.get_rank(process_group) if self.world > 1 else 0
+        self.engine.set_dropout(cfg.hidden_dropout if dropout else 0.0, cfg.attn_dropout if dropout else 0.0,
+                                shard_seed(seed, rank))
         # overlapped exchange: per-layer "gradients final" events recorded by the library, all-reduces on a side stream
         self.overlap_comm = bool(overlap_comm) and self.world > 1
         self._comm_stream = self._layer_events = None
@@ -160,6 +165,7 @@ class MartTrainer:
         """One optimizer step on a device-resident batch. Returns the loss as a device tensor (1,)."""
         eng = self.engine
         mb = self._model_inputs(batch)
+        eng.train(True)
         eng.zero_grad()
         eng.forward(mb, want_z=False)
         loss, _, _ = eng.head_loss(mb, self._head(batch), compute_grad=True)
@@ -190,6 +196,7 @@ class MartTrainer:
         """_eval (transformer.py:115-166): ranks of the gold entity (1-based), and the [MASK]-row scores."""
         eng = self.engine
         mb = self._model_inputs(batch)
+        eng.train(False)
         eng.forward(mb, want_z=False)
         loss, logits, ranks = eng.head_loss(mb, self._head(batch), compute_grad=False, want_logits=True, want_ranks=True)
         return ranks, logits, loss

@@ -48,14 +48,16 @@ def vision_embed(P, cfg, pixel_values):
     return layer_norm(x, P["unimo.vision_pre_layrnorm.weight"], P["unimo.vision_pre_layrnorm.bias"], cfg.vision_eps)
 
 
-def text_embed(P, cfg, input_ids, token_type_ids):
-    """BertEmbeddings.forward, modeling_unimo.py:152-186 (dropout omitted: oracle runs in eval mode)."""
+def text_embed(P, cfg, input_ids, token_type_ids, drop=None):
+    """BertEmbeddings.forward, modeling_unimo.py:152-186.  `drop(site, tensor)` (optional) applies the dropout of :185
+    with an explicit mask; None = eval mode."""
     L = input_ids.shape[1]
     e = (P["unimo.text_embeddings.word_embeddings.weight"][input_ids]
          + P["unimo.text_embeddings.token_type_embeddings.weight"][token_type_ids]
          + P["unimo.text_embeddings.position_embeddings.weight"][:L][None])
-    return layer_norm(e, P["unimo.text_embeddings.LayerNorm.weight"], P["unimo.text_embeddings.LayerNorm.bias"],
-                      cfg.text_eps)
+    out = layer_norm(e, P["unimo.text_embeddings.LayerNorm.weight"], P["unimo.text_embeddings.LayerNorm.bias"],
+                     cfg.text_eps)
+    return drop(0, out) if drop is not None else out
 
 
 def _heads(x, nh):
@@ -100,7 +102,7 @@ def adaptive_scale(scores, sep_split, w0, w1):
     return scores * factor
 
 
-def text_layer(P, cfg, i, x, ext_mask, vis, sep_split):
+def text_layer(P, cfg, i, x, ext_mask, vis, sep_split, drop=None):
     """BertLayer.forward :540-577 = BertSelfAttention :317-377 (+ BertFusion :400-414 on the context when a
     visual state is given) -> BertSelfOutput :380-391 -> BertIntermediate :448-464 -> BertOutput :467-478.
     Returns (hidden, (K, V)) — the layer's K/V are what the next vision layer prepends."""
@@ -114,28 +116,35 @@ def text_layer(P, cfg, i, x, ext_mask, vis, sep_split):
         sc = adaptive_scale(sc, sep_split, P[p + "attention.self.adaptive_weight.0"],
                             P[p + "attention.self.adaptive_weight.1"])
     sc = sc + ext_mask
-    ctx = (torch.softmax(sc, dim=-1) @ v).permute(0, 2, 1, 3).reshape(x.shape)
+    probs = torch.softmax(sc, dim=-1)
+    if drop is not None:
+        probs = drop(1 + 3 * i, probs)                      # :362
+    ctx = (probs @ v).permute(0, 2, 1, 3).reshape(x.shape)
     fusion = None
     if vis is not None:  # BertFusion: no 1/sqrt(d), no mask
         fusion = torch.softmax(ctx @ vis.transpose(-1, -2), dim=-1) @ vis
-    a = layer_norm(x + F.linear(ctx, P[p + "attention.output.dense.weight"], P[p + "attention.output.dense.bias"]),
-                   P[p + "attention.output.LayerNorm.weight"], P[p + "attention.output.LayerNorm.bias"], cfg.text_eps)
+    ao = F.linear(ctx, P[p + "attention.output.dense.weight"], P[p + "attention.output.dense.bias"])
+    if drop is not None:
+        ao = drop(2 + 3 * i, ao)                            # :389
+    a = layer_norm(x + ao, P[p + "attention.output.LayerNorm.weight"], P[p + "attention.output.LayerNorm.bias"], cfg.text_eps)
     h = F.linear(a, P[p + "intermediate.dense.weight"], P[p + "intermediate.dense.bias"])
     if fusion is not None:
         h = h + F.linear(fusion, P[p + "intermediate.fusion_dense.weight"], P[p + "intermediate.fusion_dense.bias"])
     h = F.gelu(h)
-    out = layer_norm(a + F.linear(h, P[p + "output.dense.weight"], P[p + "output.dense.bias"]),
-                     P[p + "output.LayerNorm.weight"], P[p + "output.LayerNorm.bias"], cfg.text_eps)
+    fo = F.linear(h, P[p + "output.dense.weight"], P[p + "output.dense.bias"])
+    if drop is not None:
+        fo = drop(3 + 3 * i, fo)                            # :476
+    out = layer_norm(a + fo, P[p + "output.LayerNorm.weight"], P[p + "output.LayerNorm.bias"], cfg.text_eps)
     return out, (k, v)
 
 
-def encoder(P, cfg, vis, txt, ext_mask, sep_split):
+def encoder(P, cfg, vis, txt, ext_mask, sep_split, drop=None):
     """UnimoEncoder.forward :589-658: interleaved loop; layer idx >= fuse_from: the vision layer gets the
     (K, V) of text layer idx-1 and the text layer fuses with the vision OUTPUT of layer idx."""
     kv = None
     for i in range(cfg.layers):
         vis = vision_layer(P, cfg, i, vis, kv if i >= cfg.fuse_from else None)
-        txt, kv = text_layer(P, cfg, i, txt, ext_mask, vis if i >= cfg.fuse_from else None, sep_split)
+        txt, kv = text_layer(P, cfg, i, txt, ext_mask, vis if i >= cfg.fuse_from else None, sep_split, drop)
     return vis, txt
 
 
@@ -147,7 +156,7 @@ def head_transform(P, cfg, x):
                       cfg.text_eps)
 
 
-def forward(P, cfg, batch, full_logits=True):
+def forward(P, cfg, batch, full_logits=True, drop=None):
     """UnimoForMaskedLM.forward :848-893.  Returns (logits (B, L, V) or None, trans_hidden (B, L, H))."""
     ids, att = batch["input_ids"], batch["attention_mask"]
     tt = batch.get("token_type_ids")
@@ -155,9 +164,9 @@ def forward(P, cfg, batch, full_logits=True):
         tt = torch.zeros_like(ids)
     sep = batch.get("sep_idx")
     vis = vision_embed(P, cfg, batch["pixel_values"])
-    txt = text_embed(P, cfg, ids, tt)
+    txt = text_embed(P, cfg, ids, tt, drop)
     ext_mask = (1.0 - att[:, None, None, :].to(txt.dtype)) * -10000.0        # get_extended_attention_mask :21-57
-    _, txt = encoder(P, cfg, vis, txt, ext_mask, None if sep is None else sep[:, 2])
+    _, txt = encoder(P, cfg, vis, txt, ext_mask, None if sep is None else sep[:, 2], drop)
     z = head_transform(P, cfg, txt)
     logits = None
     if full_logits:
@@ -204,9 +213,9 @@ def relaxation_loss(z, rel_idx, q_head_idx, a_head_idx):
     return sim.mean()
 
 
-def finetune_loss(P, cfg, batch, analogy_entity_ids, alpha=0.43, label_smoothing=0.1):
+def finetune_loss(P, cfg, batch, analogy_entity_ids, alpha=0.43, label_smoothing=0.1, drop=None):
     """training_step fine-tune branch, transformer.py:92-109.  Returns (loss, mask_logits (B, C), z)."""
-    _, z = forward(P, cfg, batch, full_logits=False)
+    _, z = forward(P, cfg, batch, full_logits=False, drop=drop)
     mpos = mask_positions(batch["input_ids"])
     cols = torch.as_tensor(analogy_entity_ids, device=z.device)
     x = mask_row_logits(P, z, mpos, cols)
@@ -231,6 +240,34 @@ def pretrain_loss(P, cfg, batch, entity_range, relation_range, label_smoothing=0
             x = mask_row_logits(P, z[sel], mpos[sel], torch.arange(st, ed, device=z.device))
             loss = loss + lf(x, batch["label"][sel])
     return loss
+
+
+def hash_dropout(seed, p_hidden, p_attn):
+    """drop(site, tensor) callback reproducing the CUDA path's stateless dropout masks (csrc/common.cuh: keep element e of
+    site s iff hash32(e ^ hash32(seed + 0x9E3779B9 (s + 1))) >= p 2^32; kept values scaled by 1/(1-p) in fp32), so the
+    training-mode graph can be checked against the oracle mask for mask.  Sites: 0 embeddings, 1+3i attention probabilities
+    (p_attn), 2+3i / 3+3i sub-layer outputs."""
+    import numpy as np
+    M = 0xFFFFFFFF
+
+    def h32(x):
+        x = x ^ (x >> 16)
+        x = (x * 0x7feb352d) & M
+        x = x ^ (x >> 15)
+        x = (x * 0x846ca68b) & M
+        return x ^ (x >> 16)
+
+    def drop(site, t):
+        p = np.float32(p_attn if (site >= 1 and (site - 1) % 3 == 0) else p_hidden)
+        if p <= 0:
+            return t
+        thresh = int(np.float64(p) * 4294967296.0)
+        scale = float(np.float32(1.0) / (np.float32(1.0) - p))
+        site_seed = int(h32(torch.tensor((seed + 0x9E3779B9 * (site + 1)) & M, dtype=torch.int64)))
+        idx = torch.arange(t.numel(), dtype=torch.int64, device=t.device)
+        keep = h32(idx ^ site_seed) >= thresh
+        return t * (keep.to(t.dtype) * scale).view(t.shape)
+    return drop
 
 
 def ranks_of_gold(x, label):

@@ -217,6 +217,7 @@ def test_dropin_module_with_torch_autograd_and_optimizer(tiny):
     from mkg_analogy_b200.modeling import MKGformerKGC
     from oracle import mkgformer_oracle as O
     model = MKGformerKGC(cfg, device="cuda")
+    model.engine.set_dropout(0.0, 0.0)                 # deterministic graph: the oracle comparison below is mask-free
     model.load_state_dict({**model.state_dict(), **{k: v for k, v in params.items()}})
     inputs = {k: batch[k] for k in ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "sep_idx")}
     out = model(**inputs, return_dict=True)
@@ -272,6 +273,7 @@ def test_fused_litmodel_shim_matches_engine(tiny):
             self.__dict__.update(data_config)
 
     model = MKGformerKGC(cfg, device="cuda")
+    model.engine.set_dropout(0.0, 0.0)
     model.load_state_dict({**model.state_dict(), **params})
     args = Namespace(pretrain=0, label_smoothing=0.1, alpha=0.43)
     tok = Namespace(mask_token_id=103)
@@ -286,3 +288,38 @@ def test_fused_litmodel_shim_matches_engine(tiny):
     assert named["unimo.text_pooler.dense.weight"].grad is None
     ranks = lit._eval({k: v.clone() for k, v in batch.items()}, 0)["entity_ranks"]
     assert ranks.shape == (g["B"],) and (ranks >= 1).all()
+
+
+def test_training_mode_dropout_matches_oracle_with_same_masks(tiny):
+    """Training-mode graph (dropout p = 0.1 at modeling_unimo.py:185, :362, :389, :476): the CUDA path's stateless hash
+    masks are rebuilt in torch (oracle.hash_dropout) and fed to the oracle, so forward, loss and every gradient are
+    compared mask for mask at the usual tolerances; eval mode afterwards is the deterministic graph again."""
+    g, cfg, params, eng, batch = tiny
+    from oracle import mkgformer_oracle as O
+    eng.set_dropout(0.1, 0.1, seed=77)
+    eng.train(True)
+    try:
+        eng.zero_grad()
+        z, _ = eng.forward(batch, want_z=True)
+        seed = eng.last_dropout_seed()
+        loss, ml, _ = eng.head_loss(batch, ft_head(batch, TINY_VOCAB), compute_grad=True, want_logits=True)
+        eng.backward(batch)
+        torch.cuda.synchronize()
+        drop = O.hash_dropout(seed, 0.1, 0.1)
+        Pg = {k: v.cuda().clone().requires_grad_(True) for k, v in params.items()}
+        ref_loss, x, zr = O.finetune_loss(Pg, cfg, batch, TINY_VOCAB.analogy_entity_ids(), alpha=0.43, label_smoothing=0.1, drop=drop)
+        ref_loss.backward()
+        print(f"dropout on: loss cuda {loss.item():.5f} oracle(same masks) {ref_loss.item():.5f} eval-mode {g['ft_loss'].item():.5f}; "
+              f"z rel err {rel(z, zr.detach()):.3e}")
+        assert abs(ref_loss.item() - g["ft_loss"].item()) > 1e-3          # the masks do change the result
+        assert rel(z, zr.detach()) <= 2e-2 and abs(loss.item() - ref_loss.item()) <= 2e-2
+        bad = _compare_grads(eng, {k: v.grad for k, v in Pg.items()}, [])
+        assert not bad, bad[:10]
+        # a second forward draws different masks
+        z2, _ = eng.forward(batch, want_z=True)
+        assert eng.last_dropout_seed() != seed and (z2 - z).abs().max().item() > 1e-3
+    finally:
+        eng.train(False)
+        eng.set_dropout(0.0, 0.0)
+    z3, _ = eng.forward(batch, want_z=True)
+    assert rel(z3.cpu(), g["ft_trans"]) <= 2e-2
