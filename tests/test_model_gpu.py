@@ -77,7 +77,7 @@ def _oracle_grads(cfg, params, batch, pretrain=False):
     return loss.detach(), x, {k: (None if v.grad is None else v.grad.detach()) for k, v in Pg.items()}
 
 
-def _compare_grads(eng, ref_grads, report):
+def _compare_grads(eng, ref_grads, report, tol_main=6e-2, tol_adaptive=0.25):
     bad = []
     # typical per-element gradient magnitude, to recognise gradients that are mathematically zero: e.g. the key bias
     # of an unmasked, unscaled softmax attention shifts every score of a row equally (vision k_proj.bias, layers < 8),
@@ -100,7 +100,7 @@ def _compare_grads(eng, ref_grads, report):
         report.append((e, cos, name))
         # the two adaptive weights are single numbers obtained as a heavily cancelling sum over all (b, h, r, c) of
         # dS * S_raw: bf16 noise on dS does not average out relative to the (small) total
-        tol = 0.25 if "adaptive_weight" in name else 6e-2
+        tol = tol_adaptive if "adaptive_weight" in name else tol_main
         # absolute floor: tensors whose gradient is far below the typical magnitude (e.g. text key.bias without adaptive
         # scaling: zero by softmax shift-invariance except for the small K/V-prefix path of layers >= 7) are column sums
         # of bf16-rounded matrices whose rounding noise does not shrink with the (cancelling) signal
@@ -323,3 +323,36 @@ def test_training_mode_dropout_matches_oracle_with_same_masks(tiny):
         eng.set_dropout(0.0, 0.0)
     z3, _ = eng.forward(batch, want_z=True)
     assert rel(z3.cpu(), g["ft_trans"]) <= 2e-2
+
+
+def test_large_shape_family_vs_oracle():
+    """MKGformer-large shapes (hidden 1024, 16 heads, ViT-L/14 patches: 256 patches/image -> 513 vision tokens, 588-element
+    patch rows that need the padded TMA path) at reduced depth: forward + loss + every gradient against the oracle.
+    With N(0, 0.02) random weights the unscaled fusion softmax of the single fused layer (1024-dim dot products over 513
+    vision tokens) is close to one-hot and amplifies bf16 operand rounding: measured 1.5e-2 on the hidden states and up to
+    9e-2 on that layer's query/key gradients (cosine >= 0.999); a layout bug would show as O(1) error, so the bound here is
+    12e-2 on tensors (cosine checked too) and an absolute floor on the scalar adaptive weights."""
+    from mkg_analogy_b200.engine import Engine
+    from oracle import mkgformer_oracle as O
+    cfg = MKGformerConfig(hidden=1024, layers=9, heads=16, intermediate=4096, vocab=TINY_VOCAB.vocab, max_position=64,
+                          image_size=224, patch=14)
+    params = init_params(cfg, 8)
+    eng = Engine(cfg)
+    eng.load(params)
+    batch = to_cuda(make_finetune_batch(2, 32, cfg.image_size, TINY_VOCAB, seed=5, min_len=20))
+    eng.zero_grad()
+    z, _ = eng.forward(batch)
+    loss, ml, _ = eng.head_loss(batch, ft_head(batch, TINY_VOCAB), want_logits=True)
+    eng.backward(batch)
+    torch.cuda.synchronize()
+    assert eng.status() == 0
+    ref_loss, x, ref_grads = _oracle_grads(cfg, params, batch)
+    with torch.no_grad():
+        _, zr = O.forward({k: v.cuda() for k, v in params.items()}, cfg, batch, full_logits=False)
+    print(f"large family: z rel err {rel(z, zr):.3e}, loss {loss.item():.5f} vs {ref_loss.item():.5f}")
+    assert rel(z, zr) <= 2e-2 and abs(loss.item() - ref_loss.item()) <= 2e-2
+    report = []
+    bad = _compare_grads(eng, ref_grads, report, tol_main=0.12, tol_adaptive=1.0)
+    assert not bad, bad[:10]
+    assert all(cos >= 0.998 for e, cos, name in report if "adaptive_weight" not in name and e > 1e-2), \
+        [(n, c) for e, c, n in report if c < 0.998][:5]
