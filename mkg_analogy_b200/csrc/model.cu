@@ -70,8 +70,9 @@ struct Workspace {
     bf16* esel16; float* bias_sel; float* logits; bf16* dlogits16; float* dzm; float* desel; float* dbias_sel;
     float* dz;                          // gradient wrt trans_hidden_states (B*L, H)
     // backward scratch
-    float *t32a, *t32b, *t32c, *dT; bf16 *t16a, *tF16, *tdqkv16;
-    float *v32a, *v32b, *dV; bf16 *v16a, *dV16, *vF16, *vdqkv16;
+    // dY scratch read by the weight-gradient side streams alternates by layer parity ([2])
+    float *t32a, *t32b, *t32c, *dT; bf16 *t16a[2], *t16b[2], *tF16[2], *tdqkv16[2];
+    float *v32a, *v32b, *dV[2]; bf16 *v16a[2], *dV16[2], *vF16[2], *vdqkv16[2];
     float *dk1, *dv1; float *pbuf, *dsbuf; float *delta, *delta_v;   // delta: text chain, delta_v: vision chain
     bf16* dpatch16;
     size_t bytes = 0;
@@ -102,7 +103,7 @@ struct b200mart_handle {
     // two-chain execution: the vision and text streams of the model are independent below the fusion depth
     // (modeling_unimo.py:616-640), so each runs on its own CUDA stream, ordered by events where they meet
     bool split_streams = true;
-    cudaStream_t sV = nullptr, sT = nullptr;
+    cudaStream_t sV = nullptr, sT = nullptr, sVw = nullptr, sTw = nullptr;
     std::vector<cudaEvent_t> evpool;
     size_t ev_used = 0;
     // optional per-category device timing (CUDA events around each launch group; see b200mart_profile_begin/end)
@@ -118,6 +119,8 @@ struct b200mart_handle {
         for (auto& e : evpool) cudaEventDestroy(e);
         if (sV) cudaStreamDestroy(sV);
         if (sT) cudaStreamDestroy(sT);
+        if (sVw) cudaStreamDestroy(sVw);
+        if (sTw) cudaStreamDestroy(sTw);
     }
 };
 
@@ -286,9 +289,12 @@ void carve(const b200mart_handle* h, int B, int L, void* base, Workspace& w) {
     w.dzm = c.take<float>((size_t)B * H); w.desel = c.take<float>(Vp * H); w.dbias_sel = c.take<float>(Vp);
     w.dz = c.take<float>(Mt * H);
     w.t32a = c.take<float>(Mt * H); w.t32b = c.take<float>(Mt * H); w.t32c = c.take<float>(Mt * H); w.dT = c.take<float>(Mt * H);
-    w.t16a = c.take<bf16>(Mt * H); w.tF16 = c.take<bf16>(Mt * F); w.tdqkv16 = c.take<bf16>(Mt * 3 * H);
-    w.v32a = c.take<float>(Mv * H); w.v32b = c.take<float>(Mv * H); w.dV = c.take<float>(Mv * H);
-    w.v16a = c.take<bf16>(Mv * H); w.dV16 = c.take<bf16>(Mv * H); w.vF16 = c.take<bf16>(Mv * F); w.vdqkv16 = c.take<bf16>(Mv * 3 * H);
+    w.v32a = c.take<float>(Mv * H); w.v32b = c.take<float>(Mv * H);
+    for (int k = 0; k < 2; ++k) {
+        w.t16a[k] = c.take<bf16>(Mt * H); w.t16b[k] = c.take<bf16>(Mt * H); w.tF16[k] = c.take<bf16>(Mt * F); w.tdqkv16[k] = c.take<bf16>(Mt * 3 * H);
+        w.dV[k] = c.take<float>(Mv * H); w.dV16[k] = c.take<bf16>(Mv * H);
+        w.v16a[k] = c.take<bf16>(Mv * H); w.vF16[k] = c.take<bf16>(Mv * F); w.vdqkv16[k] = c.take<bf16>(Mv * 3 * H);
+    }
     w.dk1 = c.take<float>(Mt * H); w.dv1 = c.take<float>(Mt * H);
     w.pbuf = c.take<float>(Mt * Nv); w.dsbuf = c.take<float>(Mt * Nv);
     w.delta = c.take<float>((size_t)B * nh * L);
@@ -403,7 +409,7 @@ struct Run {
 
 // ------------------------------------------------------------------ two-chain stream plumbing
 struct Chains {
-    b200mart_handle* h; cudaStream_t main, v, t; bool split;
+    b200mart_handle* h; cudaStream_t main, v, t, vw, tw; bool split;   // vw / tw: weight-gradient side streams
     int rc = 0;
     // event recorded on `on` (nullptr when the chains share one stream: ordering is implicit)
     cudaEvent_t mark(cudaStream_t on) {
@@ -423,17 +429,21 @@ struct Chains {
 };
 
 int chains_begin(b200mart_handle* h, cudaStream_t s, Chains& c) {
-    c.h = h; c.main = s; c.v = s; c.t = s; c.split = false;
+    c.h = h; c.main = s; c.v = s; c.t = s; c.vw = s; c.tw = s; c.split = false;
     h->ev_used = 0;
     if (!h->split_streams) return 0;
     if (!h->sV) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h->sV, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&h->sT, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->sVw, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->sTw, cudaStreamNonBlocking));
     }
-    c.v = h->sV; c.t = h->sT; c.split = true;
+    c.v = h->sV; c.t = h->sT; c.vw = h->sVw; c.tw = h->sTw; c.split = true;
     cudaEvent_t e = c.mark(s);
     c.wait(c.v, e);
     c.wait(c.t, e);
+    c.wait(c.vw, e);
+    c.wait(c.tw, e);
     return c.rc ? b200mart_set_err(3, "stream fork failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
 }
 
@@ -441,6 +451,8 @@ int chains_end(Chains& c) {
     if (c.split) {
         c.wait(c.main, c.mark(c.v));
         c.wait(c.main, c.mark(c.t));
+        c.wait(c.main, c.mark(c.vw));
+        c.wait(c.main, c.mark(c.tw));
     }
     return c.rc ? b200mart_set_err(3, "stream join failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
 }
@@ -806,47 +818,56 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
         B2_TRY(launch_colsum_bf16(dl16, Vp, r.g32(l.dec_b), Mt, d.vocab, s));
     }
     // ---- head transform backward: z = LN(gelu(T W^T + b))
-    B2_TRY(launch_layernorm_bwd(dz, w.hact, w.hmean, w.hrstd, r.p32(l.trln_w), nullptr, w.hpre16, 1, nullptr, w.t16a,
+    B2_TRY(launch_layernorm_bwd(dz, w.hact, w.hmean, w.hrstd, r.p32(l.trln_w), nullptr, w.hpre16, 1, nullptr, w.t16a[0],
                                 r.g32(l.trln_w), r.g32(l.trln_b), r.g32(l.tr_b), Mt, H, s));
-    B2_TRY(r.grad_weight(Mt, H, H, w.t16a, H, w.T16[D], H, l.tr_w, -1));
-    B2_TRY(r.grad_input(Mt, H, H, w.t16a, l.tr_w, nullptr, 0, nullptr, w.dT, nullptr));
+    B2_TRY(r.grad_weight(Mt, H, H, w.t16a[0], H, w.T16[D], H, l.tr_w, -1));
+    B2_TRY(r.grad_input(Mt, H, H, w.t16a[0], l.tr_w, nullptr, 0, nullptr, w.dT, nullptr));
 
     const bool any_fusion = D > d.fuse_from;
-    // fork: text chain / vision chain (see b200mart_forward); events order the cross-stream gradient hand-offs
+    // fork: text chain / vision chain (see b200mart_forward) plus one weight-gradient side stream per chain: dW = dY^T X
+    // (and the remaining bias column sums) only feed the optimizer, so they leave the dX critical path.  dY scratch
+    // buffers alternate by layer parity; a chain re-uses a buffer only after the side stream has consumed it.
     Chains ch;
     B2_TRY(chains_begin(h, s, ch));
-    const cudaStream_t sv = ch.v, stx = ch.t;
-    Run rv{h, bufs, sv}, rt{h, bufs, stx};
+    const cudaStream_t sv = ch.v, stx = ch.t, svw = ch.vw, stw = ch.tw;
+    Run rv{h, bufs, sv}, rt{h, bufs, stx}, rvw{h, bufs, svw}, rtw{h, bufs, stw};
     std::vector<cudaEvent_t> ev_vdone(D + 1, nullptr), ev_tfus(D, nullptr), ev_tattn(D, nullptr);
+    std::vector<cudaEvent_t> ev_tw_done(D + 2, nullptr), ev_vw_done(D + 2, nullptr);
     const float ph = h->cur_ph, pa = h->cur_pa;      // dropout of the forward whose activations are in the workspace
     const uint32_t seed = h->cur_seed;
     const DropCfg nodrop{0u, 0u, 1.f};
     for (int i = D - 1; i >= 0; --i) {
         const bool fused = i >= d.fuse_from;
+        const int pb = i & 1;                         // parity of this layer's dY scratch set
         // ================= text layer i backward
         {
             const TxtLayerP& p = l.txt[i];
             TxtLayerA& a = w.tl[i];
+            bf16 *t16a = w.t16a[pb], *t16b = w.t16b[pb], *tF16 = w.tF16[pb], *tdqkv16 = w.tdqkv16[pb];
+            ch.wait(stx, ev_tw_done[i + 2]);          // the side stream is done with this parity's buffers
             // output LayerNorm
-            B2_TRY(launch_layernorm_bwd(w.dT, a.opre, a.omean, a.orstd, rt.p32(p.oln_w), nullptr, nullptr, 0, w.t32a, w.t16a,
+            B2_TRY(launch_layernorm_bwd(w.dT, a.opre, a.omean, a.orstd, rt.p32(p.oln_w), nullptr, nullptr, 0, w.t32a, t16a,
                                         rt.g32(p.oln_w), rt.g32(p.oln_b), rt.g32(p.o_b), Mt, H, stx, nodrop, make_drop(ph, seed, 3 + 3 * i)));
-            B2_TRY(rt.grad_weight(Mt, H, F, w.t16a, H, a.i16, F, p.o_w, -1));
+            ch.wait(stw, ch.mark(stx));
+            B2_TRY(rtw.grad_weight(Mt, H, F, t16a, H, a.i16, F, p.o_w, -1));
             // d(pre-GELU) = (dY Wout) * gelu'(pre); its column sums are the intermediate (and fusion_dense) bias gradients
-            B2_TRY(rt.grad_input(Mt, H, F, w.t16a, p.o_w, a.ipre16, 3, nullptr, nullptr, w.tF16, p.i_b, fused ? p.f_b : -1));
-            B2_TRY(rt.grad_weight(Mt, F, H, w.tF16, F, a.a16, H, p.i_w, -1));
-            if (fused) B2_TRY(rt.grad_weight(Mt, F, H, w.tF16, F, a.g16, H, p.f_w, -1));
-            B2_TRY(rt.grad_input(Mt, F, H, w.tF16, p.i_w, nullptr, 0, w.t32a, w.t32b, nullptr));        // d a32 (incl. residual)
-            if (fused) B2_TRY(rt.grad_input(Mt, F, H, w.tF16, p.f_w, nullptr, 0, nullptr, w.t32c, nullptr));  // d fusion output
+            B2_TRY(rt.grad_input(Mt, H, F, t16a, p.o_w, a.ipre16, 3, nullptr, nullptr, tF16, p.i_b, fused ? p.f_b : -1));
+            ch.wait(stw, ch.mark(stx));
+            B2_TRY(rtw.grad_weight(Mt, F, H, tF16, F, a.a16, H, p.i_w, -1));
+            if (fused) B2_TRY(rtw.grad_weight(Mt, F, H, tF16, F, a.g16, H, p.f_w, -1));
+            B2_TRY(rt.grad_input(Mt, F, H, tF16, p.i_w, nullptr, 0, w.t32a, w.t32b, nullptr));        // d a32 (incl. residual)
+            if (fused) B2_TRY(rt.grad_input(Mt, F, H, tF16, p.f_w, nullptr, 0, nullptr, w.t32c, nullptr));  // d fusion output
             // attention-output LayerNorm
-            B2_TRY(launch_layernorm_bwd(w.t32b, a.apre, a.amean, a.arstd, rt.p32(p.aln_w), nullptr, nullptr, 0, w.t32a, w.t16a,
+            B2_TRY(launch_layernorm_bwd(w.t32b, a.apre, a.amean, a.arstd, rt.p32(p.aln_w), nullptr, nullptr, 0, w.t32a, t16b,
                                         rt.g32(p.aln_w), rt.g32(p.aln_b), rt.g32(p.ao_b), Mt, H, stx, nodrop, make_drop(ph, seed, 2 + 3 * i)));
-            B2_TRY(rt.grad_weight(Mt, H, H, w.t16a, H, a.ctx16, H, p.ao_w, -1));
-            B2_TRY(rt.grad_input(Mt, H, H, w.t16a, p.ao_w, nullptr, 0, nullptr, w.t32b, nullptr));      // d ctx
+            ch.wait(stw, ch.mark(stx));
+            B2_TRY(rtw.grad_weight(Mt, H, H, t16b, H, a.ctx16, H, p.ao_w, -1));
+            B2_TRY(rt.grad_input(Mt, H, H, t16b, p.ao_w, nullptr, 0, nullptr, w.t32b, nullptr));      // d ctx
             // dV (gradient wrt the vision output of layer i) and dk1/dv1 come from vision layer i+1's backward
-            if (i + 1 < D && i + 1 >= d.fuse_from - 0 && (fused || i + 1 >= d.fuse_from)) ch.wait(stx, ev_vdone[i + 1]);
+            if (i + 1 < D && i + 1 >= d.fuse_from) ch.wait(stx, ev_vdone[i + 1]);
             if (fused) {
                 { ProfScope ps(h, stx, CAT_FUSION); B2_TRY(launch_fusion_bwd_rows(w.t32c, a.ctx32, w.V32[i + 1], a.flse, w.pbuf, w.dsbuf, w.t32b, B, L, Nv, H, stx)); }
-                { ProfScope ps(h, stx, CAT_FUSION); B2_TRY(launch_fusion_bwd_keys(w.t32c, a.ctx32, w.pbuf, w.dsbuf, (i == D - 1) ? nullptr : w.dV, w.dV, w.dV16, B, L, Nv, H, stx)); }
+                { ProfScope ps(h, stx, CAT_FUSION); B2_TRY(launch_fusion_bwd_keys(w.t32c, a.ctx32, w.pbuf, w.dsbuf, (i == D - 1) ? nullptr : w.dV[pb], w.dV[pb], w.dV16[pb], B, L, Nv, H, stx)); }
             }
             if (fused) ev_tfus[i] = ch.mark(stx);      // dV / dV16 now include this layer's fusion contribution
             AttnBwd ab{};
@@ -859,28 +880,37 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             at.lse = a.lse;
             at.drop = make_drop(pa, seed, 1 + 3 * i);
             ab.dout = w.t32b; ab.lddo = H;
-            ab.dq = w.tdqkv16; ab.dk2 = w.tdqkv16 + H; ab.dv2 = w.tdqkv16 + 2 * H; ab.ldd = 3 * H;
+            ab.dq = tdqkv16; ab.dk2 = tdqkv16 + H; ab.dv2 = tdqkv16 + 2 * H; ab.ldd = 3 * H;
             if (i + 1 < D && i + 1 >= d.fuse_from) { ab.dk2_add = w.dk1; ab.dv2_add = w.dv1; ab.ldadd = H; }   // from vision layer i+1
             { ProfScope ps(h, stx, CAT_ATTN); B2_TRY(launch_attention_bwd(ab, a.ctx16, H, w.delta, stx)); }
             if (ab.dk2_add) ev_tattn[i] = ch.mark(stx);   // dk1/dv1 consumed: vision layer i may overwrite them
-            B2_TRY(rt.grad_weight(Mt, 3 * H, H, w.tdqkv16, 3 * H, w.T16[i], H, p.qkv_w, p.qkv_b));
-            B2_TRY(rt.grad_input(Mt, 3 * H, H, w.tdqkv16, p.qkv_w, nullptr, 0, w.t32a, w.dT, nullptr));  // d T^i
+            ch.wait(stw, ch.mark(stx));
+            B2_TRY(rtw.grad_weight(Mt, 3 * H, H, tdqkv16, 3 * H, w.T16[i], H, p.qkv_w, p.qkv_b));
+            B2_TRY(rt.grad_input(Mt, 3 * H, H, tdqkv16, p.qkv_w, nullptr, 0, w.t32a, w.dT, nullptr));  // d T^i
+            ev_tw_done[i] = ch.mark(stw);
         }
         // ================= vision layer i backward (only reached by gradient through the fusion / KV-prefix paths)
         if (any_fusion) {
             const VisLayerP& p = l.vis[i];
             VisLayerA& a = w.vl[i];
+            const int qb = (i + 1) & 1;               // parity of the gradient buffer this layer hands to layer i-1
+            float* dVin = w.dV[pb]; bf16* dVin16 = w.dV16[pb];
+            bf16 *v16a = w.v16a[pb], *vF16 = w.vF16[pb], *vdqkv16 = w.vdqkv16[pb];
             if (fused) ch.wait(sv, ev_tfus[i]);
+            ch.wait(sv, ev_vw_done[i + 2]);
             // fc2 bias gradient = column sums of dV: fused into the LayerNorm-1 backward of layer i+1 when no text-layer
             // fusion adds into dV afterwards (i < fuse_from), a column-sum pass otherwise
-            B2_TRY(rv.grad_weight(Mv, H, F, w.dV16, H, a.h16, F, p.fc2_w, fused ? p.fc2_b : -1));
-            B2_TRY(rv.grad_input(Mv, H, F, w.dV16, p.fc2_w, a.pre16, 3, nullptr, nullptr, w.vF16, p.fc1_b));
-            B2_TRY(rv.grad_weight(Mv, F, H, w.vF16, F, a.u2_16, H, p.fc1_w, -1));
-            B2_TRY(rv.grad_input(Mv, F, H, w.vF16, p.fc1_w, nullptr, 0, nullptr, w.v32a, nullptr));
-            B2_TRY(launch_layernorm_bwd(w.v32a, a.x1, a.mean2, a.rstd2, rv.p32(p.ln2_w), w.dV, nullptr, 0, w.v32b, w.v16a,
+            ch.wait(svw, ch.mark(sv));
+            B2_TRY(rvw.grad_weight(Mv, H, F, dVin16, H, a.h16, F, p.fc2_w, fused ? p.fc2_b : -1));
+            B2_TRY(rv.grad_input(Mv, H, F, dVin16, p.fc2_w, a.pre16, 3, nullptr, nullptr, vF16, p.fc1_b));
+            ch.wait(svw, ch.mark(sv));
+            B2_TRY(rvw.grad_weight(Mv, F, H, vF16, F, a.u2_16, H, p.fc1_w, -1));
+            B2_TRY(rv.grad_input(Mv, F, H, vF16, p.fc1_w, nullptr, 0, nullptr, w.v32a, nullptr));
+            B2_TRY(launch_layernorm_bwd(w.v32a, a.x1, a.mean2, a.rstd2, rv.p32(p.ln2_w), dVin, nullptr, 0, w.v32b, v16a,
                                         rv.g32(p.ln2_w), rv.g32(p.ln2_b), rv.g32(p.o_b), Mv, H, sv));
-            B2_TRY(rv.grad_weight(Mv, H, H, w.v16a, H, a.ctx16, H, p.o_w, -1));
-            B2_TRY(rv.grad_input(Mv, H, H, w.v16a, p.o_w, nullptr, 0, nullptr, w.v32a, nullptr));
+            ch.wait(svw, ch.mark(sv));
+            B2_TRY(rvw.grad_weight(Mv, H, H, v16a, H, a.ctx16, H, p.o_w, -1));
+            B2_TRY(rv.grad_input(Mv, H, H, v16a, p.o_w, nullptr, 0, nullptr, w.v32a, nullptr));
             AttnBwd ab{};
             AttnFwd& at = ab.f;
             at.q = a.qkv16; at.ldq = 3 * H;
@@ -889,19 +919,24 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             at.B = B; at.Lq = Nv; at.nh = nh; at.scale = 0.125f;
             at.lse = a.lse;
             ab.dout = w.v32a; ab.lddo = H;
-            ab.dq = w.vdqkv16; ab.dk2 = w.vdqkv16 + H; ab.dv2 = w.vdqkv16 + 2 * H; ab.ldd = 3 * H;
+            ab.dq = vdqkv16; ab.dk2 = vdqkv16 + H; ab.dv2 = vdqkv16 + 2 * H; ab.ldd = 3 * H;
             if (fused) { ab.dk1 = w.dk1; ab.dv1 = w.dv1; ab.ldd1 = H; ch.wait(sv, ev_tattn[i]); }
             { ProfScope ps(h, sv, CAT_ATTN); B2_TRY(launch_attention_bwd(ab, a.ctx16, H, w.delta_v, sv)); }
-            B2_TRY(rv.grad_weight(Mv, 3 * H, H, w.vdqkv16, 3 * H, a.u16, H, p.qkv_w, p.qkv_b));
-            B2_TRY(rv.grad_input(Mv, 3 * H, H, w.vdqkv16, p.qkv_w, nullptr, 0, nullptr, w.v32a, nullptr));
-            B2_TRY(launch_layernorm_bwd(w.v32a, w.V32[i], a.mean1, a.rstd1, rv.p32(p.ln1_w), w.v32b, nullptr, 0, w.dV, w.dV16,
+            ch.wait(svw, ch.mark(sv));
+            B2_TRY(rvw.grad_weight(Mv, 3 * H, H, vdqkv16, 3 * H, a.u16, H, p.qkv_w, p.qkv_b));
+            B2_TRY(rv.grad_input(Mv, 3 * H, H, vdqkv16, p.qkv_w, nullptr, 0, nullptr, w.v32a, nullptr));
+            ev_vw_done[i] = ch.mark(svw);
+            ch.wait(sv, ev_vw_done[i + 1]);           // dV16[qb] was layer i+1's input: its dW(fc2) must have read it
+            B2_TRY(launch_layernorm_bwd(w.v32a, w.V32[i], a.mean1, a.rstd1, rv.p32(p.ln1_w), w.v32b, nullptr, 0, w.dV[qb], w.dV16[qb],
                                         rv.g32(p.ln1_w), rv.g32(p.ln1_b),
                                         (i >= 1 && i - 1 < d.fuse_from) ? rv.g32(l.vis[i - 1].fc2_b) : nullptr, Mv, H, sv));
             ev_vdone[i] = ch.mark(sv);
         }
-        if (layer_events) {   // layer i's gradients are final once both chains pass this point
-            CUDA_TRY(cudaEventRecord((cudaEvent_t)layer_events[2 * i], stx));
-            CUDA_TRY(cudaEventRecord((cudaEvent_t)layer_events[2 * i + 1], any_fusion ? sv : stx));
+        if (layer_events) {   // layer i's gradients are final once both chains AND both side streams pass this point
+            ch.wait(stw, ch.mark(stx));
+            CUDA_TRY(cudaEventRecord((cudaEvent_t)layer_events[2 * i], stw));
+            if (any_fusion) ch.wait(svw, ch.mark(sv));
+            CUDA_TRY(cudaEventRecord((cudaEvent_t)layer_events[2 * i + 1], any_fusion ? svw : stw));
         }
     }
     // ---- embeddings
@@ -909,7 +944,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
                                 rt.g32(l.eln_w), rt.g32(l.eln_b), nullptr, Mt, H, stx, make_drop(ph, seed, 0), nodrop));
     B2_TRY(launch_text_embed_bwd(w.t32a, batch->input_ids, batch->token_type_ids, rt.g32(l.word), rt.g32(l.tpos), rt.g32(l.ttype), B, L, H, stx));
     if (any_fusion) {
-        B2_TRY(launch_layernorm_bwd(w.dV, w.vx0, w.vmean0, w.vrstd0, rv.p32(l.preln_w), nullptr, nullptr, 0, w.v32a, nullptr,
+        B2_TRY(launch_layernorm_bwd(w.dV[1], w.vx0, w.vmean0, w.vrstd0, rv.p32(l.preln_w), nullptr, nullptr, 0, w.v32a, nullptr,
                                     rv.g32(l.preln_w), rv.g32(l.preln_b), nullptr, Mv, H, sv));
         B2_TRY(launch_vision_embed_bwd(w.v32a, rv.g32(l.cls), rv.g32(l.vpos), w.dpatch16, B, P, H, sv));
         B2_TRY(rv.grad_weight(B * 2 * P, H, h->patch_dim, w.dpatch16, H, w.patches16, h->patch_ld, l.patch_w, -1));
