@@ -60,7 +60,8 @@ struct SmemLayout {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN >= 256) ? 4 : ((BN >= 128) ? 5 : 6);
+    // as deep as 227 KB allows: the ring has to cover the TMA round trip (~1 us) at one stage per 128-512 MMA cycles
+    static constexpr int STAGES = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
     static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
     static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;

@@ -16,6 +16,8 @@ shapes = [
     ("t.o dX", Mt, F, H, 0, 1, "dact", 1), ("t.int dX", Mt, H, F, 0, 1, "res", 1),
     ("v.fc2 dW", H, F, Mv, 1, 1, "acc", 1), ("v.fc1 dW", F, H, Mv, 1, 1, "acc", 1), ("v.qkv dW", 3 * H, H, Mv, 1, 1, "acc", 2),
     ("v.out dW", H, H, Mv, 1, 1, "acc", 4), ("t.qkv dW", 3 * H, H, Mt, 1, 1, "acc", 2), ("t.out dW", H, H, Mt, 1, 1, "acc", 4),
+    ("v.fc1 dW s2", F, H, Mv, 1, 1, "acc", 2), ("v.fc1 dW s4", F, H, Mv, 1, 1, "acc", 4), ("v.qkv dW s4", 3 * H, H, Mv, 1, 1, "acc", 4),
+    ("v.out dW s8", H, H, Mv, 1, 1, "acc", 8), ("t.int dW s2", F, H, Mt, 1, 1, "acc", 2),
 ]
 
 
@@ -57,7 +59,7 @@ def run(name, M, N, K, a_mn, b_mn, kind, split, bn, iters=20):
 if __name__ == "__main__":
     print(f"{'shape':12s} {'M':>5s} {'N':>5s} {'K':>5s}  " + "  ".join(f"bn={b:3d} us / TF" for b in (64, 128, 256, 0)))
     if "--few" in sys.argv:
-        shapes = [s for s in shapes if s[0] in ("t.qkv fwd", "v.out fwd", "v.fc2 dX", "v.fc1 dW")]
+        shapes = [s for s in shapes if "dW" in s[0] or s[0] in ("t.qkv fwd", "v.out fwd")]
     for sh in shapes:
         res = [run(*sh, bn) for bn in (64, 128, 256, 0)]
         print(f"{sh[0]:12s} {sh[1]:5d} {sh[2]:5d} {sh[3]:5d}  " + "  ".join(f"{us:8.1f} / {tf:5.0f}" for us, tf in res), flush=True)
