@@ -39,7 +39,8 @@ def config_dict(n_gpus):
     return {"workload": "MKGformer-base MARS fine-tune step (fwd + LS-CE/relaxation loss + bwd + AdamW), synthetic batch",
             "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * n_gpus, "seq_len": SEQ_LEN, "image": "2x3x224x224",
             "score_head": "2063 analogy entities of a 42007-token vocab", "params_M": 234.7,
-            "parallelism": f"dp{n_gpus}" + ("" if n_gpus == 1 else " (flat fp32 gradient mean all-reduce per layer extent, overlapped with backward)"),
+            "parallelism": f"dp{n_gpus}" + ("" if n_gpus == 1 else " (flat fp32 gradient mean all-reduce per layer extent, pipelined behind backward)"),
+            "optimizer": "AdamW per layer extent, pipelined behind the backward of the layers below",
             "dropout": "hidden 0.1 / attention 0.1 (BERT stream, as the reference trains)",
             "l2": "per-step working set (0.47 GB bf16 weights + >1 GB activations) exceeds the 126 MB L2; 4 rotating batches"}
 
@@ -249,11 +250,11 @@ def run_cuda(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--no-overlap", action="store_true", help="N>1: all-reduce after backward instead of overlapped with it")
+    ap.add_argument("--no-overlap", action="store_true", help="run the gradient exchange / AdamW after backward instead of pipelined per layer")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -186,10 +186,12 @@ int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers* bufs, cons
 /* torch.optim.AdamW step as configured at transformer.py:224-241 over the flat buffers, refreshing the bf16
  * mirror.  `step` is 1-based.  Parameters the reference never gives a gradient (text_pooler, vision_post_layernorm,
  * fusion_dense of text layers < fuse_from; in pre-training also adaptive_weight) are left untouched, as torch skips
- * parameters whose .grad is None. */
-int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* params16, const float* grads32, float* exp_avg,
+ * parameters whose .grad is None.  [begin, end) restricts the update to a flat range (end <= 0: whole buffer) so that a
+ * layer can be updated as soon as its gradients are final (b200mart_layer_extent + layer_events); zero_grads clears the
+ * gradient range after use (the next step accumulates into it). */
+int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* params16, float* grads32, float* exp_avg,
                        float* exp_avg_sq, int32_t step, float lr, float beta1, float beta2, float eps,
-                       float weight_decay, int32_t pretrain, void* stream);
+                       float weight_decay, int32_t pretrain, int64_t begin, int64_t end, int32_t zero_grads, void* stream);
 
 /* Device-side status flags of the last calls on this workspace (synchronises the stream):
  * bit0 token id out of range, bit1 token type out of range, bit2 a row without exactly one [MASK]. */

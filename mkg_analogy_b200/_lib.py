@@ -103,7 +103,7 @@ SYMBOLS = {
     "b200mart_set_option": (i32, [vp, C.c_char_p, i32]),
     "b200mart_set_dropout": (i32, [vp, f32, f32, C.c_uint32]),
     "b200mart_last_dropout_seed": (C.c_uint32, [vp]),
-    "b200mart_adamw": (i32, [vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, i32, vp]),
+    "b200mart_adamw": (i32, [vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, i32, i64, i64, i32, vp]),
     "b200mart_status": (i32, [vp, C.POINTER(Buffers), vp, C.POINTER(i32)]),
     "b200mart_attention_fwd": (i32, [C.POINTER(AttnDesc), vp]),
     "b200mart_attention_bwd": (i32, [C.POINTER(AttnDesc), vp]),

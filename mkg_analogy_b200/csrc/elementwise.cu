@@ -357,13 +357,14 @@ __global__ void scatter_add_kernel(const float* __restrict__ src, const int64_t*
 }
 
 // ---------------------------------------------------------------- AdamW (torch.optim.AdamW semantics)
-__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+__global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, bf16* __restrict__ p16, const AdamSeg* __restrict__ segs, int nseg,
-                             long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2) {
+                             long begin, long n, int zero_grads, float lr, float b1, float b2, float eps, float wd, float bc1,
+                             float bc2) {
     // one block per 4096-element chunk; the owning segment is found by binary search on the chunk start
     // (segments are aligned to 8 elements and chunks never straddle an unaligned boundary element-wise: each
     // thread re-checks its own element range).
-    const long base = (long)blockIdx.x * 4096;
+    const long base = begin + (long)blockIdx.x * 4096;     // processes the flat range [begin, n)
     for (int it = 0; it < 4; ++it) {
         const long i = base + ((long)it * blockDim.x + threadIdx.x) * 4;
         if (i >= n) return;
@@ -390,6 +391,7 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 #undef ADAM1
             st4(p + i, pv); st4(m + i, mv); st4(v + i, vv);
         }
+        if (zero_grads) st4(g + i, make_float4(0.f, 0.f, 0.f, 0.f));   // the next step accumulates into a clean buffer
         if (p16) st4_bf16(p16 + i, pv);
     }
 }
@@ -525,11 +527,12 @@ int launch_scatter_add_f32(const float* src, const int64_t* idx, float* dst, int
     B2_LAUNCHED();
     return 0;
 }
-int launch_adamw(float* p, const float* g, float* m, float* v, bf16* p16, const AdamSeg* segs_dev, int nseg, long n,
-                 float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, cudaStream_t s) {
-    B2_CHECK(n % 8 == 0, "adamw: flat length %ld must be a multiple of 8", n);
-    const long blocks = (n + 4095) / 4096;
-    adamw_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, g, m, v, p16, segs_dev, nseg, n, lr, b1, b2, eps, wd, bc1, bc2);
+int launch_adamw(float* p, float* g, float* m, float* v, bf16* p16, const AdamSeg* segs_dev, int nseg, long begin, long end,
+                 int zero_grads, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, cudaStream_t s) {
+    B2_CHECK(begin % 8 == 0 && end % 8 == 0 && begin < end, "adamw: range [%ld, %ld) must be non-empty and 8-aligned", begin, end);
+    const long blocks = (end - begin + 4095) / 4096;
+    adamw_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, g, m, v, p16, segs_dev, nseg, begin, end, zero_grads, lr, b1, b2, eps, wd,
+                                                  bc1, bc2);
     B2_LAUNCHED();
     return 0;
 }

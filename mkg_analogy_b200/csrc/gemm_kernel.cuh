@@ -412,6 +412,209 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a 2-CTA cluster computes one 256 x 256 output tile per step of its tile loop.  Each CTA
+// loads its own 128 rows of A and HALF (128 rows) of the B tile, so the operand traffic per FLOP is half that of the
+// single-CTA 128 x 256 tile; the leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256) that reads both
+// CTAs' shared memory and writes both CTAs' tensor memory.  Same roles and epilogue as above; barriers:
+//   full[s]   leader only: transaction bytes of all four loads of a stage (both CTAs signal the leader's barrier)
+//   empty[s]  both CTAs:   multicast tcgen05.commit from the leader frees the stage in both
+//   tfull[b]  both CTAs:   multicast commit when the accumulator of a tile is complete
+//   tempty[b] leader only: 8 arrivals (4 epilogue warps x 2 CTAs) before the MMA thread may overwrite buffer b
+struct PairLayout {
+    static constexpr int BN_CTA = 128;                  // B rows loaded per CTA
+    static constexpr int BN_TILE = 256;                 // accumulator columns per CTA
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN_CTA * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = 6;
+    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+    static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+    static constexpr int TMEM_COLS = 2 * BN_TILE;       // 512: two accumulator buffers
+};
+
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                       const GemmDev p) {
+    using L = PairLayout;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (L::STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * L::STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * L::STAGES + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * L::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 = leader
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int num_tiles = p.mt * p.nt * p.nsplit;     // mt counts 256-row blocks here
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < L::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_2cta(tmem_slot, L::TMEM_COLS);
+        tmem_relinquish_2cta();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // the peer's barriers are initialised before anything may signal them
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    auto tile_coords = [&](int t, int& m0, int& n0, int& kb_begin, int& kb_end) {
+        const int mb = t % p.mt;
+        const int rest = t / p.mt;
+        const int nb = rest % p.nt;
+        const int z = rest / p.nt;
+        m0 = mb * 2 * BM + (int)rank * BM;            // this CTA's 128 rows of the 256-row pair tile
+        n0 = nb * L::BN_TILE;
+        kb_begin = z * p.kb_per;
+        kb_end = min(p.kb_total, kb_begin + p.kb_per);
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = pair; t < num_tiles; t += npairs) {
+                int m0, n0, kb_begin, kb_end;
+                tile_coords(t, m0, n0, kb_begin, kb_end);
+                const int nb0 = n0 + (int)rank * L::BN_CTA;      // this CTA's half of the B tile
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sA = smem_base + stage * L::STAGE_BYTES;
+                    const uint32_t sB = sA + L::A_BYTES;
+                    if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
+                    const bool second = kb >= p.kb1;
+                    const CUtensorMap* ma = second ? &tmA2 : &tmA;
+                    const CUtensorMap* mb = second ? &tmB2 : &tmB;
+                    const int k0 = (second ? kb - p.kb1 : kb) * BK;
+                    if (!A_MN) {
+                        tma_load_2d_2cta(sA, ma, full_bar(stage), k0, m0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BM / 64; ++c)
+                            tma_load_2d_2cta(sA + c * (BK * 128), ma, full_bar(stage), m0 + c * 64, k0);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d_2cta(sB, mb, full_bar(stage), k0, nb0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < L::BN_CTA / 64; ++c)
+                            tma_load_2d_2cta(sB + c * (BK * 128), mb, full_bar(stage), nb0 + c * 64, k0);
+                    }
+                    if (++stage == L::STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread of the LEADER CTA) =====================
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, L::BN_TILE, A_MN, B_MN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = pair; t < num_tiles; t += npairs) {
+                int m0, n0, kb_begin, kb_end;
+                tile_coords(t, m0, n0, kb_begin, kb_end);
+                if (kb_end <= kb_begin) continue;
+                const int ab = it & 1;
+                const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+                ++it;
+                mbar_wait(tempty_bar(ab), aph ^ 1u);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(ab * L::BN_TILE);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_base + stage * L::STAGE_BYTES;
+                    const uint32_t sB = sA + L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = A_MN ? umma_desc_sw128(sA + k * 2048, BK * 128, 1024)
+                                                 : umma_desc_sw128(sA + k * 32, 16, 1024);
+                        const uint64_t db = B_MN ? umma_desc_sw128(sB + k * 2048, BK * 128, 1024)
+                                                 : umma_desc_sw128(sB + k * 32, 16, 1024);
+                        umma_bf16_2cta(tacc, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_2cta_mc(empty_bar(stage));     // frees the stage in both CTAs
+                    if (++stage == L::STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit_2cta_mc(tfull_bar(ab));            // accumulator complete, in both CTAs
+            }
+        }
+    } else {
+        // ===================== epilogue (4 warps in each CTA) =====================
+        const int quad = warp & 3;
+        float* stg = reinterpret_cast<float*>(smem_gen + L::EPI_OFFSET) + (warp - 2) * 32 * EPI_LD;
+        int it = 0;
+        for (int t = pair; t < num_tiles; t += npairs) {
+            int m0, n0, kb_begin, kb_end;
+            tile_coords(t, m0, n0, kb_begin, kb_end);
+            if (kb_end <= kb_begin) continue;
+            const int ab = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            ++it;
+            const int row0 = m0 + quad * 32;
+            const int nrows = min(32, p.M - row0);
+            EpiIn<EPI> cur;
+            cur.load(p, row0, nrows, n0, lane);
+            mbar_wait(tfull_bar(ab), aph);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * L::BN_TILE);
+#pragma unroll 1
+            for (int c = 0; c < L::BN_TILE / EPI_COLS; ++c) {
+                if (c > 0) cur.load(p, row0, nrows, n0 + c * EPI_COLS, lane);
+                uint32_t r[EPI_COLS];
+                tmem_ld32(tacc + (uint32_t)(c * EPI_COLS), r);
+                tmem_ld32(tacc + (uint32_t)(c * EPI_COLS + 32), r + 32);
+                tmem_ld_wait();
+                if (c == L::BN_TILE / EPI_COLS - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(tempty_bar(ab));
+                }
+                const int col0 = n0 + c * EPI_COLS;
+                if (col0 >= p.N || nrows <= 0) continue;
+#pragma unroll
+                for (int j = 0; j < EPI_COLS; ++j) stg[lane * EPI_LD + j] = __uint_as_float(r[j]);
+                __syncwarp();
+                epilogue_block<EPI>(p, stg, cur, row0, nrows, col0, lane);
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // neither CTA may leave (or free tensor memory) while the pair's MMAs / signals are in flight
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, L::TMEM_COLS);
+    }
+}
+
 typedef void (*GemmKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmDev);
 
 // the (layout, epilogue) combinations the model uses get a specialised kernel; everything else is GENERIC
@@ -445,6 +648,29 @@ inline GemmKernel pick_kernel_bn(int a_mn, int b_mn, int epi) {
     return gemm_bf16_tcgen05<BN, true, false, EPI_GENERIC>;
 }
 
+// CTA-pair kernels: instantiated for the (layout, epilogue) combinations of the model's large products
+inline GemmKernel pick_kernel_pair(int a_mn, int b_mn, int epi) {
+    if (!a_mn && !b_mn) {
+        switch (epi) {
+            case EPI_BF16: return gemm_bf16_tcgen05_pair<false, false, EPI_BF16>;
+            case EPI_ACT: return gemm_bf16_tcgen05_pair<false, false, EPI_ACT>;
+            case EPI_RES: return gemm_bf16_tcgen05_pair<false, false, EPI_RES>;
+            case EPI_F32: return gemm_bf16_tcgen05_pair<false, false, EPI_F32>;
+            default: return nullptr;
+        }
+    }
+    if (!a_mn && b_mn) {
+        switch (epi) {
+            case EPI_DACT: return gemm_bf16_tcgen05_pair<false, true, EPI_DACT>;
+            case EPI_RES: return gemm_bf16_tcgen05_pair<false, true, EPI_RES>;
+            case EPI_F32: return gemm_bf16_tcgen05_pair<false, true, EPI_F32>;
+            default: return nullptr;
+        }
+    }
+    if (a_mn && b_mn && epi == EPI_ACC) return gemm_bf16_tcgen05_pair<true, true, EPI_ACC>;
+    return nullptr;
+}
+
 // true when pick_kernel_bn has a specialised kernel for this combination
 inline bool has_specialised(int a_mn, int b_mn, int epi) {
     if (epi == EPI_GENERIC) return true;
@@ -460,3 +686,4 @@ inline bool has_specialised(int a_mn, int b_mn, int epi) {
 gemmk::GemmKernel gemm_pick_kernel_64(int a_mn, int b_mn, int epi);
 gemmk::GemmKernel gemm_pick_kernel_128(int a_mn, int b_mn, int epi);
 gemmk::GemmKernel gemm_pick_kernel_256(int a_mn, int b_mn, int epi);
+gemmk::GemmKernel gemm_pick_kernel_pair(int a_mn, int b_mn, int epi);   // gemm_inst_pair.cu

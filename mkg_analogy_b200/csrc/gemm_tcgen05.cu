@@ -63,6 +63,7 @@ struct GemmPlan {
     int smem;
     GemmKernel kernel;
     double flops;
+    bool pair;      // CTA-pair kernel: launched as 2-CTA clusters
 };
 
 int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
@@ -113,7 +114,13 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
             if (best < 0 || cost <= best) { best = cost; bn = cand; }
         }
     }
-    B2_CHECK(bn == 64 || bn == 128 || bn == 256, "gemm: unsupported N tile %d", bn);
+    B2_CHECK(bn == 64 || bn == 128 || bn == 256 || bn == 512, "gemm: unsupported N tile %d (64, 128, 256, or 512 = 256x256 CTA pair)", bn);
+    const bool pair = (bn == 512);
+    if (pair) {
+        B2_CHECK(gemm_pick_kernel_pair(op.a_mn, op.b_mn, epi) != nullptr,
+                 "gemm: no CTA-pair kernel for layout (%d,%d) / epilogue kind %d", op.a_mn, op.b_mn, epi);
+        bn = 128;    // rows of B each CTA of the pair loads
+    }
     GemmPlan* p = new GemmPlan();
     memset(p, 0, sizeof(*p));
     int rc = 0;
@@ -154,7 +161,16 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
     d.nt = (op.N + bn - 1) / bn;
     const long tiles = (long)d.mt * d.nt * split;
     p->grid = dim3((unsigned)(tiles < num_sms() ? tiles : num_sms()), 1, 1);
-    if (bn == 64) { p->kernel = gemm_pick_kernel_64(op.a_mn, op.b_mn, epi); p->smem = SmemLayout<64>::TOTAL; }
+    p->pair = pair;
+    if (pair) {
+        d.mt = (op.M + 2 * BM - 1) / (2 * BM);
+        d.nt = (op.N + PairLayout::BN_TILE - 1) / PairLayout::BN_TILE;
+        const long ptiles = (long)d.mt * d.nt * split;
+        const long pairs = num_sms() / 2;
+        p->grid = dim3((unsigned)(2 * (ptiles < pairs ? ptiles : pairs)), 1, 1);
+        p->kernel = gemm_pick_kernel_pair(op.a_mn, op.b_mn, epi);
+        p->smem = PairLayout::TOTAL;
+    } else if (bn == 64) { p->kernel = gemm_pick_kernel_64(op.a_mn, op.b_mn, epi); p->smem = SmemLayout<64>::TOTAL; }
     else if (bn == 128) { p->kernel = gemm_pick_kernel_128(op.a_mn, op.b_mn, epi); p->smem = SmemLayout<128>::TOTAL; }
     else { p->kernel = gemm_pick_kernel_256(op.a_mn, op.b_mn, epi); p->smem = SmemLayout<256>::TOTAL; }
     cudaError_t e = cudaFuncSetAttribute((const void*)p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem);
@@ -173,6 +189,23 @@ void gemm_plan_destroy(GemmPlan* p) { delete p; }
 double gemm_plan_flops(const GemmPlan* p) { return p->flops; }
 
 int gemm_plan_launch(const GemmPlan* p, cudaStream_t stream, const DropCfg* drop) {
+    if (p->pair) {
+        GemmDev dev = p->dev;
+        if (drop) dev.drop = *drop;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = p->grid;
+        cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = (size_t)p->smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, p->kernel, p->tmA, p->tmB, p->tmA2, p->tmB2, dev));
+        ++g_b200mart_launches;
+        return 0;
+    }
     if (drop) {   // per-step dropout seed: the plan (tensor maps, geometry) is reused, only the mask seed changes
         GemmDev dev = p->dev;
         dev.drop = *drop;

@@ -43,8 +43,9 @@ int launch_scatter_add_rows_f32(const float* src, const int64_t* idx, float* dst
 int launch_scatter_add_f32(const float* src, const int64_t* idx, float* dst, int R, cudaStream_t s);
 // AdamW over a flat buffer with per-segment flags (lit_models/transformer.py:224-241)
 struct AdamSeg { long begin, end; int decay; int skip; };
-int launch_adamw(float* p, const float* g, float* m, float* v, bf16* p16, const AdamSeg* segs_dev, int nseg, long n,
-                 float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, cudaStream_t s);
+// over the flat range [begin, end); zero_grads: clear g after use
+int launch_adamw(float* p, float* g, float* m, float* v, bf16* p16, const AdamSeg* segs_dev, int nseg, long begin, long end,
+                 int zero_grads, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, cudaStream_t s);
 
 // ---- attention_mma.cu (self-attention) / attention.cu (fusion)
 struct AttnFwd {

@@ -965,10 +965,13 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
 }
 
 // --------------------------------------------------------------------------------------- optimizer
-extern "C" int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* params16, const float* grads32, float* exp_avg,
+extern "C" int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* params16, float* grads32, float* exp_avg,
                                   float* exp_avg_sq, int32_t step, float lr, float beta1, float beta2, float eps,
-                                  float weight_decay, int32_t pretrain, void* stream) {
+                                  float weight_decay, int32_t pretrain, int64_t begin, int64_t end, int32_t zero_grads,
+                                  void* stream) {
     B2_CHECK(h && params32 && grads32 && exp_avg && exp_avg_sq && step >= 1, "adamw: bad arguments");
+    if (end <= 0) end = h->lay.total;
+    B2_CHECK(begin >= 0 && begin < end && end <= h->lay.total, "adamw: bad range [%ld, %ld)", (long)begin, (long)end);
     const int mode = pretrain ? 1 : 0;
     if (!h->segs_dev[mode]) {   // tiny one-off table: parameter extents + decay / skip flags
         CUDA_TRY(cudaMalloc(&h->segs_dev[mode], sizeof(AdamSeg) * h->nseg));
@@ -977,7 +980,7 @@ extern "C" int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* par
     const double bc1d = 1.0 - pow((double)beta1, (double)step), bc2d = 1.0 - pow((double)beta2, (double)step);
     const float bc1 = (float)bc1d, bc2 = (float)bc2d;
     return launch_adamw(params32, grads32, exp_avg, exp_avg_sq, reinterpret_cast<bf16*>(params16), h->segs_dev[mode],
-                        h->nseg, h->lay.total, lr, beta1, beta2, eps, weight_decay, bc1, bc2, (cudaStream_t)stream);
+                        h->nseg, begin, end, zero_grads, lr, beta1, beta2, eps, weight_decay, bc1, bc2, (cudaStream_t)stream);
 }
 
 // --------------------------------------------------------------------------------------- profiling

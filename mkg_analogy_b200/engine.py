@@ -273,7 +273,9 @@ class Engine:
         _lib.check(self.l.b200mart_backward(self.h, C.byref(bufs), C.byref(cb), int(use_head_grad), _lib.ptr(dz),
                                             _lib.ptr(dlogits), _lib.ptr(scratch), evs, _lib.cur_stream()))
 
-    def adamw(self, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, pretrain=False):
+    def adamw(self, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, pretrain=False, begin=0, end=0,
+              zero_grads=False):
+        """AdamW over the flat range [begin, end) (default: everything) on the current stream."""
         self._need_cuda()
         if self.exp_avg is None:
             self.exp_avg = torch.zeros_like(self.params32)
@@ -281,7 +283,7 @@ class Engine:
         _lib.check(self.l.b200mart_adamw(self.h, self.params32.data_ptr(), self.params16.data_ptr(), self.grads32.data_ptr(),
                                          self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), int(step), float(lr),
                                          float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(pretrain),
-                                         _lib.cur_stream()))
+                                         int(begin), int(end), int(zero_grads), _lib.cur_stream()))
         self.mirror_stale = False
 
     # ------------------------------------------------------------------ instrumentation (bench / profiles only)

@@ -102,15 +102,19 @@ class MartTrainer:
         rank = torch.distributed.get_rank(process_group) if self.world > 1 else 0
         self.engine.set_dropout(cfg.hidden_dropout if dropout else 0.0, cfg.attn_dropout if dropout else 0.0,
                                 shard_seed(seed, rank))
-        # overlapped exchange: per-layer "gradients final" events recorded by the library, all-reduces on a side stream
-        self.overlap_comm = bool(overlap_comm) and self.world > 1
+        # pipelined tail of the step: per-layer "gradients final" events recorded by the library; on a side stream each
+        # layer's gradient exchange (N > 1) and AdamW update run while the layers below are still in backward
+        self.overlap_comm = bool(overlap_comm)
         self._comm_stream = self._layer_events = None
+        self._grads_clean = False
         if self.overlap_comm:
             self._comm_stream = torch.cuda.Stream(device=self.device)
             self._layer_events = [torch.cuda.Event() for _ in range(2 * cfg.layers)]
             for e in self._layer_events:
                 e.record()                       # materialise the CUDA event handles
             self._extents = self.engine.layer_extents()
+            self.engine.exp_avg = torch.zeros_like(self.engine.params32)
+            self.engine.exp_avg_sq = torch.zeros_like(self.engine.params32)
 
     # ------------------------------------------------------------------ pieces
     def _head(self, batch):
@@ -137,27 +141,36 @@ class MartTrainer:
             return
         allreduce_mean_(self.engine.grads32, self.pg, self.grad_buckets)
 
-    def _backward_overlapped(self, mb):
-        """Backward with the gradient exchange of layer i started as soon as layer i's backward has run on both chains
-        (layers are walked top-down, so the exchange of layers D-1..1 hides behind the backward of the layers below);
-        embeddings / head gradients, final only at the end, go last.  One NCCL mean all-reduce per layer extent
-        (about 66 MB at base size) on a side stream; the optimizer step waits for all of them."""
+    def _backward_overlapped(self, mb, update=None):
+        """Backward with the tail of the step pipelined per layer: as soon as layer i's backward has run on both chains
+        (layers are walked top-down) a side stream averages that layer's gradient extent over the ranks (one NCCL
+        all-reduce of about 66 MB at base size, N > 1 only) and, when `update` = (step, lr) is given, applies AdamW to
+        it and clears its gradients, while the layers below are still in backward.  Embeddings / head, whose gradients
+        are final only at the end, go last.  A layer's parameters are dead once both chains have left that layer, so
+        updating them (and their bf16 mirror) early is safe."""
         import torch.distributed as dist
         eng, g = self.engine, self.engine.grads32
         main, comm = torch.cuda.current_stream(), self._comm_stream
         eng.backward(mb, layer_events=self._layer_events)
+
+        def finish(b, e):
+            if self.world > 1:
+                dist.all_reduce(g[b:e], op=dist.ReduceOp.AVG, group=self.pg)
+            if update is not None:
+                eng.adamw(update[0], update[1], weight_decay=self.weight_decay, pretrain=self.pretrain, begin=b, end=e,
+                          zero_grads=True)
+
         with torch.cuda.stream(comm):
             for i in reversed(range(self.cfg.layers)):
                 comm.wait_event(self._layer_events[2 * i])
                 comm.wait_event(self._layer_events[2 * i + 1])
-                b, e = self._extents[i]
-                dist.all_reduce(g[b:e], op=dist.ReduceOp.AVG, group=self.pg)
+                finish(*self._extents[i])
             comm.wait_stream(main)               # the whole backward (embeddings included) is ordered before this point
             lo, hi = self._extents[0][0], self._extents[-1][1]
             if lo > 0:
-                dist.all_reduce(g[:lo], op=dist.ReduceOp.AVG, group=self.pg)
+                finish(0, lo)
             if hi < g.numel():
-                dist.all_reduce(g[hi:], op=dist.ReduceOp.AVG, group=self.pg)
+                finish(hi, g.numel())
         main.wait_stream(comm)
 
     # ------------------------------------------------------------------ public API
@@ -166,17 +179,19 @@ class MartTrainer:
         eng = self.engine
         mb = self._model_inputs(batch)
         eng.train(True)
-        eng.zero_grad()
+        if not self._grads_clean:
+            eng.zero_grad()
         eng.forward(mb, want_z=False)
         loss, _, _ = eng.head_loss(mb, self._head(batch), compute_grad=True)
+        lr = linear_warmup_lr(self.steps_done, self.total_steps, self.lr, self.warmup_ratio)
+        self.steps_done += 1
         if self.overlap_comm:
-            self._backward_overlapped(mb)
+            self._backward_overlapped(mb, update=(self.steps_done, lr))
+            self._grads_clean = True             # AdamW cleared every gradient range it consumed
         else:
             eng.backward(mb)
             self.allreduce_grads()
-        lr = linear_warmup_lr(self.steps_done, self.total_steps, self.lr, self.warmup_ratio)
-        self.steps_done += 1
-        eng.adamw(self.steps_done, lr, weight_decay=self.weight_decay, pretrain=self.pretrain)
+            eng.adamw(self.steps_done, lr, weight_decay=self.weight_decay, pretrain=self.pretrain)
         return loss
 
     def train_step_host(self, host_batch):

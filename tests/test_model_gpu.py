@@ -356,3 +356,60 @@ def test_large_shape_family_vs_oracle():
     assert not bad, bad[:10]
     assert all(cos >= 0.998 for e, cos, name in report if "adaptive_weight" not in name and e > 1e-2), \
         [(n, c) for e, c, n in report if c < 0.998][:5]
+
+
+def test_pipelined_optimizer_matches_plain_step_and_oracle_adamw():
+    """MartTrainer with the per-layer pipelined AdamW (side stream, gradients cleared in the kernel) produces the same
+    parameters as the plain path (backward, then one whole-buffer AdamW), and one step matches the oracle's AdamW
+    restatement (lit_models/transformer.py:224-241 grouping) applied to the oracle's gradients."""
+    from mkg_analogy_b200.config import TINY
+    from mkg_analogy_b200.trainer import MartTrainer, linear_warmup_lr
+    from oracle import mkgformer_oracle as O
+    params = init_params(TINY, 11)
+    batches = [to_cuda(make_finetune_batch(4, 24, TINY.image_size, TINY_VOCAB, seed=30 + i, min_len=16)) for i in range(3)]
+    out = {}
+    for pipelined in (False, True):
+        tr = MartTrainer(TINY, TINY_VOCAB, total_steps=20, lr=1e-3, overlap_comm=pipelined, dropout=False)
+        tr.engine.load(params)
+        losses = [tr.train_step(b).item() for b in batches]
+        torch.cuda.synchronize()
+        out[pipelined] = (tr.engine.params32.clone(), losses, tr)
+    p_plain, l_plain, _ = out[False]
+    p_pipe, l_pipe, tr = out[True]
+    assert max(abs(a - b) for a, b in zip(l_plain, l_pipe)) <= 2e-3        # atomics: summation order only
+    # Adam's update is sign-like: where a gradient is ~0, summation-order noise can move a parameter by up to 2 lr per step
+    d = (p_plain - p_pipe).abs()
+    assert d.max().item() <= 2 * 2 * 1e-3 + 1e-6 and d.mean().item() <= 2e-5, (d.max().item(), d.mean().item())
+    assert tr.engine.grads32.abs().max().item() == 0.0                       # cleared by the optimizer kernel
+    # one step against the oracle: same gradients (bf16 tolerance) -> same update direction and size
+    tr1 = MartTrainer(TINY, TINY_VOCAB, total_steps=20, lr=1e-3, overlap_comm=True, dropout=False)
+    tr1.engine.load(params)
+    tr1.train_step(batches[0])
+    torch.cuda.synchronize()
+    Pg = {k: v.cuda().clone().requires_grad_(True) for k, v in params.items()}
+    loss, _, _ = O.finetune_loss(Pg, TINY, batches[0], TINY_VOCAB.analogy_entity_ids())
+    loss.backward()
+    P1 = {k: v.detach().clone() for k, v in Pg.items()}
+    O.adamw_step(P1, {k: v.grad for k, v in Pg.items() if v.grad is not None}, {}, 1, linear_warmup_lr(0, 20, 1e-3, 0.1))
+    # warm-up step 0 has lr = 0: only weight decay-free identity -> use step semantics: parameters must equal the oracle's
+    for name in ("unimo.encoder.text_layer.3.output.dense.weight", "unimo.text_pooler.dense.weight", "cls.predictions.bias"):
+        assert torch.allclose(tr1.engine.view(name), P1[name], atol=1e-6), name
+    # second step has lr > 0: compare the update against the oracle's on the same (oracle) state
+    tr1.train_step(batches[1])
+    torch.cuda.synchronize()
+    st = {}
+    Pg = {k: v.cuda().clone().requires_grad_(True) for k, v in params.items()}
+    for stepno, b in ((1, batches[0]), (2, batches[1])):
+        for v in Pg.values():
+            v.grad = None
+        loss, _, _ = O.finetune_loss(Pg, TINY, b, TINY_VOCAB.analogy_entity_ids())
+        loss.backward()
+        with torch.no_grad():
+            O.adamw_step({k: v for k, v in Pg.items()}, {k: v.grad for k, v in Pg.items() if v.grad is not None}, st, stepno,
+                         linear_warmup_lr(stepno - 1, 20, 1e-3, 0.1))
+    name = "unimo.encoder.text_layer.3.output.dense.weight"
+    upd_mine = tr1.engine.view(name) - params[name].cuda()
+    upd_ref = Pg[name].detach() - params[name].cuda()
+    cos = torch.nn.functional.cosine_similarity(upd_mine.flatten(), upd_ref.flatten(), dim=0).item()
+    assert cos >= 0.98 and abs(upd_mine.norm().item() / upd_ref.norm().item() - 1) <= 0.05, (cos, upd_mine.norm(), upd_ref.norm())
+    assert torch.equal(tr1.engine.view("unimo.text_pooler.dense.weight"), params["unimo.text_pooler.dense.weight"].cuda())

@@ -27,7 +27,7 @@ for overlap in (False, True):
     eng.forward(mb, want_z=False)
     eng.head_loss(mb, tr._head(batch), compute_grad=True)
     if overlap:
-        tr._backward_overlapped(mb)
+        tr._backward_overlapped(mb)          # exchange only (no update): gradients stay in the buffer
     else:
         local_g = None
         eng.backward(mb)
