@@ -400,10 +400,13 @@ struct Run {
         op.M = N; op.N = K; op.K1 = M;
         op.A = dY; op.lda = ldy; op.a_mn = 1; op.B = X; op.ldb = ldx; op.b_mn = 1;
         op.out_f32 = g32(w_off); op.ldo32 = K; op.accumulate = 1;
-        // wide tiles feed the tensor core better (measured: 128x256 + split-K 2 beats 128x128 by ~15 % on the F x H
-        // products); split-K then brings the CTA count back to about one per SM
-        op.bn = ((long)N * K >= 1500000L) ? 256 : 128;
-        {
+        // default: automatic tile choice (CTA-pair kernel where it exists) + split-K up to about one CTA per SM.
+        // B200MART_DW_WIDE=1 forces 128x256 single-CTA tiles instead (A/B runs: pair is ~2 % better on the whole step)
+        static int wide = -1;
+        if (wide < 0) { const char* e = getenv("B200MART_DW_WIDE"); wide = e ? atoi(e) : 0; }
+        op.bn = (wide && (long)N * K >= 1500000L) ? 256 : 128;
+        if (!wide) { op.bn = 0; op.split_k = pick_split(N, K, M); }
+        else {
             const int tiles = ((N + 127) / 128) * ((K + op.bn - 1) / op.bn);
             const int kb = (M + 63) / 64;
             int split = 148 / tiles;

@@ -21,7 +21,7 @@ def _check(out, ref, K, bf16_out=False):
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 128), (2048, 768, 768), (3168, 2304, 768),
                                    (100, 200, 192), (32, 2063, 768), (2048, 768, 3072)])
-@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("bn", [64, 128, 256, 512])     # 512 = 256x256 CTA-pair (cta_group::2) kernel
 def test_gemm_nt(M, N, K, bn):
     from mkg_analogy_b200 import _lib
     A, B = _mk((M, K), 1), _mk((N, K), 2)
@@ -36,10 +36,11 @@ def test_gemm_nn_b_mn(M, N, K):
     """dX = dY @ W with W stored [K][N] (MN-major B)."""
     from mkg_analogy_b200 import _lib
     A, B = _mk((M, K), 3), _mk((K, N), 4)
-    out = torch.full((M, N), float("nan"), device="cuda")
-    _lib.gemm_bf16(A, B, b_mn=True, out_f32=out)
-    torch.cuda.synchronize()
-    _check(out, A.float() @ B.float(), K)
+    for bn in (0, 512):
+        out = torch.full((M, N), float("nan"), device="cuda")
+        _lib.gemm_bf16(A, B, b_mn=True, out_f32=out, bn=bn)
+        torch.cuda.synchronize()
+        _check(out, A.float() @ B.float(), K)
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (768, 768, 2048), (3072, 768, 3168), (200, 136, 100)])
@@ -48,10 +49,11 @@ def test_gemm_tn_both_mn(M, N, K, split):
     """dW = dY^T @ X with both operands stored [K][rows]; accumulate (+=) semantics, split-K."""
     from mkg_analogy_b200 import _lib
     A, B = _mk((K, M), 5), _mk((K, N), 6)
-    out = torch.ones((M, N), device="cuda")
-    _lib.gemm_bf16(A, B, a_mn=True, b_mn=True, out_f32=out, accumulate=True, split_k=split)
-    torch.cuda.synchronize()
-    _check(out, 1.0 + A.float().t() @ B.float(), K)
+    for bn in (0, 128, 512):
+        out = torch.ones((M, N), device="cuda")
+        _lib.gemm_bf16(A, B, a_mn=True, b_mn=True, out_f32=out, accumulate=True, split_k=split, bn=bn)
+        torch.cuda.synchronize()
+        _check(out, 1.0 + A.float().t() @ B.float(), K)
 
 
 def test_gemm_a_mn_only():
