@@ -26,6 +26,10 @@ def test_gemm_nt(M, N, K, bn):
     from mkg_analogy_b200 import _lib
     A, B = _mk((M, K), 1), _mk((N, K), 2)
     out = torch.full((M, N), float("nan"), device="cuda")
+    if bn == 512 and N % 2:      # odd N needs the scalar GENERIC epilogue, which has no CTA-pair instantiation: loud error
+        with pytest.raises(_lib.B200MartError):
+            _lib.gemm_bf16(A, B, out_f32=out, bn=bn)
+        return
     _lib.gemm_bf16(A, B, out_f32=out, bn=bn)
     torch.cuda.synchronize()
     _check(out, A.float() @ B.float().t(), K)
