@@ -205,6 +205,43 @@ int32_t b200mart_profile_end(b200mart_handle* h, void* stream, double ms_by_cat[
                              double* gemm_flops);
 
 /* ------------------------------------------------------------------------------------------------
+ * Pre-LayerNorm encoder stack: the block FLAVA and ViLT are built from
+ *   FlavaLayer / FlavaSelfAttention  MarT/models/modeling_flava.py:620-665, :441-521  (FlavaEncoder: image, text and
+ *                                    multimodal encoders; adaptive scaling on rows 1:s of the text encoder)
+ *   ViltLayer / ViltSelfAttention    MarT/models/modeling_vilt.py:491-528, :329-400   (rows img_length+1 : s')
+ * h = x + drop(Wo attn(LN x) + bo); y = h + drop(W2 act(W1 LN h + b1) + b2); head_dim 64; act 1 = erf-GELU, 2 = quick-GELU.
+ * Parameters live in flat buffers laid out by the library (names follow the HF modules: layer.<i>.attention.attention.query.weight,
+ * layer.<i>.attention.output.dense.*, layer.<i>.intermediate.dense.*, layer.<i>.output.dense.*, layer.<i>.layernorm_before/after.*,
+ * layer.<i>.attention.attention.adaptive_weight.{0,1}); buffers/workspace conventions as for the MKGformer handle. */
+typedef struct b200mart_stack_desc {
+    int32_t hidden, layers, heads, intermediate;
+    int32_t act;
+    float eps;
+} b200mart_stack_desc;
+typedef struct b200mart_stack b200mart_stack;
+typedef struct b200mart_stack_io {
+    int32_t B, T;
+    const float* x;            /* (B*T, hidden) fp32 input hidden states */
+    const int64_t* key_mask;   /* (B, T) attention_mask (1 = keep) -> additive -1e4, or NULL */
+    const int64_t* split;      /* (B) adaptive split position s per sample (sep_idx[:, 2]), or NULL: no scaling */
+    int32_t row_lo;            /* scores of rows [row_lo, s) x cols >= s are scaled by clamp(w0,0,.5); rows >= s by clamp(w1,.5,1) */
+    float* y;                  /* (B*T, hidden) fp32 output hidden states (forward) */
+    float p_hidden, p_attn;    /* dropout probabilities (0 = eval) and seed; sites as in b200mart_set_dropout */
+    uint32_t seed;
+} b200mart_stack_io;
+int32_t b200mart_stack_create(const b200mart_stack_desc* desc, b200mart_stack** out);
+void b200mart_stack_destroy(b200mart_stack* st);
+int32_t b200mart_stack_param_count(const b200mart_stack* st);
+int64_t b200mart_stack_param_total(const b200mart_stack* st);
+int32_t b200mart_stack_param_info(const b200mart_stack* st, int32_t index, const char** name, int64_t* offset, int32_t* ndim,
+                                  int64_t shape[4]);
+int64_t b200mart_stack_workspace_bytes(const b200mart_stack* st, int32_t B, int32_t T);
+int32_t b200mart_stack_forward(b200mart_stack* st, const b200mart_buffers* bufs, const b200mart_stack_io* io, void* stream);
+/* dy (B*T, hidden) fp32 in; dx (B*T, hidden) fp32 out (may be NULL); parameter gradients accumulate into bufs->grads32 */
+int32_t b200mart_stack_backward(b200mart_stack* st, const b200mart_buffers* bufs, const b200mart_stack_io* io, const float* dy,
+                                float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stand-alone operators (kernel-level parity tests; also the building blocks of the functions above).
  */
 /* Fused attention, head_dim 64 (BertSelfAttention :317-377 with adaptive scaling :342-349 and -1e4 mask;

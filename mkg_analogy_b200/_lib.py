@@ -63,6 +63,15 @@ class Head(C.Structure):
                 ("label_smoothing", f32), ("alpha", f32), ("mask_token_id", i32)]
 
 
+class StackDesc(C.Structure):
+    _fields_ = [("hidden", i32), ("layers", i32), ("heads", i32), ("intermediate", i32), ("act", i32), ("eps", f32)]
+
+
+class StackIO(C.Structure):
+    _fields_ = [("B", i32), ("T", i32), ("x", vp), ("key_mask", vp), ("split", vp), ("row_lo", i32), ("y", vp),
+                ("p_hidden", f32), ("p_attn", f32), ("seed", C.c_uint32)]
+
+
 class AttnDesc(C.Structure):
     _fields_ = [
         ("B", i32), ("Lq", i32), ("heads", i32), ("n_prefix", i32), ("n_keys", i32),
@@ -105,6 +114,14 @@ SYMBOLS = {
     "b200mart_last_dropout_seed": (C.c_uint32, [vp]),
     "b200mart_adamw": (i32, [vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, i32, i64, i64, i32, vp]),
     "b200mart_status": (i32, [vp, C.POINTER(Buffers), vp, C.POINTER(i32)]),
+    "b200mart_stack_create": (i32, [C.POINTER(StackDesc), C.POINTER(vp)]),
+    "b200mart_stack_destroy": (None, [vp]),
+    "b200mart_stack_param_count": (i32, [vp]),
+    "b200mart_stack_param_total": (i64, [vp]),
+    "b200mart_stack_param_info": (i32, [vp, i32, C.POINTER(C.c_char_p), C.POINTER(i64), C.POINTER(i32), C.POINTER(i64 * 4)]),
+    "b200mart_stack_workspace_bytes": (i64, [vp, i32, i32]),
+    "b200mart_stack_forward": (i32, [vp, C.POINTER(Buffers), C.POINTER(StackIO), vp]),
+    "b200mart_stack_backward": (i32, [vp, C.POINTER(Buffers), C.POINTER(StackIO), vp, vp, vp]),
     "b200mart_attention_fwd": (i32, [C.POINTER(AttnDesc), vp]),
     "b200mart_attention_bwd": (i32, [C.POINTER(AttnDesc), vp]),
     "b200mart_fusion_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),

@@ -152,12 +152,13 @@ __device__ __forceinline__ float quad_max(float v) {
     return v;
 }
 
-struct Adapt { int split; float w0c, w1c; };
+struct Adapt { int split, row_lo; float w0c, w1c; };
 __device__ __forceinline__ Adapt load_adapt(const AttnFwd& a, int b) {
     Adapt ad;
-    ad.split = -1; ad.w0c = ad.w1c = 1.f;
+    ad.split = -1; ad.row_lo = 0; ad.w0c = ad.w1c = 1.f;
     if (a.sep_idx) {
-        ad.split = (int)a.sep_idx[(long)b * 6 + 2];
+        ad.split = (int)a.sep_idx[(long)b * a.sep_stride];
+        ad.row_lo = a.row_lo;
         ad.w0c = fminf(fmaxf(*a.w0, 0.f), 0.5f);
         ad.w1c = fminf(fmaxf(*a.w1, 0.5f), 1.0f);
     }
@@ -166,7 +167,8 @@ __device__ __forceinline__ Adapt load_adapt(const AttnFwd& a, int b) {
 // factor of score (query row r, own-key index j2 = key - n1); prefix keys (j2 < 0) are never scaled
 __device__ __forceinline__ float afactor(const Adapt& ad, int r, int j2) {
     if (ad.split < 0 || j2 < ad.split) return 1.0f;
-    return (r < ad.split) ? ad.w0c : ad.w1c;
+    if (r >= ad.split) return ad.w1c;
+    return (r >= ad.row_lo) ? ad.w0c : 1.0f;
 }
 
 // shared: K/V staging of all keys (prefix first) + additive mask per key (NEG_BIG for padding keys >= n)
@@ -332,7 +334,8 @@ attn_bwd_rows_mma(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx, fl
                     if (a.drop.thresh) dpe *= drop_mult(a.drop, (uint32_t)((((long)b * a.nh + h) * a.Lq + row) * n + col));
                     const float ds = p * (dpe - dl[e >> 1]);
                     if (ad.split >= 0 && j2 >= ad.split && col < n) {
-                        if (row < ad.split) dw0 = fmaf(ds, sraw, dw0); else dw1 = fmaf(ds, sraw, dw1);
+                        if (row >= ad.split) dw1 = fmaf(ds, sraw, dw1);
+                        else if (row >= ad.row_lo) dw0 = fmaf(ds, sraw, dw0);
                     }
                     s[nt][e] = ds * f;
                 }

@@ -305,6 +305,32 @@ __global__ void colsum_kernel(const T* __restrict__ x, long ld, float* out, int 
     }
 }
 
+// dst16 = bf16(src * dropout_mult), colsum[c] += sum_rows of the same values: turns an incoming fp32 gradient into the masked
+// bf16 operand of the dW / dX products of a dense layer whose output went through dropout, plus that layer's bias gradient.
+__global__ void mask_cast_colsum_kernel(const float* __restrict__ src, bf16* __restrict__ dst, float* colsum, int M, int N,
+                                        int rows_per_block, DropCfg drop) {
+    __shared__ float part[8][33];
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(M, r0 + rows_per_block);
+    float s = 0.f;
+    if (col < N)
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+            float v = src[(long)r * N + col];
+            if (drop.thresh) v *= drop_mult(drop, (uint32_t)r * (uint32_t)N + (uint32_t)col);
+            dst[(long)r * N + col] = __float2bfloat16(v);
+            s += v;
+        }
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < N && colsum) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+        atomicAdd(colsum + col, t);
+    }
+}
+
 // ---------------------------------------------------------------- embedding backward
 __global__ void text_embed_bwd_kernel(const float* __restrict__ d, const int64_t* __restrict__ ids,
                                       const int64_t* __restrict__ tt, float* dE, float* dpos, float* dtype, int B, int L,
@@ -491,6 +517,12 @@ int launch_colsum_bf16(const bf16* x, long ld, float* out, int M, int N, cudaStr
 int launch_colsum_f32(const float* x, long ld, float* out, int M, int N, cudaStream_t s) {
     const int rpb = 128;
     colsum_kernel<float><<<dim3((N + 31) / 32, (M + rpb - 1) / rpb), dim3(32, 8), 0, s>>>(x, ld, out, M, N, rpb);
+    B2_LAUNCHED();
+    return 0;
+}
+int launch_mask_cast_colsum(const float* src, bf16* dst, float* colsum, int M, int N, DropCfg drop, cudaStream_t s) {
+    const int rpb = 64;
+    mask_cast_colsum_kernel<<<dim3((N + 31) / 32, (M + rpb - 1) / rpb), dim3(32, 8), 0, s>>>(src, dst, colsum, M, N, rpb, drop);
     B2_LAUNCHED();
     return 0;
 }

@@ -28,7 +28,9 @@ int launch_layernorm_bwd(const float* dy, const float* x, const float* mean, con
                          DropCfg dx16_drop = DropCfg{0u, 0u, 1.f});
 // dy_drop: dy is the gradient wrt a DROPPED copy of this LayerNorm's output (element index row*H+col);
 // dx16_drop: dx16 (and dxsum) additionally carry the dropout mask of the dense branch that fed the LayerNorm input
-int launch_colsum_bf16(const bf16* x, long ld, float* out, int M, int N, cudaStream_t s);  // out[n] += sum_m x[m,n]
+int launch_colsum_bf16(const bf16* x, long ld, float* out, int M, int N, cudaStream_t s);
+// dst16 = bf16(src * dropout mask), colsum += column sums of the masked values (src contiguous [M, N])
+int launch_mask_cast_colsum(const float* src, bf16* dst, float* colsum, int M, int N, DropCfg drop, cudaStream_t s);  // out[n] += sum_m x[m,n]
 int launch_colsum_f32(const float* x, long ld, float* out, int M, int N, cudaStream_t s);
 // text embedding backward: dE[ids] += d, dtype[tt] += d, dpos[l] += d  (d = gradient wrt the pre-LN sum)
 int launch_text_embed_bwd(const float* d, const int64_t* ids, const int64_t* tt, float* dE, float* dpos, float* dtype,
@@ -57,7 +59,9 @@ struct AttnFwd {
     int B, Lq, nh;
     float scale;
     const int64_t* key_mask;      // (B, n2) attention_mask (1 = keep) or null; adds -10000 where 0
-    const int64_t* sep_idx;       // (B, 6) or null; split = sep_idx[b*6+2]
+    const int64_t* sep_idx;       // adaptive split column s per sample: s = sep_idx[b * sep_stride]; null = no scaling
+    int sep_stride;               //   (MKGformer passes sep_idx + 2 with stride 6, i.e. sep_idx[b][2])
+    int row_lo;                   // rows [row_lo, s) x cols >= s are scaled by clamp(w0,0,.5); rows >= s by clamp(w1,.5,1)
     const float* w0; const float* w1;   // adaptive weights (device scalars), used when sep_idx != null
     bf16* out; long ldo;          // context [B*Lq, nh*64]
     float* lse;                   // [B, nh, Lq] log-sum-exp of the final scores

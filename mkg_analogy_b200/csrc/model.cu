@@ -660,7 +660,7 @@ extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* 
             at.k2 = a.qkv16 + H; at.v2 = a.qkv16 + 2 * H; at.ld2 = 3 * H; at.n2 = L;
             at.B = B; at.Lq = L; at.nh = nh; at.scale = 0.125f;
             at.key_mask = batch->attention_mask;
-            if (batch->sep_idx) { at.sep_idx = batch->sep_idx; at.w0 = rt.p32(p.aw0); at.w1 = rt.p32(p.aw1); }
+            if (batch->sep_idx) { at.sep_idx = batch->sep_idx + 2; at.sep_stride = 6; at.w0 = rt.p32(p.aw0); at.w1 = rt.p32(p.aw1); }
             at.out = a.ctx16; at.ldo = H; at.lse = a.lse;
             at.drop = make_drop(pa, seed, 1 + 3 * i);
             { ProfScope ps(h, stx, CAT_ATTN); B2_TRY(launch_attention_fwd(at, fused ? a.ctx32 : nullptr, stx)); }
@@ -890,7 +890,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             at.k2 = a.qkv16 + H; at.v2 = a.qkv16 + 2 * H; at.ld2 = 3 * H; at.n2 = L;
             at.B = B; at.Lq = L; at.nh = nh; at.scale = 0.125f;
             at.key_mask = batch->attention_mask;
-            if (batch->sep_idx) { at.sep_idx = batch->sep_idx; at.w0 = rt.p32(p.aw0); at.w1 = rt.p32(p.aw1); ab.dw0 = rt.g32(p.aw0); ab.dw1 = rt.g32(p.aw1); }
+            if (batch->sep_idx) { at.sep_idx = batch->sep_idx + 2; at.sep_stride = 6; at.w0 = rt.p32(p.aw0); at.w1 = rt.p32(p.aw1); ab.dw0 = rt.g32(p.aw0); ab.dw1 = rt.g32(p.aw1); }
             at.lse = a.lse;
             at.drop = make_drop(pa, seed, 1 + 3 * i);
             ab.dout = w.t32b; ab.lddo = H;
@@ -1011,6 +1011,196 @@ extern "C" int32_t b200mart_profile_end(b200mart_handle* h, void* stream, double
     return 0;
 }
 
+
+// ======================================================================================= pre-LN encoder stack
+// Generic pre-LayerNorm transformer stack = the block FLAVA and ViLT are made of (and the CLIP layers above):
+//   FlavaLayer   MarT/models/modeling_flava.py:620-665  (FlavaSelfAttention :441-521 with adaptive scaling on rows 1:s)
+//   ViltLayer    MarT/models/modeling_vilt.py:491-528   (ViltSelfAttention :329-400, rows img_length+1 : s')
+//   h = x + drop(Wo attn(LN1 x) + bo);  y = h + drop(W2 act(W1 LN2 h + b1) + b2)
+// attn: S = QK^T / 8, adaptive block scaling (rows [row_lo, s) x cols >= s by clamp(w0,0,.5); rows >= s by clamp(w1,.5,1))
+// BEFORE the additive -1e4 key mask, softmax, dropout, PV.  Same kernels as the MKGformer path.
+struct b200mart_stack {
+    b200mart_handle core;      // plan cache / profiling / stream plumbing of the GEMM runner
+    b200mart_stack_desc d;
+    struct LayerP { long ln1_w, ln1_b, qkv_w, qkv_b, aw0, aw1, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b; };
+    struct LayerA { bf16 *u16, *qkv16, *ctx16, *u2_16, *pre16, *h16; float *mean1, *rstd1, *lse, *x1, *mean2, *rstd2; };
+    std::vector<LayerP> lay;
+    // workspace carving
+    int B = 0, T = 0; void* ws_base = nullptr; size_t ws_bytes = 0;
+    std::vector<float*> X;     // layers + 1 residual streams
+    std::vector<LayerA> act;
+    float *s32a, *s32b, *dX; bf16 *dX16, *s16a, *sF16, *sdqkv16; float* delta;
+};
+
+namespace {
+
+void stack_carve(b200mart_stack* st, int B, int T, void* base) {
+    const size_t H = st->d.hidden, F = st->d.intermediate, nh = st->d.heads, M = (size_t)B * T;
+    Carver c{reinterpret_cast<uint8_t*>(base)};
+    st->X.assign(st->d.layers + 1, nullptr);
+    for (auto& p : st->X) p = c.take<float>(M * H);
+    st->act.assign(st->d.layers, b200mart_stack::LayerA());
+    for (auto& a : st->act) {
+        a.u16 = c.take<bf16>(M * H); a.mean1 = c.take<float>(M); a.rstd1 = c.take<float>(M);
+        a.qkv16 = c.take<bf16>(M * 3 * H); a.lse = c.take<float>((size_t)B * nh * T);
+        a.ctx16 = c.take<bf16>(M * H); a.x1 = c.take<float>(M * H);
+        a.u2_16 = c.take<bf16>(M * H); a.mean2 = c.take<float>(M); a.rstd2 = c.take<float>(M);
+        a.pre16 = c.take<bf16>(M * F); a.h16 = c.take<bf16>(M * F);
+    }
+    st->s32a = c.take<float>(M * H); st->s32b = c.take<float>(M * H); st->dX = c.take<float>(M * H);
+    st->dX16 = c.take<bf16>(M * H); st->s16a = c.take<bf16>(M * H); st->sF16 = c.take<bf16>(M * F);
+    st->sdqkv16 = c.take<bf16>(M * 3 * H); st->delta = c.take<float>((size_t)B * nh * T);
+    st->B = B; st->T = T; st->ws_base = base; st->ws_bytes = c.off + 256;
+}
+
+int stack_bind(b200mart_stack* st, const b200mart_buffers* bufs, int B, int T) {
+    B2_CHECK(bufs && bufs->workspace && bufs->params32 && bufs->params16, "stack: null buffers");
+    if (st->ws_base != bufs->workspace || st->B != B || st->T != T) stack_carve(st, B, T, bufs->workspace);
+    B2_CHECK((long)st->ws_bytes <= bufs->workspace_bytes, "stack: workspace too small: need %zu bytes, have %ld", st->ws_bytes,
+             (long)bufs->workspace_bytes);
+    return 0;
+}
+
+void stack_attn(const b200mart_stack* st, const b200mart_stack_io* io, const Run& r, int i, AttnFwd& at) {
+    const int H = st->d.hidden;
+    const b200mart_stack::LayerA& a = st->act[i];
+    at.q = a.qkv16; at.ldq = 3 * H;
+    at.k2 = a.qkv16 + H; at.v2 = a.qkv16 + 2 * H; at.ld2 = 3 * H; at.n2 = io->T;
+    at.B = io->B; at.Lq = io->T; at.nh = st->d.heads; at.scale = 0.125f;
+    at.key_mask = io->key_mask;
+    if (io->split) {
+        at.sep_idx = io->split; at.sep_stride = 1; at.row_lo = io->row_lo;
+        at.w0 = r.p32(st->lay[i].aw0); at.w1 = r.p32(st->lay[i].aw1);
+    }
+    at.lse = a.lse;
+    at.drop = make_drop(io->p_attn, io->seed, 1 + 3 * i);
+}
+
+}  // namespace
+
+extern "C" int32_t b200mart_stack_create(const b200mart_stack_desc* desc, b200mart_stack** out) {
+    B2_CHECK(desc && out, "stack_create: null argument");
+    *out = nullptr;
+    const b200mart_stack_desc& d = *desc;
+    B2_CHECK(d.hidden % 128 == 0 && d.hidden <= 1024 && d.heads > 0 && d.hidden == d.heads * 64,
+             "stack: hidden %d must be heads * 64, a multiple of 128 and <= 1024", d.hidden);
+    B2_CHECK(d.intermediate % 64 == 0 && d.layers > 0 && (d.act == 1 || d.act == 2), "stack: bad intermediate / layers / act");
+    b200mart_stack* st = new b200mart_stack();
+    st->d = d;
+    b200mart_handle* h = &st->core;
+    const long H = d.hidden, F = d.intermediate;
+    char buf[160];
+    for (int i = 0; i < d.layers; ++i) {
+        b200mart_stack::LayerP p;
+        auto nm = [&](const char* s) { snprintf(buf, sizeof(buf), "layer.%d.%s", i, s); return std::string(buf); };
+        p.qkv_w = add_param(h, nm("attention.attention.query.weight"), {H, H});
+        add_param(h, nm("attention.attention.key.weight"), {H, H});
+        add_param(h, nm("attention.attention.value.weight"), {H, H});
+        p.qkv_b = add_param(h, nm("attention.attention.query.bias"), {H});
+        add_param(h, nm("attention.attention.key.bias"), {H});
+        add_param(h, nm("attention.attention.value.bias"), {H});
+        p.aw0 = add_param(h, nm("attention.attention.adaptive_weight.0"), {1});
+        p.aw1 = add_param(h, nm("attention.attention.adaptive_weight.1"), {1});
+        p.o_w = add_param(h, nm("attention.output.dense.weight"), {H, H});
+        p.o_b = add_param(h, nm("attention.output.dense.bias"), {H});
+        p.fc1_w = add_param(h, nm("intermediate.dense.weight"), {F, H});
+        p.fc1_b = add_param(h, nm("intermediate.dense.bias"), {F});
+        p.fc2_w = add_param(h, nm("output.dense.weight"), {H, F});
+        p.fc2_b = add_param(h, nm("output.dense.bias"), {H});
+        p.ln1_w = add_param(h, nm("layernorm_before.weight"), {H});
+        p.ln1_b = add_param(h, nm("layernorm_before.bias"), {H});
+        p.ln2_w = add_param(h, nm("layernorm_after.weight"), {H});
+        p.ln2_b = add_param(h, nm("layernorm_after.bias"), {H});
+        st->lay.push_back(p);
+    }
+    *out = st;
+    return 0;
+}
+
+extern "C" void b200mart_stack_destroy(b200mart_stack* st) { delete st; }
+extern "C" int32_t b200mart_stack_param_count(const b200mart_stack* st) { return st ? (int32_t)st->core.params.size() : 0; }
+extern "C" int64_t b200mart_stack_param_total(const b200mart_stack* st) { return st ? st->core.lay.total : 0; }
+extern "C" int32_t b200mart_stack_param_info(const b200mart_stack* st, int32_t i, const char** name, int64_t* offset, int32_t* ndim,
+                                             int64_t shape[4]) {
+    B2_CHECK(st, "stack_param_info: null handle");
+    return b200mart_param_info(&st->core, i, name, offset, ndim, shape, nullptr, nullptr);
+}
+extern "C" int64_t b200mart_stack_workspace_bytes(const b200mart_stack* st, int32_t B, int32_t T) {
+    if (!st || B <= 0 || T <= 0) return 0;
+    b200mart_stack tmp;
+    tmp.d = st->d;
+    stack_carve(&tmp, B, T, nullptr);
+    return (int64_t)tmp.ws_bytes;
+}
+
+extern "C" int32_t b200mart_stack_forward(b200mart_stack* st, const b200mart_buffers* bufs, const b200mart_stack_io* io, void* stream) {
+    B2_CHECK(st && io && io->x && io->y && io->B > 0 && io->T > 0, "stack_forward: bad arguments");
+    B2_TRY(stack_bind(st, bufs, io->B, io->T));
+    const b200mart_stack_desc& d = st->d;
+    const int H = d.hidden, F = d.intermediate, M = io->B * io->T;
+    cudaStream_t s = (cudaStream_t)stream;
+    Run r{&st->core, bufs, s};
+    CUDA_TRY(cudaMemcpyAsync(st->X[0], io->x, sizeof(float) * M * H, cudaMemcpyDeviceToDevice, s));
+    for (int i = 0; i < d.layers; ++i) {
+        const b200mart_stack::LayerP& p = st->lay[i];
+        b200mart_stack::LayerA& a = st->act[i];
+        B2_TRY(launch_layernorm_fwd(st->X[i], r.p32(p.ln1_w), r.p32(p.ln1_b), d.eps, nullptr, a.u16, a.mean1, a.rstd1, M, H, s));
+        B2_TRY(r.linear(M, 3 * H, H, a.u16, p.qkv_w, p.qkv_b, 0, nullptr, nullptr, nullptr, a.qkv16));
+        AttnFwd at{};
+        stack_attn(st, io, r, i, at);
+        at.out = a.ctx16; at.ldo = H;
+        B2_TRY(launch_attention_fwd(at, nullptr, s));
+        r.drop_next = make_drop(io->p_hidden, io->seed, 2 + 3 * i);
+        B2_TRY(r.linear(M, H, H, a.ctx16, p.o_w, p.o_b, 0, nullptr, st->X[i], a.x1, nullptr));
+        B2_TRY(launch_layernorm_fwd(a.x1, r.p32(p.ln2_w), r.p32(p.ln2_b), d.eps, nullptr, a.u2_16, a.mean2, a.rstd2, M, H, s));
+        B2_TRY(r.linear(M, F, H, a.u2_16, p.fc1_w, p.fc1_b, d.act, a.pre16, nullptr, nullptr, a.h16));
+        r.drop_next = make_drop(io->p_hidden, io->seed, 3 + 3 * i);
+        B2_TRY(r.linear(M, H, F, a.h16, p.fc2_w, p.fc2_b, 0, nullptr, a.x1, st->X[i + 1], nullptr));
+    }
+    CUDA_TRY(cudaMemcpyAsync(io->y, st->X[d.layers], sizeof(float) * M * H, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+extern "C" int32_t b200mart_stack_backward(b200mart_stack* st, const b200mart_buffers* bufs, const b200mart_stack_io* io, const float* dy,
+                                           float* dx, void* stream) {
+    B2_CHECK(st && io && dy && bufs && bufs->grads32, "stack_backward: bad arguments");
+    B2_CHECK(st->ws_base == bufs->workspace && st->B == io->B && st->T == io->T, "stack_backward: run stack_forward on this input first");
+    const b200mart_stack_desc& d = st->d;
+    const int H = d.hidden, F = d.intermediate, M = io->B * io->T, D = d.layers;
+    cudaStream_t s = (cudaStream_t)stream;
+    Run r{&st->core, bufs, s};
+    const DropCfg nodrop{0u, 0u, 1.f};
+    // gradient wrt the stack output: fp32 copy (residual path) + masked bf16 copy / bias gradient of the top fc2
+    CUDA_TRY(cudaMemcpyAsync(st->dX, dy, sizeof(float) * M * H, cudaMemcpyDeviceToDevice, s));
+    B2_TRY(launch_mask_cast_colsum(dy, st->dX16, r.g32(st->lay[D - 1].fc2_b), M, H, make_drop(io->p_hidden, io->seed, 3 + 3 * (D - 1)), s));
+    for (int i = D - 1; i >= 0; --i) {
+        const b200mart_stack::LayerP& p = st->lay[i];
+        b200mart_stack::LayerA& a = st->act[i];
+        B2_TRY(r.grad_weight(M, H, F, st->dX16, H, a.h16, F, p.fc2_w, -1));
+        B2_TRY(r.grad_input(M, H, F, st->dX16, p.fc2_w, a.pre16, 3, nullptr, nullptr, st->sF16, p.fc1_b));
+        B2_TRY(r.grad_weight(M, F, H, st->sF16, F, a.u2_16, H, p.fc1_w, -1));
+        B2_TRY(r.grad_input(M, F, H, st->sF16, p.fc1_w, nullptr, 0, nullptr, st->s32a, nullptr));
+        B2_TRY(launch_layernorm_bwd(st->s32a, a.x1, a.mean2, a.rstd2, r.p32(p.ln2_w), st->dX, nullptr, 0, st->s32b, st->s16a,
+                                    r.g32(p.ln2_w), r.g32(p.ln2_b), r.g32(p.o_b), M, H, s, nodrop, make_drop(io->p_hidden, io->seed, 2 + 3 * i)));
+        B2_TRY(r.grad_weight(M, H, H, st->s16a, H, a.ctx16, H, p.o_w, -1));
+        B2_TRY(r.grad_input(M, H, H, st->s16a, p.o_w, nullptr, 0, nullptr, st->s32a, nullptr));
+        AttnBwd ab{};
+        stack_attn(st, io, r, i, ab.f);
+        if (io->split) { ab.dw0 = r.g32(p.aw0); ab.dw1 = r.g32(p.aw1); }
+        ab.dout = st->s32a; ab.lddo = H;
+        ab.dq = st->sdqkv16; ab.dk2 = st->sdqkv16 + H; ab.dv2 = st->sdqkv16 + 2 * H; ab.ldd = 3 * H;
+        B2_TRY(launch_attention_bwd(ab, a.ctx16, H, st->delta, s));
+        B2_TRY(r.grad_weight(M, 3 * H, H, st->sdqkv16, 3 * H, a.u16, H, p.qkv_w, p.qkv_b));
+        B2_TRY(r.grad_input(M, 3 * H, H, st->sdqkv16, p.qkv_w, nullptr, 0, nullptr, st->s32a, nullptr));
+        // gradient wrt this layer's input; its bf16 copy carries the dropout mask of the fc2 output of the layer below
+        B2_TRY(launch_layernorm_bwd(st->s32a, st->X[i], a.mean1, a.rstd1, r.p32(p.ln1_w), st->s32b, nullptr, 0, st->dX, st->dX16,
+                                    r.g32(p.ln1_w), r.g32(p.ln1_b), i > 0 ? r.g32(st->lay[i - 1].fc2_b) : nullptr, M, H, s, nodrop,
+                                    i > 0 ? make_drop(io->p_hidden, io->seed, 3 + 3 * (i - 1)) : nodrop));
+    }
+    if (dx) CUDA_TRY(cudaMemcpyAsync(dx, st->dX, sizeof(float) * M * H, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
 // --------------------------------------------------------------------------------------- stand-alone operators
 extern "C" int32_t b200mart_attention_fwd(const b200mart_attn_desc* d, void* stream) {
     B2_CHECK(d, "attention_fwd: null descriptor");
@@ -1019,7 +1209,7 @@ extern "C" int32_t b200mart_attention_fwd(const b200mart_attn_desc* d, void* str
     a.k1 = (const bf16*)d->prefix_k; a.v1 = (const bf16*)d->prefix_v; a.ld1 = d->ld_prefix; a.n1 = d->prefix_k ? d->n_prefix : 0;
     a.k2 = (const bf16*)d->k; a.v2 = (const bf16*)d->v; a.ld2 = d->ldkv; a.n2 = d->n_keys;
     a.B = d->B; a.Lq = d->Lq; a.nh = d->heads; a.scale = d->scale;
-    a.key_mask = d->key_mask; a.sep_idx = d->sep_idx; a.w0 = d->w0; a.w1 = d->w1;
+    a.key_mask = d->key_mask; a.sep_idx = d->sep_idx ? d->sep_idx + 2 : nullptr; a.sep_stride = 6; a.w0 = d->w0; a.w1 = d->w1;
     a.out = (bf16*)d->out; a.ldo = d->ldo; a.lse = d->lse;
     B2_CHECK(a.out && a.lse, "attention_fwd: out / lse missing");
     return launch_attention_fwd(a, d->out_f32, (cudaStream_t)stream);
@@ -1033,7 +1223,7 @@ extern "C" int32_t b200mart_attention_bwd(const b200mart_attn_desc* d, void* str
     a.k1 = (const bf16*)d->prefix_k; a.v1 = (const bf16*)d->prefix_v; a.ld1 = d->ld_prefix; a.n1 = d->prefix_k ? d->n_prefix : 0;
     a.k2 = (const bf16*)d->k; a.v2 = (const bf16*)d->v; a.ld2 = d->ldkv; a.n2 = d->n_keys;
     a.B = d->B; a.Lq = d->Lq; a.nh = d->heads; a.scale = d->scale;
-    a.key_mask = d->key_mask; a.sep_idx = d->sep_idx; a.w0 = d->w0; a.w1 = d->w1;
+    a.key_mask = d->key_mask; a.sep_idx = d->sep_idx ? d->sep_idx + 2 : nullptr; a.sep_stride = 6; a.w0 = d->w0; a.w1 = d->w1;
     a.lse = d->lse;
     g.dout = d->dout; g.lddo = d->lddo;
     g.dq = (bf16*)d->dq; g.dk2 = (bf16*)d->dk; g.dv2 = (bf16*)d->dv; g.ldd = d->ldd;

@@ -107,11 +107,58 @@ def loss_case():
     return out
 
 
+def stack_case():
+    """Reference FlavaEncoder (text-encoder use: mask + adaptive scaling on rows 1:s) and ViltEncoder (rows img_length+1:s')
+    on seeded inputs and weights: outputs, input gradient and a few parameter gradients."""
+    from transformers import FlavaTextConfig, ViltConfig
+    Fm, Vm = RL.load_flava(), RL.load_vilt()
+    out = {}
+    for tag, mod, cfg_cls, T, row_lo in (("flava", Fm.FlavaEncoder, FlavaTextConfig, 40, 1), ("vilt", Vm.ViltEncoder, ViltConfig, 56, 17)):
+        cfg = cfg_cls(hidden_size=128, num_hidden_layers=3, num_attention_heads=2, intermediate_size=256,
+                      hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+        torch.manual_seed(31)
+        enc = mod(cfg).eval()
+        with torch.no_grad():
+            for n, prm in enc.named_parameters():
+                if prm.dim() >= 2:
+                    prm.normal_(0, 0.05)
+                elif "adaptive_weight.0" in n:
+                    prm.fill_(0.3)
+                elif "adaptive_weight.1" in n:
+                    prm.fill_(0.5)
+                elif "layernorm" in n and n.endswith("weight"):
+                    prm.normal_(1.0, 0.1)
+                else:
+                    prm.normal_(0, 0.05)
+        g = torch.Generator().manual_seed(32)
+        B = 3
+        x = torch.randn(B, T, 128, generator=g).requires_grad_(True)
+        lens = torch.tensor([T, T - 7, T - 13])
+        mask = (torch.arange(T)[None] < lens[:, None]).long()
+        sep = torch.zeros(B, 6, dtype=torch.long)
+        sep[:, 2] = torch.tensor([row_lo + 6, row_lo + 11, row_lo + 4])
+        ext = (1.0 - mask[:, None, None, :].float()) * -10000.0
+        kw = dict(attention_mask=ext, sep_idx=sep.clone(), return_dict=True)
+        if tag == "vilt":
+            kw["img_length"] = row_lo - 1
+        y = enc(x, **kw).last_hidden_state
+        gy = torch.randn(y.shape, generator=g)
+        y.backward(gy)
+        names = ["layer.0.attention.attention.query.weight", "layer.2.output.dense.bias", "layer.1.attention.attention.adaptive_weight.0",
+                 "layer.1.attention.attention.adaptive_weight.1", "layer.2.layernorm_before.weight", "layer.0.intermediate.dense.weight"]
+        sd = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+        out[tag] = dict(params=sd, x=x.detach().clone(), mask=mask, sep=sep, row_lo=row_lo, y=y.detach().clone(), gy=gy,
+                        dx=x.grad.clone(), grads={n: dict(enc.named_parameters())[n].grad.clone() for n in names},
+                        grad_norm={n: p.grad.norm().item() for n, p in enc.named_parameters()})
+    return out
+
+
 if __name__ == "__main__":
     assert RL.available(), "reference tree not found"
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     torch.save(tiny_case(), os.path.join(GOLD, "mkgformer_tiny.pt"))
     torch.save(loss_case(), os.path.join(GOLD, "ls_ce.pt"))
+    torch.save(stack_case(), os.path.join(GOLD, "preln_stack.pt"))
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))

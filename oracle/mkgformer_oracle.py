@@ -242,6 +242,61 @@ def pretrain_loss(P, cfg, batch, entity_range, relation_range, label_smoothing=0
     return loss
 
 
+# ----------------------------------------------------------------------------------------------- FLAVA / ViLT encoder
+def adaptive_scale_rows(scores, sep_split, w0, w1, row_lo):
+    """FlavaSelfAttention modeling_flava.py:491-496 (row_lo = 1) / ViltSelfAttention modeling_vilt.py:370-375
+    (row_lo = img_length + 1): rows [row_lo, s) x cols >= s scaled by clamp(w0, 0, .5); rows >= s x cols >= s by
+    clamp(w1, .5, 1); rows < row_lo untouched.  (modeling_unimo.py:342-349 is the row_lo = 0 case.)"""
+    B, nh, T, _ = scores.shape
+    ar = torch.arange(T, device=scores.device)
+    s = sep_split.view(B, 1, 1, 1)
+    col = ar.view(1, 1, 1, T) >= s
+    row = ar.view(1, 1, T, 1)
+    one = torch.ones((), device=scores.device, dtype=scores.dtype)
+    factor = torch.where(col & (row >= s), torch.clamp(w1, 0.5, 1),
+                         torch.where(col & (row >= row_lo) & (row < s), torch.clamp(w0, 0, 0.5), one))
+    return scores * factor
+
+
+def preln_stack(P, x, heads, eps=1e-12, act="gelu", attention_mask=None, sep_split=None, row_lo=1, drop=None, prefix=""):
+    """FlavaEncoder (modeling_flava.py:668-722 over FlavaLayer :620-665) / ViltEncoder (modeling_vilt.py:531-583 over
+    ViltLayer :491-528): pre-LayerNorm blocks.  P: {"layer.i....": tensor} with the HF parameter names; attention_mask
+    (B, T) 1 = keep -> additive (1 - m) * -10000 as the callers build it; drop: optional explicit-mask dropout callback
+    (sites 1+3i attention probabilities, 2+3i attention output, 3+3i MLP output)."""
+    B, T, H = x.shape
+    d = H // heads
+    n_layers = 1 + max(int(k[len(prefix):].split(".")[1]) for k in P if k.startswith(prefix + "layer."))
+    ext = None if attention_mask is None else (1.0 - attention_mask[:, None, None, :].to(x.dtype)) * -10000.0
+    fact = F.gelu if act == "gelu" else quick_gelu
+    for i in range(n_layers):
+        p = f"{prefix}layer.{i}."
+        u = layer_norm(x, P[p + "layernorm_before.weight"], P[p + "layernorm_before.bias"], eps)
+        q = _heads(F.linear(u, P[p + "attention.attention.query.weight"], P[p + "attention.attention.query.bias"]), heads)
+        k = _heads(F.linear(u, P[p + "attention.attention.key.weight"], P[p + "attention.attention.key.bias"]), heads)
+        v = _heads(F.linear(u, P[p + "attention.attention.value.weight"], P[p + "attention.attention.value.bias"]), heads)
+        sc = (q @ k.transpose(-1, -2)) / math.sqrt(d)
+        if sep_split is not None:
+            sc = adaptive_scale_rows(sc, sep_split, P[p + "attention.attention.adaptive_weight.0"],
+                                     P[p + "attention.attention.adaptive_weight.1"], row_lo)
+        if ext is not None:
+            sc = sc + ext
+        pr = torch.softmax(sc, dim=-1)
+        if drop is not None:
+            pr = drop(1 + 3 * i, pr)
+        ctx = (pr @ v).permute(0, 2, 1, 3).reshape(B, T, H)
+        ao = F.linear(ctx, P[p + "attention.output.dense.weight"], P[p + "attention.output.dense.bias"])
+        if drop is not None:
+            ao = drop(2 + 3 * i, ao)
+        h = x + ao
+        u2 = layer_norm(h, P[p + "layernorm_after.weight"], P[p + "layernorm_after.bias"], eps)
+        f = fact(F.linear(u2, P[p + "intermediate.dense.weight"], P[p + "intermediate.dense.bias"]))
+        fo = F.linear(f, P[p + "output.dense.weight"], P[p + "output.dense.bias"])
+        if drop is not None:
+            fo = drop(3 + 3 * i, fo)
+        x = h + fo
+    return x
+
+
 def hash_dropout(seed, p_hidden, p_attn):
     """drop(site, tensor) callback reproducing the CUDA path's stateless dropout masks (csrc/common.cuh: keep element e of
     site s iff hash32(e ^ hash32(seed + 0x9E3779B9 (s + 1))) >= p 2^32; kept values scaled by 1/(1-p) in fp32), so the

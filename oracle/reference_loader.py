@@ -25,6 +25,14 @@ def _install_shims():
     from transformers import pytorch_utils as pu
     if not hasattr(mu, "apply_chunking_to_forward"):
         mu.apply_chunking_to_forward = pu.apply_chunking_to_forward
+    # ViLT / FLAVA files import helpers that moved or vanished between transformers 4.19 and 5.x
+    for mod in (mu, pu):
+        if not hasattr(mod, "find_pruneable_heads_and_indices"):
+            def _no_prune(*a, **k):
+                raise NotImplementedError("head pruning is not part of the hot path")
+            mod.find_pruneable_heads_and_indices = _no_prune
+        if not hasattr(mod, "prune_linear_layer"):
+            mod.prune_linear_layer = pu.prune_linear_layer
     if "pytorch_lightning" not in sys.modules:
         pl = types.ModuleType("pytorch_lightning")
 
@@ -48,6 +56,14 @@ def load_module(name, relpath):
     sys.modules[name] = m
     spec.loader.exec_module(m)
     return m
+
+
+def load_flava():
+    return load_module("ref_flava", "models/modeling_flava.py")
+
+
+def load_vilt():
+    return load_module("ref_vilt", "models/modeling_vilt.py")
 
 
 def build_reference_model(cfg, params=None):

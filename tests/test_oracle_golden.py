@@ -93,3 +93,20 @@ def test_label_smooth_ce_known_answers():
         q = torch.full_like(x, 0.1 / C).scatter_(1, c["y"].clamp(min=0)[:, None], 0.9)
         closed = ((1 - 0.1 / C) * torch.softmax(x, 1) - q) * valid[:, None] / valid.sum()
         assert torch.allclose(closed.detach(), c["grad"], atol=1e-7, rtol=1e-5), tag
+
+
+def test_preln_stack_oracle_vs_reference_flava_and_vilt_encoders():
+    """oracle.preln_stack against outputs / gradients of the reference FlavaEncoder (modeling_flava.py:668-722) and
+    ViltEncoder (modeling_vilt.py:531-583) stored by oracle/make_golden.py::stack_case."""
+    g = torch.load(os.path.join(GOLD, "preln_stack.pt"), weights_only=False)
+    for tag, c in g.items():
+        P = {k: v.clone().requires_grad_(True) for k, v in c["params"].items()}
+        x = c["x"].clone().requires_grad_(True)
+        y = O.preln_stack(P, x, 2, attention_mask=c["mask"], sep_split=c["sep"][:, 2], row_lo=c["row_lo"])
+        y.backward(c["gy"])
+        assert torch.allclose(y, c["y"], atol=1e-5, rtol=1e-5), tag
+        assert torch.allclose(x.grad, c["dx"], atol=1e-5, rtol=1e-4), tag
+        for n, gr in c["grads"].items():
+            assert torch.allclose(P[n].grad, gr, atol=1e-5, rtol=1e-4), (tag, n)
+        for n, ref_norm in c["grad_norm"].items():
+            assert abs(P[n].grad.norm().item() - ref_norm) <= 2e-4 * ref_norm + 1e-7, (tag, n)
