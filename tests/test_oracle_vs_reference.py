@@ -83,3 +83,45 @@ def test_reference_litmodel_accepts_dropin_module():
     model.load_state_dict(ref_model.state_dict())
     assert torch.equal(model.state_dict()["unimo.encoder.text_layer.3.attention.self.query.weight"],
                        ref_model.state_dict()["unimo.encoder.text_layer.3.attention.self.query.weight"])
+
+
+def test_swap_encoders_into_reference_flava_and_vilt_models():
+    """mkg_analogy_b200.accelerate.swap_encoders on the REAL reference models (FlavaForMaskedLM: image / text / multimodal
+    encoders; ViltForMaskedLM): every pre-LN encoder is replaced, state_dict keys and values are preserved, and the oracle
+    restatement of the stack reproduces the reference encoder the adapter replaces.  (CPU: structure only — the adapter's
+    numerics are GPU-tested against the same reference encoders' golden outputs, tests/test_stack_gpu.py.)"""
+    from transformers import FlavaConfig, ViltConfig
+    from mkg_analogy_b200.accelerate import EncoderAdapter, swap_encoders
+    Fm, Vm = RL.load_flava(), RL.load_vilt()
+    small = dict(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256)
+    fc = FlavaConfig(image_config=dict(small, image_size=32, patch_size=16), text_config=dict(small, vocab_size=300),
+                     multimodal_config=dict(small), hidden_size=128, projection_dim=128)
+    for cfg, cls in ((fc, Fm.FlavaModel), (ViltConfig(**small, vocab_size=300, image_size=64, patch_size=32), Vm.ViltModel)):
+        model = cls(cfg)
+        before = {k: v.clone() for k, v in model.state_dict().items()}
+        n_enc = sum(1 for m in model.modules() if type(m).__name__ in ("FlavaEncoder", "ViltEncoder"))
+        swap_encoders(model, device="cpu")
+        adapters = [m for m in model.modules() if isinstance(m, EncoderAdapter)]
+        assert len(adapters) == n_enc and n_enc >= 1
+        assert not any(type(m).__name__ in ("FlavaEncoder", "ViltEncoder") for m in model.modules())
+        after = model.state_dict()
+        assert set(after) == set(before)
+        assert all(torch.equal(after[k], before[k]) for k in before)
+
+
+def test_preln_stack_oracle_matches_live_reference_encoder_other_seed():
+    from transformers import FlavaTextConfig
+    Fm = RL.load_flava()
+    cfg = FlavaTextConfig(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                          hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    torch.manual_seed(5)
+    enc = Fm.FlavaEncoder(cfg).eval()
+    x = torch.randn(2, 21, 128)
+    mask = torch.ones(2, 21, dtype=torch.long)
+    mask[1, 15:] = 0
+    sep = torch.zeros(2, 6, dtype=torch.long)
+    sep[:, 2] = torch.tensor([9, 5])
+    with torch.no_grad():
+        ref = enc(x, attention_mask=(1.0 - mask[:, None, None, :].float()) * -10000.0, sep_idx=sep).last_hidden_state
+        mine = O.preln_stack(dict(enc.state_dict()), x, 2, attention_mask=mask, sep_split=sep[:, 2], row_lo=1)
+    assert torch.allclose(mine, ref, atol=1e-5, rtol=1e-5)

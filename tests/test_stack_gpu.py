@@ -84,3 +84,26 @@ def test_stack_training_dropout_matches_oracle_masks():
     for n in ("layer.0.attention.attention.query.weight", "layer.2.output.dense.bias", "layer.1.attention.output.dense.bias",
               "layer.0.intermediate.dense.bias", "layer.2.layernorm_after.weight"):
         assert rel(named[n].grad, P[n].grad) <= 6e-2, n
+
+
+@pytest.mark.parametrize("tag", ["flava", "vilt"])
+def test_encoder_adapter_keeps_the_reference_call_signature(tag):
+    """EncoderAdapter is called exactly as FlavaTextModel (modeling_flava.py:1100-1108) / ViltModel (modeling_vilt.py:850-859)
+    call their encoders: additive 4-D mask, sep_idx, img_length; result indexable and with hidden_states[-1]."""
+    from mkg_analogy_b200.accelerate import EncoderAdapter
+    c = torch.load(os.path.join(GOLD, "preln_stack.pt"), weights_only=False)[tag]
+    ad = EncoderAdapter(128, 3, 2, 256, eps=1e-12, act="gelu", device="cuda").eval()
+    ad.load_state_dict(c["params"], strict=True)
+    ext = (1.0 - c["mask"][:, None, None, :].float().cuda()) * -10000.0
+    kw = dict(attention_mask=ext, head_mask=[None] * 3, output_hidden_states=True, return_dict=True, sep_idx=c["sep"].cuda())
+    if tag == "vilt":
+        kw["img_length"] = c["row_lo"] - 1
+    with torch.no_grad():
+        out = ad(c["x"].cuda(), **kw)
+    assert rel(out[0].cpu(), c["y"]) <= 2e-2 and out.hidden_states[-1] is out.last_hidden_state
+    with torch.no_grad():
+        tup = ad(c["x"].cuda(), attention_mask=ext, return_dict=False, sep_idx=c["sep"].cuda(),
+                 img_length=(c["row_lo"] - 1) if tag == "vilt" else None)
+    assert isinstance(tup, tuple) and rel(tup[0].cpu(), c["y"]) <= 2e-2
+    with pytest.raises(NotImplementedError):
+        ad(c["x"].cuda(), output_attentions=True)
