@@ -194,7 +194,8 @@ int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* params16, floa
                        float weight_decay, int32_t pretrain, int64_t begin, int64_t end, int32_t zero_grads, void* stream);
 
 /* Device-side status flags of the last calls on this workspace (synchronises the stream):
- * bit0 token id out of range, bit1 token type out of range, bit2 a row without exactly one [MASK]. */
+ * bit0 token id out of range, bit1 token type out of range, bit2 a row without exactly one [MASK], bit3 a label or a
+ * relaxation-loss position out of range (the reference raises IndexError / asserts in these cases). */
 int32_t b200mart_status(b200mart_handle* h, const b200mart_buffers* bufs, void* stream, int32_t* flags_out);
 
 /* Optional device timing by kernel family, for roofline reporting: between begin and end every tensor-core GEMM

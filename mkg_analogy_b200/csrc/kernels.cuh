@@ -100,10 +100,10 @@ struct LossGroup {
 };
 // label-smoothed CE (lit_models/utils.py:42-66) or plain CE (eps = 0), mean over the group's rows; loss[0] += CE
 int launch_ls_ce(const LossGroup& g, const int64_t* label, const int64_t* pre_type, float eps, float* loss, int B,
-                 cudaStream_t s);
+                 int* status, cudaStream_t s);   // status (may be null): bit 8 = label out of range
 // relaxation loss (lit_models/transformer.py:103-108): loss[0] += alpha * mean(...); dz rows += gradient
 int launch_relaxation(const float* z, const int64_t* rel_idx, const int64_t* q_head, const int64_t* a_head, float alpha,
-                      float* loss, float* dz, int B, int L, int H, cudaStream_t s);
+                      float* loss, float* dz, int B, int L, int H, int* status, cudaStream_t s);
 // dz[b*L + mask_pos[b], :] += dzm[b, :]
 int launch_scatter_mask_rows(const float* dzm, const int* mask_pos, float* dz, int B, int L, int H, cudaStream_t s);
 // rank of gold = 1 + #{c : x[b,c] > x[b,label]}  (lit_models/transformer.py:162-164 without the double sort)

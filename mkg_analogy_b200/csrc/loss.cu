@@ -63,7 +63,7 @@ __device__ __forceinline__ bool row_selected(int select, const int64_t* pre_type
 // loss_b = (sum q) * logsumexp(x) - sum_c q_c x_c ;  dx = ((sum q) softmax(x) - q) / n_selected.
 __global__ void __launch_bounds__(256)
 ls_ce_kernel(const LossGroup g, const int64_t* __restrict__ label, const int64_t* __restrict__ pre_type, float eps, float* loss,
-             int B) {
+             int B, int* status) {
     __shared__ float red[8];
     __shared__ int nsel_s;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -83,7 +83,9 @@ ls_ce_kernel(const LossGroup g, const int64_t* __restrict__ label, const int64_t
         return;
     }
     const float* x = g.logits + (long)b * g.ld;
-    const int y = (int)label[b];
+    long yl = label[b];
+    if (yl < 0 || yl >= C) { if (tid == 0 && status) atomicOr(status, 8); yl = 0; }   // the reference would raise IndexError
+    const int y = (int)yl;
     float mx = -INFINITY, sx = 0.f;
     for (int c = tid; c < C; c += blockDim.x) {
         const float v = x[c];
@@ -115,13 +117,19 @@ ls_ce_kernel(const LossGroup g, const int64_t* __restrict__ label, const int64_t
 // one CTA (128 threads) per sample: relu(cos(z[qh], z[ah])) + 1 - cos(z[r0], z[r1]); torch cosine_similarity eps 1e-8
 __global__ void __launch_bounds__(128)
 relaxation_kernel(const float* __restrict__ z, const int64_t* __restrict__ rel_idx, const int64_t* __restrict__ q_head,
-                  const int64_t* __restrict__ a_head, float alpha, float* loss, float* dz, int B, int L, int H) {
+                  const int64_t* __restrict__ a_head, float alpha, float* loss, float* dz, int B, int L, int H, int* status) {
     __shared__ float red[4];
     const int b = blockIdx.x, tid = threadIdx.x;
-    const float* zq = z + ((long)b * L + q_head[b]) * H;
-    const float* za = z + ((long)b * L + a_head[b]) * H;
-    const float* z0 = z + ((long)b * L + rel_idx[2 * b]) * H;
-    const float* z1 = z + ((long)b * L + rel_idx[2 * b + 1]) * H;
+    long pq = q_head[b], pa = a_head[b], p0 = rel_idx[2 * b], p1 = rel_idx[2 * b + 1];
+    if (pq < 0 || pq >= L || pa < 0 || pa >= L || p0 < 0 || p0 >= L || p1 < 0 || p1 >= L) {
+        if (tid == 0 && status) atomicOr(status, 8);
+        pq = min(max(pq, 0L), (long)L - 1); pa = min(max(pa, 0L), (long)L - 1);
+        p0 = min(max(p0, 0L), (long)L - 1); p1 = min(max(p1, 0L), (long)L - 1);
+    }
+    const float* zq = z + ((long)b * L + pq) * H;
+    const float* za = z + ((long)b * L + pa) * H;
+    const float* z0 = z + ((long)b * L + p0) * H;
+    const float* z1 = z + ((long)b * L + p1) * H;
     float qa = 0, qq = 0, aa = 0, r01 = 0, r00 = 0, r11 = 0;
     for (int c = tid; c < H; c += blockDim.x) {
         const float q = zq[c], a = za[c], u = z0[c], v = z1[c];
@@ -138,10 +146,10 @@ relaxation_kernel(const float* __restrict__ z, const int64_t* __restrict__ rel_i
     if (!dz) return;
     const float gh = cos_h > 0.f ? w : 0.f;   // d relu
     const float gr = -w;
-    float* dq = dz + ((long)b * L + q_head[b]) * H;
-    float* da = dz + ((long)b * L + a_head[b]) * H;
-    float* d0 = dz + ((long)b * L + rel_idx[2 * b]) * H;
-    float* d1 = dz + ((long)b * L + rel_idx[2 * b + 1]) * H;
+    float* dq = dz + ((long)b * L + pq) * H;
+    float* da = dz + ((long)b * L + pa) * H;
+    float* d0 = dz + ((long)b * L + p0) * H;
+    float* d1 = dz + ((long)b * L + p1) * H;
     for (int c = tid; c < H; c += blockDim.x) {
         const float q = zq[c], a = za[c], u = z0[c], v = z1[c];
         // d cos(x,y)/dx = y/(|x||y|) - cos * x/|x|^2   (rows may coincide -> atomics)
@@ -165,7 +173,8 @@ ranks_kernel(const float* __restrict__ logits, long ld, int C, const int64_t* __
     const int b = blockIdx.x;
     if (!row_selected(select, pre_type, b)) return;   // the row belongs to the other column group
     const float* x = logits + (long)b * ld;
-    const float gold = x[label[b]];
+    const long yl = label[b];
+    const float gold = x[(yl < 0 || yl >= C) ? 0 : yl];
     float cnt = 0.f;
     for (int c = threadIdx.x; c < C; c += blockDim.x) cnt += (x[c] > gold) ? 1.f : 0.f;
     cnt = block_reduce_sum(cnt, red);
@@ -186,16 +195,16 @@ int launch_gather_mask_rows(const bf16* z16, const int* mask_pos, bf16* zm, int 
     return 0;
 }
 int launch_ls_ce(const LossGroup& g, const int64_t* label, const int64_t* pre_type, float eps, float* loss, int B,
-                 cudaStream_t s) {
+                 int* status, cudaStream_t s) {
     B2_CHECK(g.C > 0 && g.ldd >= g.C, "ls_ce: bad class count %d / gradient leading dimension %ld", g.C, g.ldd);
     B2_CHECK(g.select == 0 || pre_type != nullptr, "ls_ce: row selection needs pre_type");
-    ls_ce_kernel<<<B, 256, 0, s>>>(g, label, pre_type, eps, loss, B);
+    ls_ce_kernel<<<B, 256, 0, s>>>(g, label, pre_type, eps, loss, B, status);
     B2_LAUNCHED();
     return 0;
 }
 int launch_relaxation(const float* z, const int64_t* rel_idx, const int64_t* q_head, const int64_t* a_head, float alpha,
-                      float* loss, float* dz, int B, int L, int H, cudaStream_t s) {
-    relaxation_kernel<<<B, 128, 0, s>>>(z, rel_idx, q_head, a_head, alpha, loss, dz, B, L, H);
+                      float* loss, float* dz, int B, int L, int H, int* status, cudaStream_t s) {
+    relaxation_kernel<<<B, 128, 0, s>>>(z, rel_idx, q_head, a_head, alpha, loss, dz, B, L, H, status);
     B2_LAUNCHED();
     return 0;
 }

@@ -574,7 +574,7 @@ extern "C" int32_t b200mart_status(b200mart_handle* h, const b200mart_buffers* b
     int v = 0;
     CUDA_TRY(cudaMemcpyAsync(&v, h->ws.status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-    *flags = ((v & 1) ? 1 : 0) | ((v & 2) ? 2 : 0) | ((v & 4) ? 4 : 0);
+    *flags = v & 15;
     return 0;
 }
 
@@ -756,7 +756,7 @@ extern "C" int32_t b200mart_head_loss(b200mart_handle* h, const b200mart_buffers
         lg.logits = w.logits; lg.ld = Cp; lg.C = g.C;
         lg.dlogits16 = compute_grad ? w.dlogits16 : nullptr; lg.ldd = Cp;
         lg.select = g.select;
-        B2_TRY(launch_ls_ce(lg, hd->label, hd->pre_type, hd->label_smoothing, w.loss, B, s));
+        B2_TRY(launch_ls_ce(lg, hd->label, hd->pre_type, hd->label_smoothing, w.loss, B, w.status, s));
         if (compute_grad) {
             // d zm += dlogits E_sel        (M = B, N = H, K = C; B operand stored [K = C][N = H])
             GemmOp op;
@@ -784,7 +784,7 @@ extern "C" int32_t b200mart_head_loss(b200mart_handle* h, const b200mart_buffers
     }
     if (hd->mode == 0)
         B2_TRY(launch_relaxation(w.z32, hd->rel_idx, hd->q_head_idx, hd->a_head_idx, hd->alpha, w.loss, compute_grad ? w.dz : nullptr,
-                                 B, L, H, s));
+                                 B, L, H, w.status, s));
     if (compute_grad) B2_TRY(launch_scatter_mask_rows(w.dzm, w.mask_pos, w.dz, B, L, H, s));
     if (loss_out) CUDA_TRY(cudaMemcpyAsync(loss_out, w.loss, sizeof(float), cudaMemcpyDeviceToDevice, s));
     return 0;
@@ -1267,5 +1267,5 @@ extern "C" int32_t b200mart_ls_ce(const float* logits, int32_t B, int32_t C, con
     B2_CHECK(logits && label && loss, "ls_ce: null argument");
     LossGroup g{};
     g.logits = logits; g.ld = C; g.C = C; g.dlogits32 = dlogits; g.ldd = C; g.select = 0;
-    return launch_ls_ce(g, label, nullptr, eps, loss, B, (cudaStream_t)stream);
+    return launch_ls_ce(g, label, nullptr, eps, loss, B, nullptr, (cudaStream_t)stream);
 }

@@ -198,6 +198,52 @@ class MartTrainer:
         """End-to-end step from (pinned) host tensors: H2D copies, step, D2H read of the loss. Returns a float."""
         return float(self.train_step(self.to_device(host_batch)).item())
 
+    def train_step_host_async(self, host_batch):
+        """Pipelined end-to-end step (what a training loop with asynchronous logging does): this step's inputs are copied
+        host -> device on a copy stream into one of two device staging batches while the previous step is still
+        computing, the step is launched behind that copy, and its loss is copied device -> host into pinned memory.
+        Returns the PREVIOUS step's loss as a float (None on the first call): every step still pays one H2D copy of its
+        inputs and one D2H read of a loss, but neither sits on the critical path.  `drain()` returns the last loss."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage = [None, None]
+            self._stage_free = [None, None]
+            self._loss_host = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
+            self._loss_ev = [None, None]
+            self._n_async = 0
+        k = self._n_async & 1
+        main = torch.cuda.current_stream()
+        if self._stage[k] is None or any(self._stage[k][n].shape != v.shape for n, v in host_batch.items() if n in self._stage[k]):
+            self._stage[k] = {n: torch.empty(v.shape, dtype=v.dtype, device=self.device) for n, v in host_batch.items() if n in BATCH_KEYS}
+            # The caching allocator may hand out blocks that tensors freed on the main stream used moments ago while work
+            # reading / writing them is still queued there; the copy stream is not ordered behind that work.  One full
+            # synchronisation when a staging batch is (re)allocated closes the window (steady state never allocates).
+            torch.cuda.synchronize(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            if self._stage_free[k] is not None:
+                self._copy_stream.wait_event(self._stage_free[k])      # the step that last used this staging batch is done
+            for n, d in self._stage[k].items():
+                d.copy_(host_batch[n], non_blocking=True)
+        main.wait_stream(self._copy_stream)
+        loss = self.train_step(self._stage[k])
+        self._stage_free[k] = torch.cuda.Event()
+        self._stage_free[k].record(main)
+        self._loss_host[k].copy_(loss, non_blocking=True)
+        self._loss_ev[k] = torch.cuda.Event()
+        self._loss_ev[k].record(main)
+        self._n_async += 1
+        prev = k ^ 1
+        if self._loss_ev[prev] is None:
+            return None
+        self._loss_ev[prev].synchronize()
+        return float(self._loss_host[prev].item())
+
+    def drain(self):
+        """Loss of the most recent train_step_host_async call."""
+        k = (self._n_async - 1) & 1
+        self._loss_ev[k].synchronize()
+        return float(self._loss_host[k].item())
+
     def to_device(self, host_batch):
         if self._dev_batch is None or any(self._dev_batch[k].shape != v.shape for k, v in host_batch.items() if k in self._dev_batch):
             self._dev_batch = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host_batch.items()

@@ -413,3 +413,47 @@ def test_pipelined_optimizer_matches_plain_step_and_oracle_adamw():
     cos = torch.nn.functional.cosine_similarity(upd_mine.flatten(), upd_ref.flatten(), dim=0).item()
     assert cos >= 0.98 and abs(upd_mine.norm().item() / upd_ref.norm().item() - 1) <= 0.05, (cos, upd_mine.norm(), upd_ref.norm())
     assert torch.equal(tr1.engine.view("unimo.text_pooler.dense.weight"), params["unimo.text_pooler.dense.weight"].cuda())
+
+
+def test_async_host_step_equals_sync_host_step():
+    """train_step_host_async (copy stream + deferred loss read) computes exactly what train_step_host computes."""
+    from mkg_analogy_b200.config import TINY
+    from mkg_analogy_b200.trainer import MartTrainer, BATCH_KEYS
+    params = init_params(TINY, 11)
+    host = [{k: v.pin_memory() for k, v in make_finetune_batch(4, 24, TINY.image_size, TINY_VOCAB, seed=60 + i, min_len=16).items()
+             if k in BATCH_KEYS} for i in range(4)]
+    res = {}
+    for mode in ("sync", "async"):
+        tr = MartTrainer(TINY, TINY_VOCAB, total_steps=20, lr=1e-3, dropout=False)
+        tr.engine.load(params)
+        if mode == "sync":
+            losses = [tr.train_step_host(b) for b in host]
+        else:
+            out = [tr.train_step_host_async(b) for b in host]
+            assert out[0] is None
+            losses = out[1:] + [tr.drain()]
+        torch.cuda.synchronize()
+        res[mode] = (losses, tr.engine.params32.clone())
+    assert max(abs(a - b) for a, b in zip(res["sync"][0], res["async"][0])) <= 2e-3
+    d = (res["sync"][1] - res["async"][1]).abs()
+    assert d.max().item() <= 2 * 3 * 1e-3 + 1e-6 and d.mean().item() <= 2e-5
+
+
+def test_bad_indices_flag_status_instead_of_faulting(tiny):
+    """Out-of-range labels / relaxation positions / token ids set status bits (the reference raises IndexError)."""
+    g, cfg, params, eng, batch = tiny
+    bad = dict(batch)
+    bad["label"] = batch["label"].clone()
+    bad["label"][1] = 10 ** 9
+    bad["rel_idx"] = batch["rel_idx"].clone()
+    bad["rel_idx"][0, 1] = 77777
+    bad["input_ids"] = batch["input_ids"].clone()
+    bad["input_ids"][2, 3] = cfg.vocab + 5
+    eng.zero_grad()
+    eng.forward(bad, want_z=False)
+    eng.head_loss(bad, ft_head(bad, TINY_VOCAB), compute_grad=True)
+    torch.cuda.synchronize()
+    assert eng.status() == (1 | 8)
+    eng.forward(batch, want_z=False)
+    eng.head_loss(batch, ft_head(batch, TINY_VOCAB), compute_grad=False)
+    assert eng.status() == 0
