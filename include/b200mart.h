@@ -204,6 +204,8 @@ int32_t b200mart_status(b200mart_handle* h, const b200mart_buffers* bufs, void* 
 int32_t b200mart_profile_begin(b200mart_handle* h);
 int32_t b200mart_profile_end(b200mart_handle* h, void* stream, double ms_by_cat[3], int64_t launches_by_cat[3],
                              double* gemm_flops);
+/* algorithmic bytes (operands + epilogue inputs/outputs, each once) of the GEMM launches of the last profiled window */
+double b200mart_profile_gemm_bytes(const b200mart_handle* h);
 
 /* ------------------------------------------------------------------------------------------------
  * Pre-LayerNorm encoder stack: the block FLAVA and ViLT are built from

@@ -111,7 +111,7 @@ struct b200mart_handle {
     struct ProfRec { cudaEvent_t e0, e1; int cat; };
     std::vector<ProfRec> prof;
     size_t prof_used = 0;
-    double prof_flops = 0.0;
+    double prof_flops = 0.0, prof_bytes = 0.0;   // GEMM FLOPs / algorithmic operand+result bytes of the profiled launches
     ~b200mart_handle() {
         for (auto& kv : plans) gemm_plan_destroy(kv.second);
         for (auto* p : segs_dev) if (p) cudaFree(p);
@@ -342,7 +342,18 @@ int run_gemm(b200mart_handle* h, const GemmOp& op, cudaStream_t s) {
         plan = it->second;
     }
     ProfScope ps(h, s, CAT_GEMM);
-    if (h->profiling) h->prof_flops += gemm_plan_flops(plan);
+    if (h->profiling) {
+        h->prof_flops += gemm_plan_flops(plan);
+        // algorithmic bytes of this product: both operands once, every epilogue input and output once
+        double b = 2.0 * ((double)op.M * (op.K1 + op.K2) + (double)op.N * (op.K1 + op.K2));
+        const double mn = (double)op.M * op.N;
+        if (op.out_f32) b += (op.accumulate ? 8.0 : 4.0) * mn;
+        if (op.out_bf16) b += 2.0 * mn;
+        if (op.out_preact) b += 2.0 * mn;
+        if (op.residual) b += 4.0 * mn;
+        if (op.dact_src) b += 2.0 * mn;
+        h->prof_bytes += b;
+    }
     return gemm_plan_launch(plan, s, op.drop.thresh ? &op.drop : nullptr);
 }
 
@@ -987,11 +998,14 @@ extern "C" int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* par
 }
 
 // --------------------------------------------------------------------------------------- profiling
+extern "C" double b200mart_profile_gemm_bytes(const b200mart_handle* h) { return h ? h->prof_bytes : 0.0; }
+
 extern "C" int32_t b200mart_profile_begin(b200mart_handle* h) {
     B2_CHECK(h, "profile_begin: null handle");
     h->profiling = true;
     h->prof_used = 0;
     h->prof_flops = 0.0;
+    h->prof_bytes = 0.0;
     return 0;
 }
 

@@ -297,6 +297,7 @@ class Engine:
         """{'gemm'|'attention'|'fusion': (device ms, launches)}, gemm flops."""
         ms, n, fl = (C.c_double * 3)(), (_lib.i64 * 3)(), C.c_double()
         _lib.check(self.l.b200mart_profile_end(self.h, _lib.cur_stream(), C.byref(ms), C.byref(n), C.byref(fl)))
+        self.last_profile_gemm_bytes = float(self.l.b200mart_profile_gemm_bytes(self.h))
         return {k: (ms[i], n[i]) for i, k in enumerate(("gemm", "attention", "fusion"))}, fl.value
 
     def status(self):
