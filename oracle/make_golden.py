@@ -153,6 +153,55 @@ def stack_case():
     return out
 
 
+def vilt_case():
+    """Reference ViltForMaskedLM (modeling_vilt.py:896-968) on a tiny config: logits / trans_hidden of the text rows (the
+    only rows MarT reads; they do not depend on the reference's random patch permutation) and a few gradients."""
+    from transformers import ViltConfig
+    Vm = RL.load_vilt()
+    cfg = ViltConfig(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, vocab_size=300,
+                     image_size=64, patch_size=32, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    torch.manual_seed(41)
+    ref = Vm.ViltForMaskedLM(cfg).eval()
+    with torch.no_grad():
+        for n, prm in ref.named_parameters():
+            if prm.dim() >= 2:
+                prm.normal_(0, 0.05)
+            elif "adaptive_weight.0" in n:
+                prm.fill_(0.25)
+            elif "adaptive_weight.1" in n:
+                prm.fill_(0.5)
+            elif "ayer" in n and "norm" in n.lower() and n.endswith("weight"):
+                prm.normal_(1.0, 0.1)
+            else:
+                prm.normal_(0, 0.05)
+    ref.mlm_score.decoder.weight = ref.vilt.embeddings.text_embeddings.word_embeddings.weight   # tie (main.py:121; 4.19 did it)
+    g = torch.Generator().manual_seed(42)
+    B, L = 3, 48                                       # longer than max_position_embeddings = 40 on purpose
+    ids = torch.randint(5, 300, (B, L), generator=g)
+    lens = torch.tensor([48, 41, 30])
+    mask = (torch.arange(L)[None] < lens[:, None]).long()
+    ids = ids * mask
+    tt = (torch.arange(L)[None] > torch.tensor([20, 18, 9])[:, None]).long() * mask
+    px = torch.randn(B, 2, 3, 64, 64, generator=g)
+    sep = torch.zeros(B, 6, dtype=torch.long)
+    sep[:, 2] = torch.tensor([20, 18, 9])
+    out = ref(input_ids=ids, attention_mask=mask, token_type_ids=tt, pixel_values=px, sep_idx=sep.clone(), return_dict=True)
+    logits, trans = out[0].logits, out[1]
+    gl = torch.randn(logits.shape, generator=g) * 1e-2
+    gt = torch.randn(trans.shape, generator=g) * 1e-1
+    ((logits * gl).sum() + (trans * gt).sum()).backward()
+    names = ["vilt.embeddings.text_embeddings.word_embeddings.weight", "vilt.embeddings.patch_embeddings.projection.weight",
+             "vilt.embeddings.position_embeddings", "vilt.embeddings.cls_token", "vilt.embeddings.token_type_embeddings.weight",
+             "vilt.encoder.layer.1.attention.attention.value.weight", "vilt.encoder.layer.0.attention.attention.adaptive_weight.1",
+             "vilt.layernorm.weight", "mlm_score.transform.dense.weight", "mlm_score.bias"]
+    prm = dict(ref.named_parameters())
+    return dict(cfg=dict(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, vocab_size=300,
+                         image_size=64, patch_size=32),
+                params={k: v.detach().clone() for k, v in ref.state_dict().items()}, ids=ids, mask=mask, tt=tt, px=px, sep=sep,
+                logits=logits.detach().clone(), trans=trans.detach().clone(), gl=gl, gt=gt,
+                grads={n: prm[n].grad.clone() for n in names})
+
+
 if __name__ == "__main__":
     assert RL.available(), "reference tree not found"
     os.makedirs(GOLD, exist_ok=True)
@@ -160,5 +209,6 @@ if __name__ == "__main__":
     torch.save(tiny_case(), os.path.join(GOLD, "mkgformer_tiny.pt"))
     torch.save(loss_case(), os.path.join(GOLD, "ls_ce.pt"))
     torch.save(stack_case(), os.path.join(GOLD, "preln_stack.pt"))
+    torch.save(vilt_case(), os.path.join(GOLD, "vilt_tiny.pt"))
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))

@@ -33,6 +33,12 @@ def _install_shims():
             mod.find_pruneable_heads_and_indices = _no_prune
         if not hasattr(mod, "prune_linear_layer"):
             mod.prune_linear_layer = pu.prune_linear_layer
+    # 4.19 signatures the vendored ViLT / FLAVA models rely on
+    if not getattr(mu.PreTrainedModel, "_b200_shimmed", False):
+        mu.PreTrainedModel.get_head_mask = lambda self, hm, n, is_attention_chunked=False: [None] * n
+        mu.PreTrainedModel.get_extended_attention_mask = lambda self, m, shape=None, device=None, dtype=None: \
+            (1.0 - (m[:, None, None, :] if m.dim() == 2 else m[:, None, :, :]).float()) * -10000.0
+        mu.PreTrainedModel._b200_shimmed = True
     if "pytorch_lightning" not in sys.modules:
         pl = types.ModuleType("pytorch_lightning")
 

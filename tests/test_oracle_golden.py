@@ -110,3 +110,45 @@ def test_preln_stack_oracle_vs_reference_flava_and_vilt_encoders():
             assert torch.allclose(P[n].grad, gr, atol=1e-5, rtol=1e-4), (tag, n)
         for n, ref_norm in c["grad_norm"].items():
             assert abs(P[n].grad.norm().item() - ref_norm) <= 2e-4 * ref_norm + 1e-7, (tag, n)
+
+
+def _vilt_with_oracle_encoder(c):
+    """ViltKGC's PyTorch plumbing (embeddings, final LN, head) with the ORACLE pre-LN stack injected in place of the CUDA
+    encoder — test infrastructure only: lets the CPU suite pin the plumbing against the reference ViltForMaskedLM."""
+    from mkg_analogy_b200.modeling_vilt import ViltKGC
+    m = ViltKGC(device="cpu", **c["cfg"])
+    m.load_state_dict(c["params"])
+    m.tie_weights()
+
+    class OracleEncoder(torch.nn.Module):
+        def __init__(self, st):
+            super().__init__()
+            self.st = st
+
+        def forward(self, x, attention_mask=None, sep_idx=None, row_lo=1):
+            P = dict(self.st.named_parameters())
+            return O.preln_stack(P, x, c["cfg"]["num_attention_heads"], attention_mask=attention_mask,
+                                 sep_split=None if sep_idx is None else sep_idx[:, 2], row_lo=row_lo)
+    m.vilt.encoder = OracleEncoder(m.vilt.encoder)
+    return m.eval()
+
+
+def test_vilt_dropin_plumbing_vs_reference_golden():
+    """ViltKGC (embeddings incl. the 40-position quirk, [text, img1, img2] layout, modality embeddings, sep_idx + img_length,
+    final LN, first-L rows, tied MLM head) == reference ViltForMaskedLM on the text rows, although the reference permutes the
+    image patches randomly (self-attention is permutation-equivariant)."""
+    c = torch.load(os.path.join(GOLD, "vilt_tiny.pt"), weights_only=False)
+    m = _vilt_with_oracle_encoder(c)
+    sep = c["sep"].clone()
+    out = m(input_ids=c["ids"], attention_mask=c["mask"], token_type_ids=c["tt"], pixel_values=c["px"], sep_idx=sep)
+    assert torch.equal(sep, c["sep"])                     # unlike the reference, the caller's sep_idx is not mutated
+    assert torch.allclose(out[0].logits, c["logits"], atol=2e-5, rtol=1e-4)
+    assert torch.allclose(out[1], c["trans"], atol=2e-5, rtol=1e-4)
+    ((out[0].logits * c["gl"]).sum() + (out[1] * c["gt"]).sum()).backward()
+    prm = dict(m.named_parameters())
+    for n, gr in c["grads"].items():
+        key = n.replace("vilt.encoder.", "vilt.encoder.st.")
+        assert torch.allclose(prm[key].grad, gr, atol=1e-5, rtol=2e-4), n
+    assert m.get_output_embeddings().weight is m.get_input_embeddings().weight
+    emb = m.resize_token_embeddings(305)
+    assert emb.weight.shape[0] == 305 and m.get_output_embeddings().weight is emb.weight and m.mlm_score.bias.shape[0] == 305
