@@ -202,6 +202,60 @@ def vilt_case():
                 grads={n: prm[n].grad.clone() for n in names})
 
 
+def flava_case():
+    """Reference FlavaForMaskedLM (modeling_flava.py:2127-2204) on a tiny config: logits / trans_hidden_states (text rows of
+    the multimodal encoder) and a few gradients from each of the three towers."""
+    from transformers import FlavaConfig
+    Fm = RL.load_flava()
+    small = dict(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256)
+    cfg = dict(image_config=dict(small, image_size=32, patch_size=16),
+               text_config=dict(small, vocab_size=300, max_position_embeddings=64),
+               multimodal_config=dict(small), hidden_size=128, projection_dim=64)
+    torch.manual_seed(51)
+    ref = Fm.FlavaForMaskedLM(FlavaConfig(**cfg)).eval()
+    with torch.no_grad():
+        for n, prm in ref.named_parameters():
+            if prm.dim() >= 2 and "token" not in n:
+                prm.normal_(0, 0.05)
+            elif "adaptive_weight.0" in n:
+                prm.fill_(0.25)
+            elif "adaptive_weight.1" in n:
+                prm.fill_(0.5)
+            elif "ayer" in n and "norm" in n.lower() and n.endswith("weight"):
+                prm.normal_(1.0, 0.1)
+            elif n != "flava.logit_scale":
+                prm.normal_(0, 0.05)
+    ref.cls.decoder.weight = ref.flava.text_model.embeddings.word_embeddings.weight      # tie (4.19 did it in post_init)
+    g = torch.Generator().manual_seed(52)
+    B, L = 3, 40
+    ids = torch.randint(5, 300, (B, L), generator=g)
+    lens = torch.tensor([40, 33, 25])
+    mask = (torch.arange(L)[None] < lens[:, None]).long()
+    ids = ids * mask
+    tt = (torch.arange(L)[None] > torch.tensor([17, 15, 8])[:, None]).long() * mask
+    px = torch.randn(B, 2, 3, 32, 32, generator=g)
+    sep = torch.zeros(B, 6, dtype=torch.long)
+    sep[:, 2] = torch.tensor([17, 15, 8])
+    out = ref(input_ids=ids, attention_mask=mask, token_type_ids=tt, pixel_values=px, sep_idx=sep.clone(), return_dict=True)
+    logits, trans = out[0].logits, out[1]
+    gl = torch.randn(logits.shape, generator=g) * 1e-2
+    gt = torch.randn(trans.shape, generator=g) * 1e-1
+    ((logits * gl).sum() + (trans * gt).sum()).backward()
+    names = ["flava.text_model.embeddings.word_embeddings.weight", "flava.text_model.embeddings.position_embeddings.weight",
+             "flava.image_model.embeddings.patch_embeddings.projection.weight", "flava.image_model.embeddings.position_embeddings",
+             "flava.image_model.embeddings.cls_token", "flava.multimodal_model.cls_token",
+             "flava.text_model.encoder.layer.1.attention.attention.value.weight",
+             "flava.text_model.encoder.layer.0.attention.attention.adaptive_weight.1",
+             "flava.image_model.encoder.layer.0.intermediate.dense.weight",
+             "flava.multimodal_model.encoder.layer.1.output.dense.weight", "flava.multimodal_model.layernorm.weight",
+             "flava.image_to_mm_projection.weight", "flava.text_to_mm_projection.bias", "cls.transform.dense.weight", "cls.bias"]
+    prm = dict(ref.named_parameters())
+    unused = sorted(n for n, v in prm.items() if v.grad is None)
+    return dict(cfg=cfg, params={k: v.detach().clone() for k, v in ref.state_dict().items()}, ids=ids, mask=mask, tt=tt, px=px,
+                sep=sep, logits=logits.detach().clone(), trans=trans.detach().clone(), gl=gl, gt=gt,
+                grads={n: prm[n].grad.clone() for n in names}, unused=unused)
+
+
 if __name__ == "__main__":
     assert RL.available(), "reference tree not found"
     os.makedirs(GOLD, exist_ok=True)
@@ -210,5 +264,6 @@ if __name__ == "__main__":
     torch.save(loss_case(), os.path.join(GOLD, "ls_ce.pt"))
     torch.save(stack_case(), os.path.join(GOLD, "preln_stack.pt"))
     torch.save(vilt_case(), os.path.join(GOLD, "vilt_tiny.pt"))
+    torch.save(flava_case(), os.path.join(GOLD, "flava_tiny.pt"))
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))

@@ -152,3 +152,42 @@ def test_vilt_dropin_plumbing_vs_reference_golden():
     assert m.get_output_embeddings().weight is m.get_input_embeddings().weight
     emb = m.resize_token_embeddings(305)
     assert emb.weight.shape[0] == 305 and m.get_output_embeddings().weight is emb.weight and m.mlm_score.bias.shape[0] == 305
+
+
+def test_flava_dropin_plumbing_vs_reference_golden():
+    """FlavaKGC's PyTorch plumbing (image embeddings with the image-2 position quirk, text embeddings, mm projections on the
+    pre-final-LN states, [cls ; image ; text] multimodal input without a mask, final LN, last-L rows, tied MLM head) with the
+    ORACLE pre-LN stack injected as the three encoders (test infrastructure only) == reference FlavaForMaskedLM."""
+    from mkg_analogy_b200.modeling_flava import FlavaKGC
+    c = torch.load(os.path.join(GOLD, "flava_tiny.pt"), weights_only=False)
+    m = FlavaKGC(device="cpu", **c["cfg"])
+    m.load_state_dict(c["params"])
+    m.tie_weights()
+
+    class OracleEncoder(torch.nn.Module):
+        def __init__(self, st):
+            super().__init__()
+            self.st = st
+
+        def forward(self, x, attention_mask=None, sep_idx=None, row_lo=1):
+            return O.preln_stack(dict(self.st.named_parameters()), x, 2, attention_mask=attention_mask,
+                                 sep_split=None if sep_idx is None else sep_idx[:, 2], row_lo=row_lo)
+    for tower in (m.flava.image_model, m.flava.text_model, m.flava.multimodal_model):
+        tower.encoder = OracleEncoder(tower.encoder)
+    m.eval()
+    out = m(input_ids=c["ids"], attention_mask=c["mask"], token_type_ids=c["tt"], pixel_values=c["px"], sep_idx=c["sep"].clone())
+    assert torch.allclose(out[0].logits, c["logits"], atol=2e-5, rtol=1e-4)
+    assert torch.allclose(out[1], c["trans"], atol=2e-5, rtol=1e-4)
+    ((out[0].logits * c["gl"]).sum() + (out[1] * c["gt"]).sum()).backward()
+    prm = dict(m.named_parameters())
+    for n, gr in c["grads"].items():
+        key = n.replace(".encoder.", ".encoder.st.")
+        assert torch.allclose(prm[key].grad, gr, atol=2e-5, rtol=2e-4), n
+    # parameters the reference never reaches stay without gradient here too (pooler, contrastive heads, final LNs of the towers)
+    for n in c["unused"]:
+        if "adaptive_weight" in n:
+            continue                      # oracle stack returns zeros for scaling weights of unscaled towers
+        assert prm[n.replace(".encoder.", ".encoder.st.")].grad is None, n
+    assert m.get_output_embeddings().weight is m.get_input_embeddings().weight
+    emb = m.resize_token_embeddings(305)
+    assert emb.weight.shape[0] == 305 and m.get_output_embeddings().weight is emb.weight and m.cls.bias.shape[0] == 305

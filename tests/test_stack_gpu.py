@@ -128,3 +128,24 @@ def test_vilt_dropin_model_vs_reference_golden():
     for n, gr in c["grads"].items():
         e = rel(prm[n].grad.cpu(), gr)
         assert e <= (0.25 if "adaptive_weight" in n else 6e-2), (n, e)
+
+
+def test_flava_dropin_model_vs_reference_golden():
+    """FlavaKGC end to end on the GPU (three CUDA encoder stacks + torch plumbing) against the reference FlavaForMaskedLM
+    fixture: logits, trans_hidden_states and parameter gradients from every tower."""
+    from mkg_analogy_b200.modeling_flava import FlavaKGC
+    c = torch.load(os.path.join(GOLD, "flava_tiny.pt"), weights_only=False)
+    m = FlavaKGC(device="cuda", **c["cfg"])
+    m.load_state_dict(c["params"])
+    m.tie_weights()
+    m.eval()
+    out = m(input_ids=c["ids"].cuda(), attention_mask=c["mask"].cuda(), token_type_ids=c["tt"].cuda(), pixel_values=c["px"].cuda(),
+            sep_idx=c["sep"].cuda(), return_dict=True)
+    logits, trans = out[0].logits, out[1]
+    print(f"flava: logits rel err {rel(logits.detach().cpu(), c['logits']):.3e}, trans {rel(trans.detach().cpu(), c['trans']):.3e}")
+    assert rel(logits.detach().cpu(), c["logits"]) <= 2e-2 and rel(trans.detach().cpu(), c["trans"]) <= 2e-2
+    ((logits * c["gl"].cuda()).sum() + (trans * c["gt"].cuda()).sum()).backward()
+    prm = dict(m.named_parameters())
+    for n, gr in c["grads"].items():
+        e = rel(prm[n].grad.cpu(), gr)
+        assert e <= (0.25 if "adaptive_weight" in n else 6e-2), (n, e)
