@@ -18,6 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .modeling import MaskedLMOutput
+from .pretrained import PretrainedMixin, init_hf_style
 from .stack import EncoderStack
 
 DEFAULTS = dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072, layer_norm_eps=1e-12,
@@ -133,7 +134,7 @@ class _Head(nn.Module):
         self.decoder.bias = self.bias
 
 
-class FlavaKGC(nn.Module):
+class FlavaKGC(PretrainedMixin, nn.Module):
     def __init__(self, config=None, device=None, image_config=None, text_config=None, multimodal_config=None, hidden_size=None,
                  projection_dim=None):
         super().__init__()
@@ -152,6 +153,7 @@ class FlavaKGC(nn.Module):
             device = "cuda" if torch.cuda.is_available() else "cpu"
         self.flava = _Flava(ic, tc, mc, hidden_size, projection_dim or 768, device)
         self.cls = _Head(tc["hidden_size"], tc["vocab_size"], tc["layer_norm_eps"])
+        init_hf_style(self, tc["initializer_range"])
         self.tie_weights()
         self.to(device)          # EncoderStack._apply is a no-op for its own device
 

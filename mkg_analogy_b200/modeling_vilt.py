@@ -20,6 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .modeling import MaskedLMOutput
+from .pretrained import PretrainedMixin, init_hf_style
 from .stack import EncoderStack
 
 
@@ -112,7 +113,7 @@ DEFAULTS = dict(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_att
                 initializer_range=0.02)
 
 
-class ViltKGC(nn.Module):
+class ViltKGC(PretrainedMixin, nn.Module):
     def __init__(self, config=None, device=None, **overrides):
         super().__init__()
         cfg = dict(DEFAULTS)
@@ -126,6 +127,7 @@ class ViltKGC(nn.Module):
             device = "cuda" if torch.cuda.is_available() else "cpu"
         self.vilt = _Vilt(cfg, device)
         self.mlm_score = _MLMHead(cfg["hidden_size"], cfg["vocab_size"], cfg["layer_norm_eps"])
+        init_hf_style(self, cfg["initializer_range"])
         self.tie_weights()
         for m in (self.vilt.embeddings, self.vilt.layernorm, self.vilt.pooler, self.mlm_score):
             m.to(device)

@@ -217,3 +217,37 @@ def test_layer_extents_partition_the_encoder():
             assert inside == [layer], p.name
         else:
             assert inside == [], p.name
+
+
+@pytest.mark.parametrize("family", ["vilt", "flava"])
+def test_from_pretrained_local_checkpoint(tmp_path, family):
+    """`model_class.from_pretrained(path[, config=config])` (MarT/main.py:119-125) on a local HF-layout directory:
+    config.json + safetensors / .bin weights load by name, absent tensors are initialised HF-style, the decoder stays tied."""
+    import os
+    from safetensors.torch import save_file
+    GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    c = torch.load(os.path.join(GOLD, f"{family}_tiny.pt"), weights_only=False)
+    if family == "vilt":
+        from transformers import ViltConfig as Cfg
+        from mkg_analogy_b200.modeling_vilt import ViltKGC as M
+        head = "mlm_score."
+    else:
+        from transformers import FlavaConfig as Cfg
+        from mkg_analogy_b200.modeling_flava import FlavaKGC as M
+        head = "cls."
+    Cfg(**c["cfg"]).save_pretrained(tmp_path)
+    body = {k: v.contiguous() for k, v in c["params"].items() if not k.startswith(head) and "position_ids" not in k}
+    if family == "vilt":
+        save_file(body, os.path.join(tmp_path, "model.safetensors"))
+    else:
+        torch.save(body, os.path.join(tmp_path, "pytorch_model.bin"))
+    m = M.from_pretrained(str(tmp_path), device="cpu")
+    sd = m.state_dict()
+    for k, v in body.items():
+        assert torch.equal(sd[k], v), k
+    assert all(k.startswith(head) or "position_ids" in k for k in m.loading_info["missing_keys"]), m.loading_info
+    assert m.get_output_embeddings().weight is m.get_input_embeddings().weight
+    dense = sd[head + "transform.dense.weight"]
+    assert 0.01 < dense.std().item() < 0.03 and sd[head + "transform.dense.bias"].abs().max().item() == 0.0
+    m2 = M.from_pretrained(str(tmp_path), config=Cfg(**c["cfg"]), device="cpu")     # explicit config, as main.py:123 passes it
+    assert torch.equal(m2.state_dict()[next(iter(body))], body[next(iter(body))])
