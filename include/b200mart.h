@@ -206,6 +206,12 @@ int32_t b200mart_profile_end(b200mart_handle* h, void* stream, double ms_by_cat[
                              double* gemm_flops);
 /* algorithmic bytes (operands + epilogue inputs/outputs, each once) of the GEMM launches of the last profiled window */
 double b200mart_profile_gemm_bytes(const b200mart_handle* h);
+/* Intra-kernel timeline of the tensor-core product (profiling runs only, never inside a timed region): while a device buffer
+ * of `records` x 148 x 16 uint64 is registered, the i-th GEMM launch writes, per CTA, clock64 stamps of its phases (entry,
+ * prologue done, first TMA issued, first operands landed, first tile's MMAs issued / retired, first / last tile's epilogue
+ * done, exit) plus globaltimer at entry/exit, tile count, SM id and the problem shape (gemm_kernel.cuh: GemmStamp).
+ * Passing NULL switches it off. Returns the number of launches recorded since the previous call. */
+int64_t b200mart_gemm_timeline(void* device_buffer, int64_t records);
 
 /* ------------------------------------------------------------------------------------------------
  * Pre-LayerNorm encoder stack: the block FLAVA and ViLT are built from

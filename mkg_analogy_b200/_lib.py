@@ -97,6 +97,7 @@ SYMBOLS = {
     "b200mart_profile_begin": (i32, [vp]),
     "b200mart_profile_end": (i32, [vp, vp, C.POINTER(C.c_double * 3), C.POINTER(i64 * 3), C.POINTER(C.c_double)]),
     "b200mart_profile_gemm_bytes": (C.c_double, [vp]),
+    "b200mart_gemm_timeline": (i64, [vp, i64]),
     "b200mart_gemm_bf16": (i32, [C.POINTER(GemmDesc), vp]),
     "b200mart_create": (i32, [C.POINTER(ModelDesc), C.POINTER(vp)]),
     "b200mart_destroy": (None, [vp]),

@@ -23,7 +23,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int GEMM_THREADS = 192;
 constexpr int EPI_COLS = 64;   // columns per epilogue pass
-constexpr int EPI_LD = 65;     // padded row of the per-warp transpose buffer (fp32 words)
+constexpr int EPI_LD = 66;     // padded row of the per-warp transpose buffer (fp32 words; even: rows stay 8-byte aligned)
 
 // fused epilogues (compile-time).  Every kind except GENERIC requires even N and even leading dimensions.
 enum EpiKind {
@@ -52,8 +52,45 @@ struct GemmDev {
     int accumulate;
     DropCfg drop;                            // dropout on (acc*alpha + bias) before the residual add (EPI_RES / GENERIC)
     float* colsum_out; float* colsum_out2;   // EPI_DACT: += column sums of the output (bias gradient of the producing layer)
+    unsigned long long* prof;   // b200mart_gemm_timeline: 16 stamps per CTA (null = off), see GemmStamp
     int debug;   // B200MART_GEMM_DEBUG bitmask (bring-up only): 1 no epilogue global access, 2 no TMA, 4 no MMA
 };
+
+
+// Intra-kernel timeline (b200mart_gemm_timeline; profiling runs only): per CTA 16 x u64
+enum GemmStamp {
+    ST_GT_START = 0, ST_CLK_START, ST_CLK_PROLOGUE, ST_CLK_TMA0, ST_CLK_FULL0, ST_CLK_MMA_ISSUED0, ST_CLK_TFULL0, ST_CLK_EPI0,
+    ST_CLK_EPI_LAST, ST_CLK_END, ST_GT_END, ST_TILES_SMID, ST_SHAPE_MN, ST_SHAPE_K_GRID, ST_KIND, ST_UNUSED
+};
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint32_t smid() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void stamp(const GemmDev& p, int slot) {
+    if (p.prof) p.prof[(size_t)blockIdx.x * 16 + slot] = (unsigned long long)clock64();
+}
+__device__ __forceinline__ void stamp_begin(const GemmDev& p, int kind, int bn) {
+    if (!p.prof) return;
+    unsigned long long* r = p.prof + (size_t)blockIdx.x * 16;
+    r[ST_GT_START] = gtimer();
+    r[ST_CLK_START] = (unsigned long long)clock64();
+    r[ST_SHAPE_MN] = ((unsigned long long)(uint32_t)p.N << 32) | (uint32_t)p.M;
+    r[ST_SHAPE_K_GRID] = ((unsigned long long)gridDim.x << 32) | (uint32_t)p.kb_total;
+    r[ST_KIND] = ((unsigned long long)(uint32_t)bn << 32) | (uint32_t)kind;
+}
+__device__ __forceinline__ void stamp_end(const GemmDev& p, int tiles) {
+    if (!p.prof) return;
+    unsigned long long* r = p.prof + (size_t)blockIdx.x * 16;
+    r[ST_CLK_END] = (unsigned long long)clock64();
+    r[ST_GT_END] = gtimer();
+    r[ST_TILES_SMID] = ((unsigned long long)smid() << 32) | (uint32_t)tiles;
+}
 
 template <int BN>
 struct SmemLayout {
@@ -77,7 +114,7 @@ __device__ __forceinline__ float act_fwd(int act, float v) {
 }
 __device__ __forceinline__ float act_grad(int act, float x) { return act == 1 ? gelu_erf_grad(x) : quick_gelu_grad(x); }
 
-// Per-pass epilogue inputs that come from HBM (residual / saved pre-activation): one 32-row x 64-column block,
+// Per-pass epilogue inputs that come from HBM (residual / saved activation derivative): one 32-row x 64-column block,
 // lane = column pair, ALL 32 rows issued back to back so that a warp keeps 32 x 256 B (128 B) loads in flight; they are
 // issued before the TMEM read + transpose of the pass (pass 0: before the accumulator-ready wait).
 template <int EPI>
@@ -85,40 +122,68 @@ struct EpiIn {
     static constexpr bool kRes = (EPI == EPI_RES), kDact = (EPI == EPI_DACT);
     float2 rs[kRes ? 32 : 1];
     uint32_t xs[kDact ? 32 : 1];
+    template <bool FULL>
+    __device__ __forceinline__ void load_t(const GemmDev& p, int row0, int nrows, int col) {
+        if (kRes) {
+            const float* rp = p.residual + (long)row0 * p.ldr + col;
+            const int ld = (int)p.ldr;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+                if (FULL || rr < nrows) rs[rr] = *reinterpret_cast<const float2*>(rp + rr * ld);
+        }
+        if (kDact) {
+            const bf16* xp = p.dact_src + (long)row0 * p.ldx + col;
+            const int ld = (int)p.ldx;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+                if (FULL || rr < nrows) xs[rr] = *reinterpret_cast<const uint32_t*>(xp + rr * ld);
+        }
+    }
     __device__ __forceinline__ void load(const GemmDev& p, int row0, int nrows, int col0, int lane) {
         const int col = col0 + 2 * lane;
         if (!(kRes || kDact) || col >= p.N) return;
-#pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
-            if (rr < nrows) {
-                const long row = row0 + rr;
-                if (kRes) rs[rr] = *reinterpret_cast<const float2*>(p.residual + row * p.ldr + col);
-                if (kDact) xs[rr] = *reinterpret_cast<const uint32_t*>(p.dact_src + row * p.ldx + col);
-            }
-        }
+        if (nrows >= 32) load_t<true>(p, row0, nrows, col);
+        else load_t<false>(p, row0, nrows, col);
     }
 };
 
-// activation value and derivative from one evaluation of the transcendental part
+// activation value and derivative from ONE exponential.
+//   exact GELU: y = x Phi(x), y' = Phi(x) + x phi(x); Phi through erf(z) = 1 - P(t) exp(-z^2), t = 1 / (1 + 0.3275911 z)
+//   (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 - far inside the bf16 rounding of the outputs), with z = |x| / sqrt(2) so
+//   that exp(-z^2) = exp(-x^2 / 2) is also the Gaussian of the derivative: one MUFU.EX2 + one MUFU.RCP per element.
+__device__ __forceinline__ float rcp_fast(float x) {      // MUFU.RCP (1 ulp), no denormal / special-case slow path
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 template <int ACT> __device__ __forceinline__ void act_both(float x, float& y, float& dy) {
-    if (ACT == 1) {          // exact (erf) GELU: y = x Phi(x), y' = Phi(x) + x phi(x)
-        const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+    if (ACT == 1) {
+        const float ax = fabsf(x);
+        const float t = rcp_fast(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
+        const float e = __expf(-0.5f * x * x);
+        float q = fmaf(1.061405429f, t, -1.453152027f);
+        q = fmaf(q, t, 1.421413741f);
+        q = fmaf(q, t, -0.284496736f);
+        q = fmaf(q, t, 0.254829592f);
+        const float h = 0.5f * q * t * e;             // = 0.5 erfc(|x| / sqrt 2) = Phi(-|x|)
+        const float cdf = (x >= 0.f) ? 1.0f - h : h;
         y = x * cdf;
-        dy = cdf + x * 0.39894228040143268f * __expf(-0.5f * x * x);
+        dy = fmaf(x * 0.39894228040143268f, e, cdf);
     } else {                 // quick GELU: y = x s, s = sigmoid(1.702 x), y' = s + 1.702 x s (1 - s)
-        const float sg = 1.0f / (1.0f + __expf(-1.702f * x));
+        const float sg = rcp_fast(1.0f + __expf(-1.702f * x));
         y = x * sg;
-        dy = sg + 1.702f * x * sg * (1.0f - sg);
+        dy = fmaf(1.702f * y, 1.0f - sg, sg);
     }
 }
 
-// One 32-row x 64-column block of the output, values staged in `stg` (row-major, EPI_LD), lane = column pair.
-// ACT: compile-time activation (1 gelu-erf, 2 quick-gelu) for EPI_ACT / EPI_DACT.
+// One row of a 32-row x 64-column block: values staged in `stg` (row-major, EPI_LD), lane = column pair.
+// ACT: compile-time activation (1 gelu-erf, 2 quick-gelu) for EPI_ACT.  Ragged / generic-flag variant (runtime checks).
 template <int EPI, int ACT>
 __device__ __forceinline__ void epilogue_row(const GemmDev& p, const float* stg, float2 rs, uint32_t xs, long row, int rr, int col,
                                              float b0, float b1, int lane, float& cs0, float& cs1) {
-    const float v0 = stg[rr * EPI_LD + 2 * lane] * p.alpha + b0;
-    const float v1 = stg[rr * EPI_LD + 2 * lane + 1] * p.alpha + b1;
+    const float2 a = *reinterpret_cast<const float2*>(stg + rr * EPI_LD + 2 * lane);
+    const float v0 = fmaf(a.x, p.alpha, b0);
+    const float v1 = fmaf(a.y, p.alpha, b1);
     if (EPI == EPI_BF16) {
         *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(v0, v1);
     } else if (EPI == EPI_ACT) {
@@ -150,11 +215,84 @@ __device__ __forceinline__ void epilogue_row(const GemmDev& p, const float* stg,
     }
 }
 
+// Full block (32 valid rows, valid column pair): no predicates and no per-row branches, so the rows are independent
+// straight-line chains the scheduler interleaves (the epilogue warps have no other latency hiding: one warp per scheduler);
+// per-row addresses are 32-bit offsets from per-pass base pointers.  DROP / OUT16 / SAVEG: hoisted runtime flags.
+template <int EPI, int ACT, bool DROP, bool OUT16, bool SAVEG>
+__device__ __forceinline__ void epilogue_rows_full(const GemmDev& p, const float* stg, const EpiIn<EPI>& in, int row0, int col,
+                                                   float b0, float b1, int lane) {
+    constexpr bool kF32 = (EPI == EPI_RES || EPI == EPI_F32 || EPI == EPI_ACC);
+    constexpr bool k16 = (EPI == EPI_BF16 || EPI == EPI_ACT || EPI == EPI_DACT || (EPI == EPI_RES && OUT16));
+    const float* sp = stg + 2 * lane;
+    float* o32 = kF32 ? p.out_f32 + (long)row0 * p.ldo32 + col : nullptr;
+    bf16* o16 = k16 ? p.out_bf16 + (long)row0 * p.ldo16 + col : nullptr;
+    bf16* opre = (EPI == EPI_ACT) ? p.out_preact + (long)row0 * p.ldp + col : nullptr;
+    const int ld32 = (int)p.ldo32, ld16 = (int)p.ldo16, ldp = (int)p.ldp;
+    const float alpha = p.alpha;
+    const uint32_t e0 = (uint32_t)row0 * (uint32_t)p.N + (uint32_t)col;
+    float cs0 = 0.f, cs1 = 0.f;
+    constexpr int kUnroll = (EPI == EPI_ACT) ? 4 : 32;
+#pragma unroll(kUnroll)
+    for (int rr = 0; rr < 32; ++rr) {
+        const float2 a = *reinterpret_cast<const float2*>(sp + rr * EPI_LD);
+        const float v0 = fmaf(a.x, alpha, b0);
+        const float v1 = fmaf(a.y, alpha, b1);
+        if (EPI == EPI_BF16) {
+            *reinterpret_cast<uint32_t*>(o16 + rr * ld16) = pack_bf16x2(v0, v1);
+        } else if (EPI == EPI_ACT) {
+            float y0, y1, d0, d1;
+            act_both<ACT>(v0, y0, d0);
+            act_both<ACT>(v1, y1, d1);
+            *reinterpret_cast<uint32_t*>(opre + rr * ldp) = SAVEG ? pack_bf16x2(d0, d1) : pack_bf16x2(v0, v1);
+            *reinterpret_cast<uint32_t*>(o16 + rr * ld16) = pack_bf16x2(y0, y1);
+        } else if (EPI == EPI_RES) {
+            float d0 = v0, d1 = v1;
+            if (DROP) {
+                const uint32_t e = e0 + (uint32_t)rr * (uint32_t)p.N;
+                d0 *= drop_mult(p.drop, e);
+                d1 *= drop_mult(p.drop, e + 1);
+            }
+            const float2 r = in.rs[EpiIn<EPI>::kRes ? rr : 0];
+            const float o0 = d0 + r.x, o1 = d1 + r.y;
+            *reinterpret_cast<float2*>(o32 + rr * ld32) = make_float2(o0, o1);
+            if (OUT16) *reinterpret_cast<uint32_t*>(o16 + rr * ld16) = pack_bf16x2(o0, o1);
+        } else if (EPI == EPI_F32) {
+            *reinterpret_cast<float2*>(o32 + rr * ld32) = make_float2(v0, v1);
+        } else if (EPI == EPI_DACT) {
+            const uint32_t xs = in.xs[EpiIn<EPI>::kDact ? rr : 0];
+            const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs));
+            const float o0 = v0 * x.x, o1 = v1 * x.y;
+            cs0 += o0; cs1 += o1;
+            *reinterpret_cast<uint32_t*>(o16 + rr * ld16) = pack_bf16x2(o0, o1);
+        } else if (EPI == EPI_ACC) {
+            red_add_v2(o32 + rr * ld32, v0, v1);
+        }
+    }
+    if (EPI == EPI_DACT) {
+        if (p.colsum_out) red_add_v2(p.colsum_out + col, cs0, cs1);
+        if (p.colsum_out2) red_add_v2(p.colsum_out2 + col, cs0, cs1);
+    }
+}
+
 // One 32-row x 64-column block of the output, values staged in `stg` (row-major, EPI_LD), lane = column pair.
-// ACT: compile-time activation (1 gelu-erf, 2 quick-gelu) for EPI_ACT.
 template <int EPI, int ACT>
 __device__ __forceinline__ void epilogue_rows(const GemmDev& p, const float* stg, const EpiIn<EPI>& in, int row0, int nrows,
                                               int col, float b0, float b1, int lane) {
+    if (nrows >= 32) {      // warp-uniform; every tile but the ragged last row block
+        if (EPI == EPI_RES) {
+            const bool drop = p.drop.thresh != 0, o16 = p.out_bf16 != nullptr;
+            if (drop && o16) epilogue_rows_full<EPI, ACT, true, true, false>(p, stg, in, row0, col, b0, b1, lane);
+            else if (drop) epilogue_rows_full<EPI, ACT, true, false, false>(p, stg, in, row0, col, b0, b1, lane);
+            else if (o16) epilogue_rows_full<EPI, ACT, false, true, false>(p, stg, in, row0, col, b0, b1, lane);
+            else epilogue_rows_full<EPI, ACT, false, false, false>(p, stg, in, row0, col, b0, b1, lane);
+        } else if (EPI == EPI_ACT) {
+            if (p.save_grad) epilogue_rows_full<EPI, ACT, false, false, true>(p, stg, in, row0, col, b0, b1, lane);
+            else epilogue_rows_full<EPI, ACT, false, false, false>(p, stg, in, row0, col, b0, b1, lane);
+        } else {
+            epilogue_rows_full<EPI, ACT, false, false, false>(p, stg, in, row0, col, b0, b1, lane);
+        }
+        return;
+    }
     float cs0 = 0.f, cs1 = 0.f;
     if (EPI == EPI_RES || EPI == EPI_DACT) {
         // per-row register arrays -> compile-time indices (full unroll, predicated rows)
@@ -168,7 +306,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmDev& p, const float* stg
             if (p.colsum_out2) red_add_v2(p.colsum_out2 + col, cs0, cs1);
         }
     } else {
-#pragma unroll 2
+#pragma unroll 1
         for (int rr = 0; rr < nrows; ++rr)
             epilogue_row<EPI, ACT>(p, stg, make_float2(0.f, 0.f), 0u, row0 + rr, rr, col, b0, b1, lane, cs0, cs1);
     }
@@ -224,6 +362,7 @@ __device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* st
     }
 }
 
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -245,6 +384,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int lane = threadIdx.x & 31;
     const int num_tiles = p.mt * p.nt * p.nsplit;
 
+    if (threadIdx.x == 0) stamp_begin(p, EPI | (A_MN ? 16 : 0) | (B_MN ? 32 : 0), BN);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -267,6 +407,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (threadIdx.x == 0) stamp(p, ST_CLK_PROLOGUE);
 
     // tile -> (m block, n block, k range).  m fastest: concurrently running CTAs share few B (weight) tiles.
     auto tile_coords = [&](int t, int& m0, int& n0, int& kb_begin, int& kb_end) {
@@ -316,6 +457,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int c = 0; c < BN / 64; ++c)
                             tma_load_2d(sB + c * (BK * 128), mb, full_bar(stage), n0 + c * 64, k0);
                     }
+                    if (t == (int)blockIdx.x && kb == kb_begin) stamp(p, ST_CLK_TMA0);
                     if (++stage == L::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -340,6 +482,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
+                    if (it == 1 && kb == kb_begin) stamp(p, ST_CLK_FULL0);
                     const uint32_t sA = smem_base + stage * L::STAGE_BYTES;
                     const uint32_t sB = sA + L::A_BYTES;
 #pragma unroll
@@ -359,6 +502,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (++stage == L::STAGES) { stage = 0; phase ^= 1u; }
                 }
                 umma_commit(tfull_bar(ab));  // accumulator complete
+                if (it == 1) stamp(p, ST_CLK_MMA_ISSUED0);
             }
         }
     } else {
@@ -375,11 +519,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ++it;
             const int row0 = m0 + quad * 32;
             const int nrows = min(32, p.M - row0);   // may be <= 0 for the ragged last tile
+            const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN);
             EpiIn<EPI> cur;
             if (!(p.debug & 1)) cur.load(p, row0, nrows, n0, lane);   // pass 0: fetched while the main loop still runs
             mbar_wait(tfull_bar(ab), aph);
             tc_fence_after();
-            const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN);
+            if (it == 1 && warp == 2 && lane == 0) stamp(p, ST_CLK_TFULL0);
 #pragma unroll 1
             for (int c = 0; c < BN / EPI_COLS; ++c) {
                 // HBM inputs of this pass are requested before the TMEM read + transpose so that their latency overlaps
@@ -396,16 +541,19 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int col0 = n0 + c * EPI_COLS;
                 if (col0 >= p.N || nrows <= 0 || (p.debug & 1)) continue;   // warp-uniform
 #pragma unroll
-                for (int j = 0; j < EPI_COLS; ++j) stg[lane * EPI_LD + j] = __uint_as_float(r[j]);
+                for (int j = 0; j < EPI_COLS; j += 2)
+                    *reinterpret_cast<float2*>(stg + lane * EPI_LD + j) = make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
                 __syncwarp();
                 epilogue_block<EPI>(p, stg, cur, row0, nrows, col0, lane);
                 __syncwarp();   // the transpose buffer is reused by the next pass
             }
+            if (warp == 2 && lane == 0) stamp(p, it == 1 ? ST_CLK_EPI0 : ST_CLK_EPI_LAST);
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) stamp_end(p, ((int)num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, L::TMEM_COLS);
@@ -457,6 +605,7 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int num_tiles = p.mt * p.nt * p.nsplit;     // mt counts 256-row blocks here
 
+    if (threadIdx.x == 0) stamp_begin(p, EPI | (A_MN ? 16 : 0) | (B_MN ? 32 : 0), 512);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -480,6 +629,7 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (threadIdx.x == 0) stamp(p, ST_CLK_PROLOGUE);
 
     auto tile_coords = [&](int t, int& m0, int& n0, int& kb_begin, int& kb_end) {
         const int mb = t % p.mt;
@@ -524,6 +674,7 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         for (int c = 0; c < L::BN_CTA / 64; ++c)
                             tma_load_2d_2cta(sB + c * (BK * 128), mb, full_bar(stage), nb0 + c * 64, k0);
                     }
+                    if (t == pair && kb == kb_begin) stamp(p, ST_CLK_TMA0);
                     if (++stage == L::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -548,6 +699,7 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
+                    if (it == 1 && kb == kb_begin) stamp(p, ST_CLK_FULL0);
                     const uint32_t sA = smem_base + stage * L::STAGE_BYTES;
                     const uint32_t sB = sA + L::A_BYTES;
 #pragma unroll
@@ -562,6 +714,7 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     if (++stage == L::STAGES) { stage = 0; phase ^= 1u; }
                 }
                 umma_commit_2cta_mc(tfull_bar(ab));            // accumulator complete, in both CTAs
+                if (it == 1) stamp(p, ST_CLK_MMA_ISSUED0);
             }
         }
     } else {
@@ -578,11 +731,12 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
             ++it;
             const int row0 = m0 + quad * 32;
             const int nrows = min(32, p.M - row0);
+            const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * L::BN_TILE);
             EpiIn<EPI> cur;
             cur.load(p, row0, nrows, n0, lane);
             mbar_wait(tfull_bar(ab), aph);
             tc_fence_after();
-            const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * L::BN_TILE);
+            if (it == 1 && warp == 2 && lane == 0) stamp(p, ST_CLK_TFULL0);
 #pragma unroll 1
             for (int c = 0; c < L::BN_TILE / EPI_COLS; ++c) {
                 if (c > 0) cur.load(p, row0, nrows, n0 + c * EPI_COLS, lane);
@@ -598,16 +752,19 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 const int col0 = n0 + c * EPI_COLS;
                 if (col0 >= p.N || nrows <= 0) continue;
 #pragma unroll
-                for (int j = 0; j < EPI_COLS; ++j) stg[lane * EPI_LD + j] = __uint_as_float(r[j]);
+                for (int j = 0; j < EPI_COLS; j += 2)
+                    *reinterpret_cast<float2*>(stg + lane * EPI_LD + j) = make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
                 __syncwarp();
                 epilogue_block<EPI>(p, stg, cur, row0, nrows, col0, lane);
                 __syncwarp();
             }
+            if (warp == 2 && lane == 0) stamp(p, it == 1 ? ST_CLK_EPI0 : ST_CLK_EPI_LAST);
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) stamp_end(p, (num_tiles - pair + npairs - 1) / npairs);
     cluster_sync_all();          // neither CTA may leave (or free tensor memory) while the pair's MMAs / signals are in flight
     if (warp == 1) {
         tc_fence_after();

@@ -204,10 +204,36 @@ void gemm_plan_destroy(GemmPlan* p) { delete p; }
 
 double gemm_plan_flops(const GemmPlan* p) { return p->flops; }
 
+// b200mart_gemm_timeline: device buffer of `records` x 148 x 16 u64; launch i writes its CTAs' stamps into record i
+static unsigned long long* g_timeline = nullptr;
+static long g_timeline_records = 0, g_timeline_next = 0;
+
+extern "C" int64_t b200mart_gemm_timeline(void* device_buffer, int64_t records) {
+    const long used = g_timeline_next;
+    g_timeline = static_cast<unsigned long long*>(device_buffer);
+    g_timeline_records = device_buffer ? records : 0;
+    g_timeline_next = 0;
+    return used;
+}
+
+static unsigned long long* timeline_slot() {
+    if (!g_timeline || g_timeline_next >= g_timeline_records) return nullptr;
+    return g_timeline + (size_t)(g_timeline_next++) * 148 * 16;
+}
+
 int gemm_plan_launch(const GemmPlan* p, cudaStream_t stream, const DropCfg* drop) {
+    if (g_timeline && !p->pair) {
+        GemmDev dev = p->dev;
+        if (drop) dev.drop = *drop;
+        dev.prof = timeline_slot();
+        p->kernel<<<p->grid, GEMM_THREADS, p->smem, stream>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, dev);
+        B2_LAUNCHED();
+        return 0;
+    }
     if (p->pair) {
         GemmDev dev = p->dev;
         if (drop) dev.drop = *drop;
+        if (g_timeline) dev.prof = timeline_slot();
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = p->grid;
         cfg.blockDim = dim3(GEMM_THREADS, 1, 1);

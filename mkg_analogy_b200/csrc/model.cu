@@ -458,10 +458,17 @@ int chains_begin(b200mart_handle* h, cudaStream_t s, Chains& c) {
     h->ev_used = 0;
     if (!h->split_streams) return 0;
     if (!h->sV) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->sV, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->sT, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->sVw, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->sTw, cudaStreamNonBlocking));
+        // Priorities: the two dependent chains are the critical path, so their CTAs are scheduled first; the weight-gradient
+        // products fill the SMs they leave idle; everything the caller runs at default priority next to them (the pipelined
+        // AdamW / gradient exchange of the trainer) only gets what is left.  B200MART_STREAM_PRIO=0: all default (A/B runs).
+        int least = 0, greatest = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        { const char* e = getenv("B200MART_STREAM_PRIO"); if (e && atoi(e) == 0) greatest = least; }
+        const int mid = (greatest < least - 1) ? greatest + (least - greatest) / 2 : greatest;
+        CUDA_TRY(cudaStreamCreateWithPriority(&h->sV, cudaStreamNonBlocking, greatest));
+        CUDA_TRY(cudaStreamCreateWithPriority(&h->sT, cudaStreamNonBlocking, greatest));
+        CUDA_TRY(cudaStreamCreateWithPriority(&h->sVw, cudaStreamNonBlocking, mid));
+        CUDA_TRY(cudaStreamCreateWithPriority(&h->sTw, cudaStreamNonBlocking, mid));
     }
     c.v = h->sV; c.t = h->sT; c.vw = h->sVw; c.tw = h->sTw; c.split = true;
     cudaEvent_t e = c.mark(s);
