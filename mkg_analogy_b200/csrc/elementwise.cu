@@ -3,6 +3,7 @@
 // Layout rule: one warp per row for everything LayerNorm-shaped (H % 128 == 0, H <= 1024), lanes own
 // float4 columns {lane*4 + 128*t}; all global accesses are 16-byte vectors.
 #include "kernels.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -187,7 +188,7 @@ __global__ void text_embed_ln_kernel(const int64_t* __restrict__ ids, const int6
 // LayerNorm backward. Each warp walks rows r = warp_id, warp_id + nwarps, ...; dgamma/dbeta (and, optionally, the column
 // sums of the produced dx = bias gradient of the linear layer that fed this LayerNorm's input) stay in registers (same
 // lane->column mapping for every row) and are reduced through shared memory + one atomic per column per block.
-template <bool COLSUM>
+template <bool COLSUM, int NV>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ add,
@@ -196,9 +197,9 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     extern __shared__ float red[];  // [warps][H] x (2 or 3)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int nv = H / 128;
-    float4 g[MAXV], ag[MAXV], ab[MAXV], ac[COLSUM ? MAXV : 1];
+    float4 g[NV], ag[NV], ab[NV], ac[COLSUM ? NV : 1];
 #pragma unroll
-    for (int t = 0; t < MAXV; ++t) {
+    for (int t = 0; t < NV; ++t) {
         ag[t] = make_float4(0, 0, 0, 0);
         ab[t] = make_float4(0, 0, 0, 0);
         if (COLSUM) ac[t] = make_float4(0, 0, 0, 0);
@@ -206,10 +207,19 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     }
     for (int row = blockIdx.x * nw + warp; row < M; row += gridDim.x * nw) {
         const float mu = mean[row], rs = rstd[row];
-        float4 d[MAXV], xh[MAXV];
+        float4 d[NV], xh[NV], av[NV];
+        uint2 qv[NV];
         float s1 = 0.f, s2 = 0.f;
+        // every HBM input of the row is requested up front (one round trip per row instead of two)
 #pragma unroll
-        for (int t = 0; t < MAXV; ++t)
+        for (int t = 0; t < NV; ++t)
+            if (t < nv) {
+                const long off = (long)row * H + lane * 4 + t * 128;
+                if (add) av[t] = ld4(add + off);
+                if (dact) qv[t] = *reinterpret_cast<const uint2*>(dact_src + off);
+            }
+#pragma unroll
+        for (int t = 0; t < NV; ++t)
             if (t < nv) {
                 const long off = (long)row * H + lane * 4 + t * 128;
                 d[t] = ld4(dy + off);
@@ -229,7 +239,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
         s1 = warp_sum(s1) / H;
         s2 = warp_sum(s2) / H;
 #pragma unroll
-        for (int t = 0; t < MAXV; ++t)
+        for (int t = 0; t < NV; ++t)
             if (t < nv) {
                 const long off = (long)row * H + lane * 4 + t * 128;
                 float4 o;
@@ -238,7 +248,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                 o.z = rs * (d[t].z - s1 - xh[t].z * s2);
                 o.w = rs * (d[t].w - s1 - xh[t].w * s2);
                 if (dact) {
-                    const uint2 q = *reinterpret_cast<const uint2*>(dact_src + off);
+                    const uint2 q = qv[t];
                     const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
                     const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
                     if (dact == 1) {
@@ -248,7 +258,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                     }
                 }
                 if (add) {
-                    float4 a = ld4(add + off);
+                    const float4 a = av[t];
                     o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
                 }
                 if (dx32) st4(dx32 + off, o);      // full gradient: the residual path
@@ -265,7 +275,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     float* rb = red + nw * H;
     float* rc = red + 2 * nw * H;
 #pragma unroll
-    for (int t = 0; t < MAXV; ++t)
+    for (int t = 0; t < NV; ++t)
         if (t < nv) {
             st4(rg + warp * H + lane * 4 + t * 128, ag[t]);
             st4(rb + warp * H + lane * 4 + t * 128, ab[t]);
@@ -494,17 +504,20 @@ int launch_layernorm_bwd(const float* dy, const float* x, const float* mean, con
     B2_TRY(check_h(H));
     const int nw = 8;
     int blocks = (M + nw - 1) / nw;
-    if (blocks > 148) blocks = 148;   // one block per SM: per-column atomics stay at <= 148 per address
+    // rows per warp vs per-column atomics (2-3 x H per block): B200MART_LNB_BLOCKS = blocks per SM; 1: the register arrays allow one resident block
+    static int per_sm = -1;
+    if (per_sm < 0) { const char* e = getenv("B200MART_LNB_BLOCKS"); per_sm = e ? atoi(e) : 1; if (per_sm < 1) per_sm = 1; }
+    if (blocks > 148 * per_sm) blocks = 148 * per_sm;
     const size_t smem = (size_t)(dxsum ? 3 : 2) * nw * H * sizeof(float);
-    if (dxsum) {
-        CUDA_TRY(cudaFuncSetAttribute((const void*)layernorm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        layernorm_bwd_kernel<true><<<blocks, nw * 32, smem, s>>>(dy, x, mean, rstd, gamma, add, dact_src, dact_src ? dact : 0, dx32,
-                                                               dx16, dgamma, dbeta, dxsum, M, H, dy_drop, dx16_drop);
-    } else {
-        CUDA_TRY(cudaFuncSetAttribute((const void*)layernorm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        layernorm_bwd_kernel<false><<<blocks, nw * 32, smem, s>>>(dy, x, mean, rstd, gamma, add, dact_src, dact_src ? dact : 0, dx32,
-                                                                dx16, dgamma, dbeta, nullptr, M, H, dy_drop, dx16_drop);
-    }
+    auto go = [&](auto kernel) -> int {
+        CUDA_TRY(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<blocks, nw * 32, smem, s>>>(dy, x, mean, rstd, gamma, add, dact_src, dact_src ? dact : 0, dx32, dx16, dgamma, dbeta,
+                                            dxsum, M, H, dy_drop, dx16_drop);
+        return 0;
+    };
+    const bool small = H <= 768;       // register arrays sized for the hidden size: 6 (base) or 8 (large) float4 per lane
+    if (dxsum) { B2_TRY(small ? go(layernorm_bwd_kernel<true, 6>) : go(layernorm_bwd_kernel<true, 8>)); }
+    else { B2_TRY(small ? go(layernorm_bwd_kernel<false, 6>) : go(layernorm_bwd_kernel<false, 8>)); }
     B2_LAUNCHED();
     return 0;
 }
