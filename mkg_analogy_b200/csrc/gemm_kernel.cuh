@@ -23,7 +23,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int GEMM_THREADS = 192;
 constexpr int EPI_COLS = 64;   // columns per epilogue pass
-constexpr int EPI_LD = 66;     // padded row of the per-warp transpose buffer (fp32 words; even: rows stay 8-byte aligned)
+constexpr int EPI_LD = 64;     // row of the per-warp transpose buffer (fp32 words; XOR-swizzled chunks instead of padding)
 
 // fused epilogues (compile-time).  Every kind except GENERIC requires even N and even leading dimensions.
 enum EpiKind {
@@ -114,48 +114,54 @@ __device__ __forceinline__ float act_fwd(int act, float v) {
 }
 __device__ __forceinline__ float act_grad(int act, float x) { return act == 1 ? gelu_erf_grad(x) : quick_gelu_grad(x); }
 
-// Per-pass epilogue inputs that come from HBM (residual / saved activation derivative): one 32-row x 64-column block,
-// lane = column pair, ALL 32 rows issued back to back so that a warp keeps 32 x 256 B (128 B) loads in flight; they are
-// issued before the TMEM read + transpose of the pass (pass 0: before the accumulator-ready wait).
+// Per-warp transpose buffer of one epilogue pass: 32 rows x 64 columns fp32, NO padding; the 16-byte chunk c of row r lives
+// at chunk (c ^ (r & 15)).  Writers (lane = row, 16 chunks) and readers (16 lanes = the 16 chunks of one row) both touch
+// eight different 4-bank groups per quarter warp, so every 128-bit shared-memory access is conflict-free.
+__device__ __forceinline__ int stg_off(int row, int chunk) { return row * EPI_LD + ((chunk ^ (row & 15)) << 2); }
+
+// Epilogue work split of a pass: lane = (row parity hr = lane >> 4, column quad c = lane & 15); iteration i handles row
+// 2 i + hr, columns 4 c .. 4 c + 3, so each warp-wide access covers two full 256-byte (fp32) / 128-byte (bf16) row segments.
+// Per-pass inputs that come from HBM (residual / saved activation derivative): 16 vector loads per lane, all issued back to
+// back before the TMEM read + transpose of the pass (pass 0: before the accumulator-ready wait).
 template <int EPI>
 struct EpiIn {
     static constexpr bool kRes = (EPI == EPI_RES), kDact = (EPI == EPI_DACT);
-    float2 rs[kRes ? 32 : 1];
-    uint32_t xs[kDact ? 32 : 1];
+    float4 rs[kRes ? 16 : 1];
+    uint2 xs[kDact ? 16 : 1];
     template <bool FULL>
-    __device__ __forceinline__ void load_t(const GemmDev& p, int row0, int nrows, int col) {
+    __device__ __forceinline__ void load_t(const GemmDev& p, int row0, int nrows, int col, int hr) {
         if (kRes) {
-            const float* rp = p.residual + (long)row0 * p.ldr + col;
-            const int ld = (int)p.ldr;
+            const float* rp = p.residual + (long)(row0 + hr) * p.ldr + col;
+            const int ld2 = 2 * (int)p.ldr;
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr)
-                if (FULL || rr < nrows) rs[rr] = *reinterpret_cast<const float2*>(rp + rr * ld);
+            for (int i = 0; i < 16; ++i)
+                if (FULL || 2 * i + hr < nrows) rs[i] = *reinterpret_cast<const float4*>(rp + i * ld2);
         }
         if (kDact) {
-            const bf16* xp = p.dact_src + (long)row0 * p.ldx + col;
-            const int ld = (int)p.ldx;
+            const bf16* xp = p.dact_src + (long)(row0 + hr) * p.ldx + col;
+            const int ld2 = 2 * (int)p.ldx;
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr)
-                if (FULL || rr < nrows) xs[rr] = *reinterpret_cast<const uint32_t*>(xp + rr * ld);
+            for (int i = 0; i < 16; ++i)
+                if (FULL || 2 * i + hr < nrows) xs[i] = *reinterpret_cast<const uint2*>(xp + i * ld2);
         }
     }
     __device__ __forceinline__ void load(const GemmDev& p, int row0, int nrows, int col0, int lane) {
-        const int col = col0 + 2 * lane;
+        const int col = col0 + 4 * (lane & 15);
         if (!(kRes || kDact) || col >= p.N) return;
-        if (nrows >= 32) load_t<true>(p, row0, nrows, col);
-        else load_t<false>(p, row0, nrows, col);
+        if (nrows >= 32) load_t<true>(p, row0, nrows, col, lane >> 4);
+        else load_t<false>(p, row0, nrows, col, lane >> 4);
     }
 };
 
-// activation value and derivative from ONE exponential.
-//   exact GELU: y = x Phi(x), y' = Phi(x) + x phi(x); Phi through erf(z) = 1 - P(t) exp(-z^2), t = 1 / (1 + 0.3275911 z)
-//   (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 - far inside the bf16 rounding of the outputs), with z = |x| / sqrt(2) so
-//   that exp(-z^2) = exp(-x^2 / 2) is also the Gaussian of the derivative: one MUFU.EX2 + one MUFU.RCP per element.
 __device__ __forceinline__ float rcp_fast(float x) {      // MUFU.RCP (1 ulp), no denormal / special-case slow path
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// activation value and derivative from ONE exponential.
+//   exact GELU: y = x Phi(x), y' = Phi(x) + x phi(x); Phi through erf(z) = 1 - P(t) exp(-z^2), t = 1 / (1 + 0.3275911 z)
+//   (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 - far inside the bf16 rounding of the outputs), with z = |x| / sqrt(2) so
+//   that exp(-z^2) = exp(-x^2 / 2) is also the Gaussian of the derivative: one MUFU.EX2 + one MUFU.RCP per element.
 template <int ACT> __device__ __forceinline__ void act_both(float x, float& y, float& dy) {
     if (ACT == 1) {
         const float ax = fabsf(x);
@@ -176,139 +182,92 @@ template <int ACT> __device__ __forceinline__ void act_both(float x, float& y, f
     }
 }
 
-// One row of a 32-row x 64-column block: values staged in `stg` (row-major, EPI_LD), lane = column pair.
-// ACT: compile-time activation (1 gelu-erf, 2 quick-gelu) for EPI_ACT.  Ragged / generic-flag variant (runtime checks).
-template <int EPI, int ACT>
-__device__ __forceinline__ void epilogue_row(const GemmDev& p, const float* stg, float2 rs, uint32_t xs, long row, int rr, int col,
-                                             float b0, float b1, int lane, float& cs0, float& cs1) {
-    const float2 a = *reinterpret_cast<const float2*>(stg + rr * EPI_LD + 2 * lane);
-    const float v0 = fmaf(a.x, p.alpha, b0);
-    const float v1 = fmaf(a.y, p.alpha, b1);
-    if (EPI == EPI_BF16) {
-        *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(v0, v1);
-    } else if (EPI == EPI_ACT) {
-        float y0, y1, d0, d1;
-        act_both<ACT>(v0, y0, d0);
-        act_both<ACT>(v1, y1, d1);
-        // saved for backward: the pre-activation, or directly the activation derivative (save_grad)
-        *reinterpret_cast<uint32_t*>(p.out_preact + row * p.ldp + col) = p.save_grad ? pack_bf16x2(d0, d1) : pack_bf16x2(v0, v1);
-        *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(y0, y1);
-    } else if (EPI == EPI_RES) {
-        float d0 = v0, d1 = v1;
-        if (p.drop.thresh) {   // BertSelfOutput :389 / BertOutput :476: dropout(dense(x)) + residual
-            const uint32_t e = (uint32_t)row * (uint32_t)p.N + (uint32_t)col;
-            d0 *= drop_mult(p.drop, e);
-            d1 *= drop_mult(p.drop, e + 1);
-        }
-        const float o0 = d0 + rs.x, o1 = d1 + rs.y;
-        *reinterpret_cast<float2*>(p.out_f32 + row * p.ldo32 + col) = make_float2(o0, o1);
-        if (p.out_bf16) *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(o0, o1);
-    } else if (EPI == EPI_F32) {
-        *reinterpret_cast<float2*>(p.out_f32 + row * p.ldo32 + col) = make_float2(v0, v1);
-    } else if (EPI == EPI_DACT) {
-        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs));
-        const float o0 = v0 * x.x, o1 = v1 * x.y;
-        cs0 += o0; cs1 += o1;
-        *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ldo16 + col) = pack_bf16x2(o0, o1);
-    } else if (EPI == EPI_ACC) {
-        red_add_v2(p.out_f32 + row * p.ldo32 + col, v0, v1);
-    }
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) { return make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)); }
 
-// Full block (32 valid rows, valid column pair): no predicates and no per-row branches, so the rows are independent
-// straight-line chains the scheduler interleaves (the epilogue warps have no other latency hiding: one warp per scheduler);
-// per-row addresses are 32-bit offsets from per-pass base pointers.  DROP / OUT16 / SAVEG: hoisted runtime flags.
-template <int EPI, int ACT, bool DROP, bool OUT16, bool SAVEG>
-__device__ __forceinline__ void epilogue_rows_full(const GemmDev& p, const float* stg, const EpiIn<EPI>& in, int row0, int col,
-                                                   float b0, float b1, int lane) {
+// One 32-row x 64-column block of the output from the transpose buffer.  FULL: all 32 rows valid -> no predicates, the
+// 16 iterations are independent straight-line chains the scheduler interleaves (the epilogue warps have no other latency
+// hiding: one warp per scheduler).  DROP / OUT16 / SAVEG: runtime flags hoisted to compile time.
+template <int EPI, int ACT, bool FULL, bool DROP, bool OUT16, bool SAVEG>
+__device__ __forceinline__ void epilogue_rows_t(const GemmDev& p, const float* stg, const EpiIn<EPI>& in, int row0, int nrows,
+                                                int col, float4 b, int lane) {
     constexpr bool kF32 = (EPI == EPI_RES || EPI == EPI_F32 || EPI == EPI_ACC);
     constexpr bool k16 = (EPI == EPI_BF16 || EPI == EPI_ACT || EPI == EPI_DACT || (EPI == EPI_RES && OUT16));
-    const float* sp = stg + 2 * lane;
-    float* o32 = kF32 ? p.out_f32 + (long)row0 * p.ldo32 + col : nullptr;
-    bf16* o16 = k16 ? p.out_bf16 + (long)row0 * p.ldo16 + col : nullptr;
-    bf16* opre = (EPI == EPI_ACT) ? p.out_preact + (long)row0 * p.ldp + col : nullptr;
-    const int ld32 = (int)p.ldo32, ld16 = (int)p.ldo16, ldp = (int)p.ldp;
+    const int hr = lane >> 4, c = lane & 15;
+    float* o32 = kF32 ? p.out_f32 + (long)(row0 + hr) * p.ldo32 + col : nullptr;
+    bf16* o16 = k16 ? p.out_bf16 + (long)(row0 + hr) * p.ldo16 + col : nullptr;
+    bf16* opre = (EPI == EPI_ACT) ? p.out_preact + (long)(row0 + hr) * p.ldp + col : nullptr;
+    const int ld32 = 2 * (int)p.ldo32, ld16 = 2 * (int)p.ldo16, ldp = 2 * (int)p.ldp;
     const float alpha = p.alpha;
-    const uint32_t e0 = (uint32_t)row0 * (uint32_t)p.N + (uint32_t)col;
-    float cs0 = 0.f, cs1 = 0.f;
-    constexpr int kUnroll = (EPI == EPI_ACT) ? 4 : 32;
+    const uint32_t e0 = (uint32_t)(row0 + hr) * (uint32_t)p.N + (uint32_t)col;
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int kUnroll = (EPI == EPI_ACT) ? 4 : 16;
 #pragma unroll(kUnroll)
-    for (int rr = 0; rr < 32; ++rr) {
-        const float2 a = *reinterpret_cast<const float2*>(sp + rr * EPI_LD);
-        const float v0 = fmaf(a.x, alpha, b0);
-        const float v1 = fmaf(a.y, alpha, b1);
+    for (int i = 0; i < 16; ++i) {
+        const int rl = 2 * i + hr;
+        if (!FULL && rl >= nrows) continue;
+        const float4 a = *reinterpret_cast<const float4*>(stg + stg_off(rl, c));
+        float4 v = make_float4(fmaf(a.x, alpha, b.x), fmaf(a.y, alpha, b.y), fmaf(a.z, alpha, b.z), fmaf(a.w, alpha, b.w));
         if (EPI == EPI_BF16) {
-            *reinterpret_cast<uint32_t*>(o16 + rr * ld16) = pack_bf16x2(v0, v1);
+            *reinterpret_cast<uint2*>(o16 + i * ld16) = pack_bf16x4(v);
         } else if (EPI == EPI_ACT) {
-            float y0, y1, d0, d1;
-            act_both<ACT>(v0, y0, d0);
-            act_both<ACT>(v1, y1, d1);
-            *reinterpret_cast<uint32_t*>(opre + rr * ldp) = SAVEG ? pack_bf16x2(d0, d1) : pack_bf16x2(v0, v1);
-            *reinterpret_cast<uint32_t*>(o16 + rr * ld16) = pack_bf16x2(y0, y1);
+            float4 y, d;
+            act_both<ACT>(v.x, y.x, d.x);
+            act_both<ACT>(v.y, y.y, d.y);
+            act_both<ACT>(v.z, y.z, d.z);
+            act_both<ACT>(v.w, y.w, d.w);
+            // saved for backward: the pre-activation, or the activation derivative itself (save_grad)
+            *reinterpret_cast<uint2*>(opre + i * ldp) = pack_bf16x4(SAVEG ? d : v);
+            *reinterpret_cast<uint2*>(o16 + i * ld16) = pack_bf16x4(y);
         } else if (EPI == EPI_RES) {
-            float d0 = v0, d1 = v1;
-            if (DROP) {
-                const uint32_t e = e0 + (uint32_t)rr * (uint32_t)p.N;
-                d0 *= drop_mult(p.drop, e);
-                d1 *= drop_mult(p.drop, e + 1);
+            if (DROP) {   // BertSelfOutput :389 / BertOutput :476: dropout(dense(x)) + residual
+                const uint32_t e = e0 + (uint32_t)(2 * i) * (uint32_t)p.N;
+                v.x *= drop_mult(p.drop, e); v.y *= drop_mult(p.drop, e + 1);
+                v.z *= drop_mult(p.drop, e + 2); v.w *= drop_mult(p.drop, e + 3);
             }
-            const float2 r = in.rs[EpiIn<EPI>::kRes ? rr : 0];
-            const float o0 = d0 + r.x, o1 = d1 + r.y;
-            *reinterpret_cast<float2*>(o32 + rr * ld32) = make_float2(o0, o1);
-            if (OUT16) *reinterpret_cast<uint32_t*>(o16 + rr * ld16) = pack_bf16x2(o0, o1);
+            const float4 r = in.rs[EpiIn<EPI>::kRes ? i : 0];
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            *reinterpret_cast<float4*>(o32 + i * ld32) = v;
+            if (OUT16) *reinterpret_cast<uint2*>(o16 + i * ld16) = pack_bf16x4(v);
         } else if (EPI == EPI_F32) {
-            *reinterpret_cast<float2*>(o32 + rr * ld32) = make_float2(v0, v1);
+            *reinterpret_cast<float4*>(o32 + i * ld32) = v;
         } else if (EPI == EPI_DACT) {
-            const uint32_t xs = in.xs[EpiIn<EPI>::kDact ? rr : 0];
-            const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs));
-            const float o0 = v0 * x.x, o1 = v1 * x.y;
-            cs0 += o0; cs1 += o1;
-            *reinterpret_cast<uint32_t*>(o16 + rr * ld16) = pack_bf16x2(o0, o1);
+            const uint2 xs = in.xs[EpiIn<EPI>::kDact ? i : 0];
+            const float2 x0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs.x));
+            const float2 x1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs.y));
+            v.x *= x0.x; v.y *= x0.y; v.z *= x1.x; v.w *= x1.y;
+            cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+            *reinterpret_cast<uint2*>(o16 + i * ld16) = pack_bf16x4(v);
         } else if (EPI == EPI_ACC) {
-            red_add_v2(o32 + rr * ld32, v0, v1);
+            red_add_v4(o32 + i * ld32, v);
         }
     }
-    if (EPI == EPI_DACT) {
-        if (p.colsum_out) red_add_v2(p.colsum_out + col, cs0, cs1);
-        if (p.colsum_out2) red_add_v2(p.colsum_out2 + col, cs0, cs1);
+    if (EPI == EPI_DACT) {     // column sums of this block: fold the two row parities, then one vector reduction per column quad
+        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+        if (hr == 0) {
+            if (p.colsum_out) red_add_v4(p.colsum_out + col, cs);
+            if (p.colsum_out2) red_add_v4(p.colsum_out2 + col, cs);
+        }
     }
 }
 
-// One 32-row x 64-column block of the output, values staged in `stg` (row-major, EPI_LD), lane = column pair.
-template <int EPI, int ACT>
+template <int EPI, int ACT, bool FULL>
 __device__ __forceinline__ void epilogue_rows(const GemmDev& p, const float* stg, const EpiIn<EPI>& in, int row0, int nrows,
-                                              int col, float b0, float b1, int lane) {
-    if (nrows >= 32) {      // warp-uniform; every tile but the ragged last row block
-        if (EPI == EPI_RES) {
-            const bool drop = p.drop.thresh != 0, o16 = p.out_bf16 != nullptr;
-            if (drop && o16) epilogue_rows_full<EPI, ACT, true, true, false>(p, stg, in, row0, col, b0, b1, lane);
-            else if (drop) epilogue_rows_full<EPI, ACT, true, false, false>(p, stg, in, row0, col, b0, b1, lane);
-            else if (o16) epilogue_rows_full<EPI, ACT, false, true, false>(p, stg, in, row0, col, b0, b1, lane);
-            else epilogue_rows_full<EPI, ACT, false, false, false>(p, stg, in, row0, col, b0, b1, lane);
-        } else if (EPI == EPI_ACT) {
-            if (p.save_grad) epilogue_rows_full<EPI, ACT, false, false, true>(p, stg, in, row0, col, b0, b1, lane);
-            else epilogue_rows_full<EPI, ACT, false, false, false>(p, stg, in, row0, col, b0, b1, lane);
-        } else {
-            epilogue_rows_full<EPI, ACT, false, false, false>(p, stg, in, row0, col, b0, b1, lane);
-        }
-        return;
-    }
-    float cs0 = 0.f, cs1 = 0.f;
-    if (EPI == EPI_RES || EPI == EPI_DACT) {
-        // per-row register arrays -> compile-time indices (full unroll, predicated rows)
-#pragma unroll
-        for (int rr = 0; rr < 32; ++rr)
-            if (rr < nrows)
-                epilogue_row<EPI, ACT>(p, stg, in.rs[EpiIn<EPI>::kRes ? rr : 0], in.xs[EpiIn<EPI>::kDact ? rr : 0], row0 + rr, rr, col,
-                                       b0, b1, lane, cs0, cs1);
-        if (EPI == EPI_DACT) {
-            if (p.colsum_out) red_add_v2(p.colsum_out + col, cs0, cs1);
-            if (p.colsum_out2) red_add_v2(p.colsum_out2 + col, cs0, cs1);
-        }
+                                              int col, float4 b, int lane) {
+    if (EPI == EPI_RES) {
+        const bool drop = p.drop.thresh != 0, o16 = p.out_bf16 != nullptr;
+        if (drop && o16) epilogue_rows_t<EPI, ACT, FULL, true, true, false>(p, stg, in, row0, nrows, col, b, lane);
+        else if (drop) epilogue_rows_t<EPI, ACT, FULL, true, false, false>(p, stg, in, row0, nrows, col, b, lane);
+        else if (o16) epilogue_rows_t<EPI, ACT, FULL, false, true, false>(p, stg, in, row0, nrows, col, b, lane);
+        else epilogue_rows_t<EPI, ACT, FULL, false, false, false>(p, stg, in, row0, nrows, col, b, lane);
+    } else if (EPI == EPI_ACT) {
+        if (p.save_grad) epilogue_rows_t<EPI, ACT, FULL, false, false, true>(p, stg, in, row0, nrows, col, b, lane);
+        else epilogue_rows_t<EPI, ACT, FULL, false, false, false>(p, stg, in, row0, nrows, col, b, lane);
     } else {
-#pragma unroll 1
-        for (int rr = 0; rr < nrows; ++rr)
-            epilogue_row<EPI, ACT>(p, stg, make_float2(0.f, 0.f), 0u, row0 + rr, rr, col, b0, b1, lane, cs0, cs1);
+        epilogue_rows_t<EPI, ACT, FULL, false, false, false>(p, stg, in, row0, nrows, col, b, lane);
     }
 }
 
@@ -319,7 +278,8 @@ __device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* st
         // scalar, any flags: lane handles columns col0+lane and col0+32+lane
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-            const int col = col0 + half * 32 + lane;
+            const int cl = half * 32 + lane;
+            const int col = col0 + cl;
             if (col >= p.N) continue;
             float badd = 0.f;
             if (p.bias) badd = __ldg(p.bias + col);
@@ -327,7 +287,7 @@ __device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* st
 #pragma unroll 1
             for (int rr = 0; rr < nrows; ++rr) {
                 const long row = row0 + rr;
-                float v = stg[rr * EPI_LD + half * 32 + lane] * p.alpha + badd;
+                float v = stg[stg_off(rr, cl >> 2) + (cl & 3)] * p.alpha + badd;
                 if (p.out_preact) p.out_preact[row * p.ldp + col] = __float2bfloat16((p.save_grad && p.act) ? act_grad(p.act, v) : v);
                 v = act_fwd(p.act, v);
                 if (p.dact) {
@@ -345,23 +305,29 @@ __device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* st
         }
         return;
     }
-    const int col = col0 + 2 * lane;       // even; N even -> the pair is valid or invalid together
+    const int col = col0 + 4 * (lane & 15);       // N % 4 == 0 -> the quad is valid or invalid together
     if (col >= p.N) return;
-    float b0 = 0.f, b1 = 0.f;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (EPI == EPI_BF16 || EPI == EPI_ACT || EPI == EPI_RES || EPI == EPI_F32) {
-        if (p.bias) { const float2 t = __ldg(reinterpret_cast<const float2*>(p.bias + col)); b0 = t.x; b1 = t.y; }
+        if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         if ((EPI == EPI_BF16 || EPI == EPI_ACT) && p.bias2) {
-            const float2 t = __ldg(reinterpret_cast<const float2*>(p.bias2 + col)); b0 += t.x; b1 += t.y;
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias2 + col));
+            b.x += t.x; b.y += t.y; b.z += t.z; b.w += t.w;
         }
     }
     if (EPI == EPI_ACT) {
-        if (p.act == 1) epilogue_rows<EPI, 1>(p, stg, in, row0, nrows, col, b0, b1, lane);
-        else epilogue_rows<EPI, 2>(p, stg, in, row0, nrows, col, b0, b1, lane);
+        if (nrows >= 32) {
+            if (p.act == 1) epilogue_rows<EPI, 1, true>(p, stg, in, row0, nrows, col, b, lane);
+            else epilogue_rows<EPI, 2, true>(p, stg, in, row0, nrows, col, b, lane);
+        } else {
+            if (p.act == 1) epilogue_rows<EPI, 1, false>(p, stg, in, row0, nrows, col, b, lane);
+            else epilogue_rows<EPI, 2, false>(p, stg, in, row0, nrows, col, b, lane);
+        }
     } else {
-        epilogue_rows<EPI, 0>(p, stg, in, row0, nrows, col, b0, b1, lane);
+        if (nrows >= 32) epilogue_rows<EPI, 0, true>(p, stg, in, row0, nrows, col, b, lane);
+        else epilogue_rows<EPI, 0, false>(p, stg, in, row0, nrows, col, b, lane);
     }
 }
-
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -541,8 +507,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int col0 = n0 + c * EPI_COLS;
                 if (col0 >= p.N || nrows <= 0 || (p.debug & 1)) continue;   // warp-uniform
 #pragma unroll
-                for (int j = 0; j < EPI_COLS; j += 2)
-                    *reinterpret_cast<float2*>(stg + lane * EPI_LD + j) = make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+                for (int q = 0; q < EPI_COLS / 4; ++q)
+                    *reinterpret_cast<float4*>(stg + stg_off(lane, q)) = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
                 __syncwarp();
                 epilogue_block<EPI>(p, stg, cur, row0, nrows, col0, lane);
                 __syncwarp();   // the transpose buffer is reused by the next pass
@@ -752,8 +719,9 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 const int col0 = n0 + c * EPI_COLS;
                 if (col0 >= p.N || nrows <= 0) continue;
 #pragma unroll
-                for (int j = 0; j < EPI_COLS; j += 2)
-                    *reinterpret_cast<float2*>(stg + lane * EPI_LD + j) = make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+                for (int q = 0; q < EPI_COLS / 4; ++q)
+                    *reinterpret_cast<float4*>(stg + stg_off(lane, q)) = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
                 __syncwarp();
                 epilogue_block<EPI>(p, stg, cur, row0, nrows, col0, lane);
                 __syncwarp();

@@ -78,16 +78,20 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
     B2_CHECK(op.M > 0 && op.N > 0 && op.K1 > 0, "gemm: bad shape M=%d N=%d K1=%d", op.M, op.N, op.K1);
     B2_CHECK(op.K2 == 0 || op.K1 % BK == 0, "gemm: K1=%d must be a multiple of %d when a second operand pair is used", op.K1, BK);
     B2_CHECK(op.split_k >= 1, "gemm: split_k must be >= 1");
-    B2_CHECK(!(op.colsum_out || op.colsum_out2) || (op.dact_src && op.dact == 3 && op.out_bf16 && op.N % 2 == 0 && op.ldx % 2 == 0 && op.ldo16 % 2 == 0),
-             "gemm: column sums are only produced by the saved-derivative (dact = 3) bf16 epilogue with even N / leading dimensions");
     B2_CHECK(op.split_k == 1 || (op.accumulate && op.out_f32 && !op.out_bf16 && !op.out_preact && !op.bias && !op.bias2 &&
                                  !op.residual && op.act == 0 && op.dact == 0),
              "gemm: split-K needs a pure fp32 accumulate epilogue");
     // ---- fused-epilogue kind
     int epi = EPI_GENERIC;
-    const bool even = (op.N % 2 == 0) && (!op.out_preact || op.ldp % 2 == 0) && (!op.dact_src || op.ldx % 2 == 0) &&
-                      (!op.residual || op.ldr % 2 == 0) && (!op.out_f32 || op.ldo32 % 2 == 0) &&
-                      (!op.out_bf16 || op.ldo16 % 2 == 0);
+    // the specialised epilogues move 4 columns per lane: 16-byte fp32 / 8-byte bf16 vector accesses
+    auto al = [](const void* q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
+    const bool even = (op.N % 4 == 0) && (!op.out_preact || (op.ldp % 4 == 0 && al(op.out_preact, 8))) &&
+                      (!op.dact_src || (op.ldx % 4 == 0 && al(op.dact_src, 8))) &&
+                      (!op.residual || (op.ldr % 4 == 0 && al(op.residual, 16))) &&
+                      (!op.out_f32 || (op.ldo32 % 4 == 0 && al(op.out_f32, 16))) &&
+                      (!op.out_bf16 || (op.ldo16 % 4 == 0 && al(op.out_bf16, 8))) && (!op.bias || al(op.bias, 16)) &&
+                      (!op.bias2 || al(op.bias2, 16)) && (!op.colsum_out || al(op.colsum_out, 16)) &&
+                      (!op.colsum_out2 || al(op.colsum_out2, 16));
     const bool has_dact = op.dact_src && op.dact;
     if (even) {
         if (op.accumulate && op.out_f32 && !op.out_bf16 && !op.out_preact && !op.bias && !op.bias2 && !op.residual &&
@@ -110,6 +114,9 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
     }
     if (!has_specialised(op.a_mn, op.b_mn, epi)) epi = EPI_GENERIC;
     { const char* e = getenv("B200MART_GEMM_GENERIC"); if (e && atoi(e)) epi = EPI_GENERIC; }
+    B2_CHECK(!(op.colsum_out || op.colsum_out2) || epi == EPI_DACT,
+             "gemm: column sums are only produced by the saved-derivative (dact = 3) bf16 epilogue of a K-major A / MN-major B "
+             "product with N and the leading dimensions multiples of 4 and 16-byte aligned column-sum vectors");
     // ---- N tile: rounds of the persistent grid x per-tile cost (main loop ~ bn, plus a fixed part); ties -> wider tile
     int bn = op.bn;
     if (bn == 0) {

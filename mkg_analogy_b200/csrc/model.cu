@@ -895,10 +895,12 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             ch.wait(stw, ch.mark(stx));
             B2_TRY(rtw.grad_weight(Mt, H, H, t16b, H, a.ctx16, H, p.ao_w, -1));
             B2_TRY(rt.grad_input(Mt, H, H, t16b, p.ao_w, nullptr, 0, nullptr, w.t32b, nullptr));      // d ctx
-            // dV (gradient wrt the vision output of layer i) and dk1/dv1 come from vision layer i+1's backward
+            // the rows pass of the fusion backward only needs this chain's own tensors; dV (gradient wrt the vision output of
+            // layer i, which the keys pass adds into) and dk1/dv1 come from vision layer i+1's backward: wait as late as possible
+            if (fused)
+                { ProfScope ps(h, stx, CAT_FUSION); B2_TRY(launch_fusion_bwd_rows(w.t32c, a.ctx32, w.V32[i + 1], a.flse, w.pbuf, w.dsbuf, w.t32b, B, L, Nv, H, stx)); }
             if (i + 1 < D && i + 1 >= d.fuse_from) ch.wait(stx, ev_vdone[i + 1]);
             if (fused) {
-                { ProfScope ps(h, stx, CAT_FUSION); B2_TRY(launch_fusion_bwd_rows(w.t32c, a.ctx32, w.V32[i + 1], a.flse, w.pbuf, w.dsbuf, w.t32b, B, L, Nv, H, stx)); }
                 { ProfScope ps(h, stx, CAT_FUSION); B2_TRY(launch_fusion_bwd_keys(w.t32c, a.ctx32, w.pbuf, w.dsbuf, (i == D - 1) ? nullptr : w.dV[pb], w.dV[pb], w.dV16[pb], B, L, Nv, H, stx)); }
             }
             if (fused) ev_tfus[i] = ch.mark(stx);      // dV / dV16 now include this layer's fusion contribution
