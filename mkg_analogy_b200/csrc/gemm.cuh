@@ -34,6 +34,7 @@ struct GemmOp {
     int accumulate = 0;                   // out_f32 += value (atomic; required when split_k > 1)
     int split_k = 1;
     int bn = 0;                           // N tile (0 = auto: 128)
+    int max_ctas = 0;                     // bound of the persistent grid (0 = one CTA per SM): leaves SMs to concurrent streams
 };
 
 struct GemmPlan;  // opaque: encoded tensor maps + launch geometry

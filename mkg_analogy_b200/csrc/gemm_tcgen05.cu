@@ -183,6 +183,7 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
     const long tiles = (long)d.mt * d.nt * split;
     long cap = num_sms();
     if (grid_cap() > 0 && grid_cap() < cap) cap = grid_cap();
+    if (op.max_ctas > 0 && op.max_ctas < cap) cap = op.max_ctas;
     p->grid = dim3((unsigned)(tiles < cap ? tiles : cap), 1, 1);
     p->pair = pair;
     if (pair) {

@@ -327,7 +327,7 @@ int run_gemm(b200mart_handle* h, const GemmOp& op, cudaStream_t s) {
     key[k++] = (long)op.dact_src; key[k++] = op.ldx; key[k++] = op.dact; key[k++] = (long)op.residual; key[k++] = op.ldr;
     key[k++] = (long)op.out_f32; key[k++] = op.ldo32; key[k++] = (long)op.out_bf16; key[k++] = op.ldo16;
     key[k++] = op.accumulate; key[k++] = op.split_k; key[k++] = op.bn; key[k++] = op.save_grad;
-    key[k++] = (long)op.colsum_out; key[k++] = (long)op.colsum_out2; key[k++] = op.drop.thresh;
+    key[k++] = (long)op.colsum_out; key[k++] = (long)op.colsum_out2; key[k++] = op.drop.thresh; key[k++] = op.max_ctas;
     std::string ks(reinterpret_cast<const char*>(key), k * sizeof(long));
     auto it = h->plans.find(ks);
     GemmPlan* plan = nullptr;
@@ -357,12 +357,22 @@ int run_gemm(b200mart_handle* h, const GemmOp& op, cudaStream_t s) {
     return gemm_plan_launch(plan, s, op.drop.thresh ? &op.drop : nullptr);
 }
 
-// split-K factor for weight-gradient GEMMs so that the grid covers the machine (148 SMs)
-int pick_split(int M, int N, int K) {
+// bound of the persistent grid of the weight-gradient GEMMs (B200MART_DW_MAXCTAS; 0 = one CTA per SM): they run on side
+// streams next to the two dependent chains, and a resident persistent CTA is never preempted whatever the stream priority
+int dw_max_ctas() {
+    static int cap = -1;
+    // default 40 of 148 SMs (about the weight gradients' share of the backward FLOPs): measured 7.87 -> 7.67 ms per step
+    if (cap < 0) { const char* e = getenv("B200MART_DW_MAXCTAS"); cap = e ? atoi(e) : 40; if (cap < 0) cap = 0; }
+    return cap;
+}
+
+// split-K factor for weight-gradient GEMMs so that the grid covers the CTAs it may use (148 SMs, or the side-stream bound)
+int pick_split(int M, int N, int K, int ctas = 148) {
     const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
     const int kb = (K + 63) / 64;
+    const int want = ctas * 120 / 148;
     int split = 1;
-    while (tiles * split < 120 && split * 2 <= kb && split < 16) split *= 2;
+    while (tiles * split < want && split * 2 <= kb && split < 16) split *= 2;
     return split;
 }
 
@@ -416,7 +426,7 @@ struct Run {
         static int wide = -1;
         if (wide < 0) { const char* e = getenv("B200MART_DW_WIDE"); wide = e ? atoi(e) : 0; }
         op.bn = (wide && (long)N * K >= 1500000L) ? 256 : 128;
-        if (!wide) { op.bn = 0; op.split_k = pick_split(N, K, M); }
+        if (!wide) { op.bn = 0; op.split_k = pick_split(N, K, M, dw_max_ctas() > 0 ? dw_max_ctas() : 148); }
         else {
             const int tiles = ((N + 127) / 128) * ((K + op.bn - 1) / op.bn);
             const int kb = (M + 63) / 64;
@@ -426,6 +436,9 @@ struct Run {
             if (split > kb) split = kb;
             op.split_k = split;
         }
+        // weight-gradient products run on side streams next to the two dependent chains: a bounded grid keeps SMs free for
+        // the chains' kernels (a resident persistent CTA is never preempted, whatever the stream priorities)
+        op.max_ctas = dw_max_ctas();
         B2_TRY(run_gemm(h, op, s));
         if (b_off >= 0) B2_TRY(launch_colsum_bf16(dY, ldy, g32(b_off), M, N, s));
         return 0;
