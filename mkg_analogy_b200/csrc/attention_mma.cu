@@ -10,6 +10,7 @@
 // (The 97 % of the step's FLOPs that are large GEMMs run on tcgen05, gemm_kernel.cuh.)
 // Backward = rows pass (dQ, dW0/dW1, delta) + keys pass (dK, dV; fp32 for prefix keys), both recomputing P.
 #include "kernels.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -484,6 +485,197 @@ attn_bwd_keys_mma(const AttnBwd gr, const float* __restrict__ delta) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ backward, one kernel
+// Both passes in ONE CTA per (head, sample) when P and dS of the whole (head, sample) fit in shared memory (bf16,
+// [Lq][n]): phase A = the rows pass above (warp per 16 query rows: S, dP, P, dS, dQ, dW0/dW1) which also leaves P (with
+// its dropout mask) and dS f in shared memory; phase B = the keys pass (warp per 16 keys) reading them back TRANSPOSED
+// with ldmatrix.trans as the A operand of dV = P^T dO and dK = (dS f)^T Q, instead of recomputing S^T and dP^T from
+// global memory.  5 matrix products instead of 7, one launch, no delta round trip, Q / dO staged once over the K / V
+// buffers phase A is done with.  (The two-kernel path stays for shapes whose P does not fit: MKGformer-large vision.)
+template <int NW>
+__global__ void __launch_bounds__(NW * 32)
+attn_bwd_fused(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const AttnFwd& a = gr.f;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int n1 = a.n1, n2 = a.n2, n = n1 + n2, n_pad = (n + 63) & ~63, Lq = a.Lq, Lq16 = (Lq + 15) & ~15;
+    const int R0 = n_pad > Lq16 ? n_pad : Lq16;     // rows of each half of the operand region
+    const int LDP = n_pad + 8;                      // row of P / dS (bf16 elements): 16 B past a multiple of 128 B
+    bf16* Ks = reinterpret_cast<bf16*>(smem);       // phase A: K | V ; phase B: Q | dO
+    bf16* Vs = Ks + (size_t)R0 * LDS;
+    bf16* Ps = Vs + (size_t)R0 * LDS;               // [Lq16][LDP]  P (dropped)
+    bf16* Ds = Ps + (size_t)Lq16 * LDP;             // [Lq16][LDP]  dS * f
+    float* madd = reinterpret_cast<float*>(Ds + (size_t)Lq16 * LDP);
+    __shared__ float wred[2][NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    {   // stage_keys with this kernel's thread count
+        if (n1 > 0) {
+            stage_bf16(Ks, a.k1 + (long)b * n1 * a.ld1 + h * D, a.ld1, n1, n1, tid, NW * 32);
+            stage_bf16(Vs, a.v1 + (long)b * n1 * a.ld1 + h * D, a.ld1, n1, n1, tid, NW * 32);
+        }
+        stage_bf16(Ks + n1 * LDS, a.k2 + (long)b * n2 * a.ld2 + h * D, a.ld2, n2, n_pad - n1, tid, NW * 32);
+        stage_bf16(Vs + n1 * LDS, a.v2 + (long)b * n2 * a.ld2 + h * D, a.ld2, n2, n_pad - n1, tid, NW * 32);
+        for (int j = tid; j < n_pad; j += NW * 32) {
+            float m = 0.f;
+            if (j >= n) m = NEG_BIG;
+            else if (a.key_mask && j >= n1) m = (1.0f - (float)a.key_mask[(long)b * n2 + (j - n1)]) * -10000.0f;
+            madd[j] = m;
+        }
+    }
+    const Adapt ad = load_adapt(a, b);
+    __syncthreads();
+
+    // ---------------- phase A: query-row blocks
+    const bf16* qbase = a.q + (long)b * Lq * a.ldq + h * D;
+    const float* dobase = gr.dout + (long)b * Lq * gr.lddo + h * D;
+    const bf16* obase = ctx + (long)b * Lq * ldctx + h * D;
+    float dw0 = 0.f, dw1 = 0.f;
+    for (int r0 = warp * 16; r0 < Lq16; r0 += NW * 16) {
+        uint32_t qa[4][4], doa[4][4];
+        float dl[2];
+        load_a_bf16(qbase, a.ldq, r0, Lq, lane, qa);
+        load_a_f32(dobase, gr.lddo, r0, Lq, lane, doa, obase, ldctx, dl);
+        float lse[2];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            dl[hh] = quad_sum(dl[hh]);
+            const int row = r0 + g + 8 * hh;
+            lse[hh] = (row < Lq) ? a.lse[((long)b * a.nh + h) * Lq + row] : 0.f;
+        }
+        float dq[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+        for (int kc = 0; kc < n_pad; kc += 64) {
+            float s[8][4], dp[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+                dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+            }
+            mma_a_bt(s, qa, Ks, kc, lane);
+            mma_a_bt(dp, doa, Vs, kc, lane);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                float pd[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = kc + nt * 8 + 2 * t + (e & 1);
+                    const int row = r0 + g + 8 * (e >> 1);
+                    const int j2 = col - n1;
+                    const float f = afactor(ad, row, j2);
+                    const float sraw = s[nt][e] * a.scale;
+                    const float p = (row < Lq) ? __expf(sraw * f + madd[col] - lse[e >> 1]) : 0.f;
+                    float mult = 1.f;
+                    if (a.drop.thresh) mult = drop_mult(a.drop, (uint32_t)((((long)b * a.nh + h) * Lq + row) * n + col));
+                    const float ds = p * (dp[nt][e] * mult - dl[e >> 1]);
+                    if (ad.split >= 0 && j2 >= ad.split && col < n) {
+                        if (row >= ad.split) dw1 = fmaf(ds, sraw, dw1);
+                        else if (row >= ad.row_lo) dw0 = fmaf(ds, sraw, dw0);
+                    }
+                    pd[e] = p * mult;
+                    s[nt][e] = ds * f;
+                }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int off = (r0 + g + 8 * hh) * LDP + kc + nt * 8 + 2 * t;
+                    *reinterpret_cast<uint32_t*>(Ps + off) = pack_bf16x2(pd[2 * hh], pd[2 * hh + 1]);
+                    *reinterpret_cast<uint32_t*>(Ds + off) = pack_bf16x2(s[nt][2 * hh], s[nt][2 * hh + 1]);
+                }
+            }
+            uint32_t da[4][4];
+            acc_to_a(s, da);
+            mma_p_b(dq, da, Ks, kc, lane);
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int row = r0 + g + 8 * hh;
+            if (row < Lq) {
+                const long off = ((long)b * Lq + row) * gr.ldd + h * D;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+                    *reinterpret_cast<uint32_t*>(gr.dq + off + nt * 8 + 2 * t) =
+                        pack_bf16x2(dq[nt][2 * hh] * a.scale, dq[nt][2 * hh + 1] * a.scale);
+            }
+        }
+    }
+    __syncthreads();            // P / dS complete, K / V dead
+    bf16* Qs = Ks;
+    bf16* Os = Vs;
+    stage_bf16(Qs, qbase, a.ldq, Lq, Lq16, tid, NW * 32);
+    stage_f32_as_bf16(Os, dobase, gr.lddo, Lq, Lq16, tid, NW * 32);
+    __syncthreads();
+
+    // ---------------- phase B: key blocks
+    const int lr = lane & 7, sel = lane >> 3;
+    const uint32_t ps_u = smem_u32(Ps), ds_u = smem_u32(Ds), qs_u = smem_u32(Qs), os_u = smem_u32(Os);
+    for (int j0 = warp * 16; j0 < n; j0 += NW * 16) {
+        float dk[8][4], dv[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+            dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+        }
+        for (int r16 = 0; r16 < Lq16; r16 += 16) {
+            // A = P^T / (dS f)^T tile (16 keys x 16 query rows): transposed 8x8 blocks of the row-major [row][key] buffers
+            uint32_t pa[4], da[4];
+            const uint32_t aoff = (uint32_t)((r16 + lr + 8 * (sel >> 1)) * LDP + j0 + 8 * (sel & 1)) * 2u;
+            ldsm_x4_t(ps_u + aoff, pa);
+            ldsm_x4_t(ds_u + aoff, da);
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                const uint32_t boff = (uint32_t)((r16 + (sel & 1) * 8 + lr) * LDS + np * 16 + (sel >> 1) * 8) * 2u;
+                uint32_t bo[4], bq[4];
+                ldsm_x4_t(os_u + boff, bo);
+                ldsm_x4_t(qs_u + boff, bq);
+                mma16816(dv[2 * np], pa, bo[0], bo[1]);
+                mma16816(dv[2 * np + 1], pa, bo[2], bo[3]);
+                mma16816(dk[2 * np], da, bq[0], bq[1]);
+                mma16816(dk[2 * np + 1], da, bq[2], bq[3]);
+            }
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int j = j0 + g + 8 * hh;
+            if (j >= n) continue;
+            if (j < n1) {
+                const long off = ((long)b * n1 + j) * gr.ldd1 + h * D;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    *reinterpret_cast<float2*>(gr.dk1 + off + nt * 8 + 2 * t) = make_float2(dk[nt][2 * hh] * a.scale, dk[nt][2 * hh + 1] * a.scale);
+                    *reinterpret_cast<float2*>(gr.dv1 + off + nt * 8 + 2 * t) = make_float2(dv[nt][2 * hh], dv[nt][2 * hh + 1]);
+                }
+            } else {
+                const long row = (long)b * n2 + (j - n1);
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    float k0 = dk[nt][2 * hh] * a.scale, k1 = dk[nt][2 * hh + 1] * a.scale;
+                    float v0 = dv[nt][2 * hh], v1 = dv[nt][2 * hh + 1];
+                    if (gr.dk2_add) {
+                        const float2 ak = *reinterpret_cast<const float2*>(gr.dk2_add + row * gr.ldadd + h * D + nt * 8 + 2 * t);
+                        const float2 av = *reinterpret_cast<const float2*>(gr.dv2_add + row * gr.ldadd + h * D + nt * 8 + 2 * t);
+                        k0 += ak.x; k1 += ak.y; v0 += av.x; v1 += av.y;
+                    }
+                    *reinterpret_cast<uint32_t*>(gr.dk2 + row * gr.ldd + h * D + nt * 8 + 2 * t) = pack_bf16x2(k0, k1);
+                    *reinterpret_cast<uint32_t*>(gr.dv2 + row * gr.ldd + h * D + nt * 8 + 2 * t) = pack_bf16x2(v0, v1);
+                }
+            }
+        }
+    }
+    if (a.sep_idx) {
+        dw0 = warp_sum(dw0);
+        dw1 = warp_sum(dw1);
+        if (lane == 0) { wred[0][warp] = dw0; wred[1][warp] = dw1; }
+        __syncthreads();
+        if (tid == 0) {
+            float s0 = 0.f, s1 = 0.f;
+            for (int w = 0; w < NW; ++w) { s0 += wred[0][w]; s1 += wred[1][w]; }
+            const float w0 = *a.w0, w1 = *a.w1;     // torch.clamp passes the gradient at both (inclusive) bounds
+            if (w0 >= 0.f && w0 <= 0.5f) atomicAdd(gr.dw0, s0);
+            if (w1 >= 0.5f && w1 <= 1.0f) atomicAdd(gr.dw1, s1);
+        }
+    }
+}
+
 int check_attn(const AttnFwd& a) {
     B2_CHECK(a.B > 0 && a.Lq > 0 && a.nh > 0 && a.n2 > 0 && a.n1 >= 0, "attention: bad sizes B=%d Lq=%d nh=%d n1=%d n2=%d", a.B,
              a.Lq, a.nh, a.n1, a.n2);
@@ -520,6 +712,24 @@ int launch_attention_bwd(const AttnBwd& g, const bf16* ctx, long ldctx, float* d
     B2_CHECK(a.n1 == 0 || (g.dk1 && g.dv1), "attention bwd: prefix gradients need dk1/dv1");
     B2_CHECK(g.lddo % 4 == 0 && g.ldd % 2 == 0 && ldctx % 2 == 0, "attention bwd: bad leading dimensions");
     const int n_pad = (a.n1 + a.n2 + 63) & ~63;
+    {   // one-kernel path when P and dS of a (head, sample) fit in shared memory next to the operands
+        static int allow = -1;
+        if (allow < 0) { const char* e = getenv("B200MART_ATTN_FUSED_BWD"); allow = e ? atoi(e) : 1; }
+        const int lq16 = (a.Lq + 15) & ~15;
+        const int r0 = n_pad > lq16 ? n_pad : lq16;
+        const size_t smemf = (size_t)2 * r0 * LDS * 2 + (size_t)2 * lq16 * (n_pad + 8) * 2 + (size_t)n_pad * 4;
+        if (allow && smemf <= 200 * 1024) {
+            if (a.Lq <= 64 && a.n1 + a.n2 <= 64) {
+                B2_TRY(set_smem(attn_bwd_fused<4>, smemf));
+                attn_bwd_fused<4><<<dim3(a.nh, a.B), 4 * 32, smemf, s>>>(g, ctx, ldctx);
+            } else {
+                B2_TRY(set_smem(attn_bwd_fused<8>, smemf));
+                attn_bwd_fused<8><<<dim3(a.nh, a.B), 8 * 32, smemf, s>>>(g, ctx, ldctx);
+            }
+            B2_LAUNCHED();
+            return 0;
+        }
+    }
     const size_t smem1 = (size_t)2 * n_pad * LDS * 2 + (size_t)n_pad * 4;
     B2_TRY(set_smem(attn_bwd_rows_mma, smem1));
     attn_bwd_rows_mma<<<dim3(a.nh, a.B), WARPS * 32, smem1, s>>>(g, ctx, ldctx, delta);
