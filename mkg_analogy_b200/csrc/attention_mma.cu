@@ -98,6 +98,66 @@ __device__ __forceinline__ void stage_f32_as_bf16(bf16* dst, const float* src, l
     }
 }
 
+// asynchronous variant (cp.async, 16 B per request, zero fill for the padding rows): every request of a thread is in
+// flight at once; finish with cp_async_wait_all() + __syncthreads()
+__device__ __forceinline__ void stage_bf16_async(bf16* dst, const bf16* src, long ld, int rows, int rows_pad, int tid, int nthreads) {
+    for (int i = tid; i < rows_pad * 8; i += nthreads) {
+        const int r = i >> 3, c = i & 7;
+        const bool ok = r < rows;
+        const uint32_t d = smem_u32(dst + r * LDS + c * 8);
+        const bf16* g = src + (long)(ok ? r : 0) * ld + c * 8;
+        const int bytes = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(bytes) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// dO (fp32, global) -> bf16 rows in shared memory, and delta[r] = sum_d dO[r][d] * O[r][d] (O = forward context, bf16) in
+// fp32.  16 consecutive lanes cover one row (4 columns each); loads are issued four rows ahead of their use.
+__device__ __forceinline__ void stage_do_delta(bf16* dst, float* delta_s, const float* dsrc, long ldd, const bf16* osrc, long ldo, int rows,
+                                               int rows_pad, int tid, int nthreads) {
+    const int total = rows_pad * 16;
+    for (int base = 0; base < total; base += 4 * nthreads) {      // uniform trip count: the shuffles below need whole warps
+        const int i0 = base + tid;
+        float4 v[4];
+        uint2 o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * nthreads, r = i >> 4, c = i & 15;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            o[u] = make_uint2(0u, 0u);
+            if (i < total && r < rows) {
+                v[u] = *reinterpret_cast<const float4*>(dsrc + (long)r * ldd + c * 4);
+                o[u] = *reinterpret_cast<const uint2*>(osrc + (long)r * ldo + c * 4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * nthreads, r = i >> 4, c = i & 15;
+            const float2 o0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o[u].x));
+            const float2 o1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o[u].y));
+            float part = v[u].x * o0.x + v[u].y * o0.y + v[u].z * o1.x + v[u].w * o1.y;
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            part += __shfl_xor_sync(0xffffffffu, part, 4);
+            part += __shfl_xor_sync(0xffffffffu, part, 8);
+            if (i < total) {
+                *reinterpret_cast<uint2*>(dst + r * LDS + c * 4) = make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
+                if (c == 0) delta_s[r] = part;
+            }
+        }
+    }
+}
+// rows [row0, row0 + 16) x 64 columns of a padded shared-memory matrix as mma A fragments (4 k-steps)
+__device__ __forceinline__ void load_a_smem(const bf16* As, int row0, int lane, uint32_t (&a)[4][4]) {
+    const uint32_t base = smem_u32(As);
+    const int lr = lane & 7, sel = lane >> 3;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+        ldsm_x4(base + (uint32_t)((row0 + lr + 8 * (sel & 1)) * LDS + ks * 16 + 8 * (sel >> 1)) * 2u, a[ks]);
+}
+
 // C[16 x 64 keys] = A[16 x 64] * Bs[key][d]^T for the 64 "n" rows starting at n0 of a padded smem matrix (n x k row-major)
 __device__ __forceinline__ void mma_a_bt(float (&c)[8][4], const uint32_t (&a)[4][4], const bf16* Bs, int n0, int lane) {
     const uint32_t base = smem_u32(Bs);
@@ -493,53 +553,57 @@ attn_bwd_keys_mma(const AttnBwd gr, const float* __restrict__ delta) {
 // global memory.  5 matrix products instead of 7, one launch, no delta round trip, Q / dO staged once over the K / V
 // buffers phase A is done with.  (The two-kernel path stays for shapes whose P does not fit: MKGformer-large vision.)
 template <int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 3 : 1)     // text tiles: 3 CTAs per SM hold all B * heads CTAs in one wave
 attn_bwd_fused(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx) {
     extern __shared__ __align__(16) uint8_t smem[];
     const AttnFwd& a = gr.f;
     const int h = blockIdx.x, b = blockIdx.y;
     const int n1 = a.n1, n2 = a.n2, n = n1 + n2, n_pad = (n + 63) & ~63, Lq = a.Lq, Lq16 = (Lq + 15) & ~15;
-    const int R0 = n_pad > Lq16 ? n_pad : Lq16;     // rows of each half of the operand region
     const int LDP = n_pad + 8;                      // row of P / dS (bf16 elements): 16 B past a multiple of 128 B
-    bf16* Ks = reinterpret_cast<bf16*>(smem);       // phase A: K | V ; phase B: Q | dO
-    bf16* Vs = Ks + (size_t)R0 * LDS;
-    bf16* Ps = Vs + (size_t)R0 * LDS;               // [Lq16][LDP]  P (dropped)
+    bf16* Ks = reinterpret_cast<bf16*>(smem);       // [n_pad][LDS]
+    bf16* Vs = Ks + (size_t)n_pad * LDS;
+    bf16* Qs = Vs + (size_t)n_pad * LDS;            // [Lq16][LDS]
+    bf16* Os = Qs + (size_t)Lq16 * LDS;             // [Lq16][LDS]  dO (bf16)
+    bf16* Ps = Os + (size_t)Lq16 * LDS;             // [Lq16][LDP]  P (dropped)
     bf16* Ds = Ps + (size_t)Lq16 * LDP;             // [Lq16][LDP]  dS * f
-    float* madd = reinterpret_cast<float*>(Ds + (size_t)Lq16 * LDP);
+    float* madd = reinterpret_cast<float*>(Ds + (size_t)Lq16 * LDP);   // [n_pad]
+    float* dl_s = madd + n_pad;                     // [Lq16] delta = rowsum(dO * O)
     __shared__ float wred[2][NW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-    {   // stage_keys with this kernel's thread count
+    const bf16* qbase = a.q + (long)b * Lq * a.ldq + h * D;
+    const float* dobase = gr.dout + (long)b * Lq * gr.lddo + h * D;
+    const bf16* obase = ctx + (long)b * Lq * ldctx + h * D;
+    {   // every operand of the (head, sample) goes to shared memory once; all requests in flight together
         if (n1 > 0) {
-            stage_bf16(Ks, a.k1 + (long)b * n1 * a.ld1 + h * D, a.ld1, n1, n1, tid, NW * 32);
-            stage_bf16(Vs, a.v1 + (long)b * n1 * a.ld1 + h * D, a.ld1, n1, n1, tid, NW * 32);
+            stage_bf16_async(Ks, a.k1 + (long)b * n1 * a.ld1 + h * D, a.ld1, n1, n1, tid, NW * 32);
+            stage_bf16_async(Vs, a.v1 + (long)b * n1 * a.ld1 + h * D, a.ld1, n1, n1, tid, NW * 32);
         }
-        stage_bf16(Ks + n1 * LDS, a.k2 + (long)b * n2 * a.ld2 + h * D, a.ld2, n2, n_pad - n1, tid, NW * 32);
-        stage_bf16(Vs + n1 * LDS, a.v2 + (long)b * n2 * a.ld2 + h * D, a.ld2, n2, n_pad - n1, tid, NW * 32);
+        stage_bf16_async(Ks + n1 * LDS, a.k2 + (long)b * n2 * a.ld2 + h * D, a.ld2, n2, n_pad - n1, tid, NW * 32);
+        stage_bf16_async(Vs + n1 * LDS, a.v2 + (long)b * n2 * a.ld2 + h * D, a.ld2, n2, n_pad - n1, tid, NW * 32);
+        stage_bf16_async(Qs, qbase, a.ldq, Lq, Lq16, tid, NW * 32);
+        stage_do_delta(Os, dl_s, dobase, gr.lddo, obase, ldctx, Lq, Lq16, tid, NW * 32);
         for (int j = tid; j < n_pad; j += NW * 32) {
             float m = 0.f;
             if (j >= n) m = NEG_BIG;
             else if (a.key_mask && j >= n1) m = (1.0f - (float)a.key_mask[(long)b * n2 + (j - n1)]) * -10000.0f;
             madd[j] = m;
         }
+        cp_async_wait_all();
     }
     const Adapt ad = load_adapt(a, b);
     __syncthreads();
 
     // ---------------- phase A: query-row blocks
-    const bf16* qbase = a.q + (long)b * Lq * a.ldq + h * D;
-    const float* dobase = gr.dout + (long)b * Lq * gr.lddo + h * D;
-    const bf16* obase = ctx + (long)b * Lq * ldctx + h * D;
     float dw0 = 0.f, dw1 = 0.f;
     for (int r0 = warp * 16; r0 < Lq16; r0 += NW * 16) {
         uint32_t qa[4][4], doa[4][4];
-        float dl[2];
-        load_a_bf16(qbase, a.ldq, r0, Lq, lane, qa);
-        load_a_f32(dobase, gr.lddo, r0, Lq, lane, doa, obase, ldctx, dl);
-        float lse[2];
+        load_a_smem(Qs, r0, lane, qa);
+        load_a_smem(Os, r0, lane, doa);
+        float dl[2], lse[2];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-            dl[hh] = quad_sum(dl[hh]);
             const int row = r0 + g + 8 * hh;
+            dl[hh] = dl_s[row];
             lse[hh] = (row < Lq) ? a.lse[((long)b * a.nh + h) * Lq + row] : 0.f;
         }
         float dq[8][4];
@@ -598,12 +662,7 @@ attn_bwd_fused(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx) {
             }
         }
     }
-    __syncthreads();            // P / dS complete, K / V dead
-    bf16* Qs = Ks;
-    bf16* Os = Vs;
-    stage_bf16(Qs, qbase, a.ldq, Lq, Lq16, tid, NW * 32);
-    stage_f32_as_bf16(Os, dobase, gr.lddo, Lq, Lq16, tid, NW * 32);
-    __syncthreads();
+    __syncthreads();            // P / dS complete
 
     // ---------------- phase B: key blocks
     const int lr = lane & 7, sel = lane >> 3;
@@ -716,8 +775,7 @@ int launch_attention_bwd(const AttnBwd& g, const bf16* ctx, long ldctx, float* d
         static int allow = -1;
         if (allow < 0) { const char* e = getenv("B200MART_ATTN_FUSED_BWD"); allow = e ? atoi(e) : 1; }
         const int lq16 = (a.Lq + 15) & ~15;
-        const int r0 = n_pad > lq16 ? n_pad : lq16;
-        const size_t smemf = (size_t)2 * r0 * LDS * 2 + (size_t)2 * lq16 * (n_pad + 8) * 2 + (size_t)n_pad * 4;
+        const size_t smemf = (size_t)2 * (n_pad + lq16) * LDS * 2 + (size_t)2 * lq16 * (n_pad + 8) * 2 + (size_t)(n_pad + lq16) * 4;
         if (allow && smemf <= 200 * 1024) {
             if (a.Lq <= 64 && a.n1 + a.n2 <= 64) {
                 B2_TRY(set_smem(attn_bwd_fused<4>, smemf));
