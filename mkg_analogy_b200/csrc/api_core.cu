@@ -2,6 +2,7 @@
 #include "gemm.cuh"
 #include "../../include/b200mart.h"
 #include <stdarg.h>
+#include <stdlib.h>
 
 thread_local char g_b200mart_err[512] = "";
 unsigned long long g_b200mart_launches = 0;
@@ -12,6 +13,12 @@ int b200mart_set_err(int code, const char* fmt, ...) {
     vsnprintf(g_b200mart_err, sizeof(g_b200mart_err), fmt, ap);
     va_end(ap);
     return code;
+}
+
+int b200mart_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("B200MART_PDL"); on = e ? (atoi(e) != 0) : 1; }
+    return on;
 }
 
 extern "C" const char* b200mart_last_error(void) { return g_b200mart_err; }

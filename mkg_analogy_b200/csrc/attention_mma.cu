@@ -253,6 +253,8 @@ __device__ __forceinline__ void stage_keys(const AttnFwd& a, int b, int h, bf16*
 __global__ void __launch_bounds__(WARPS * 32)
 attn_fwd_mma(const AttnFwd a, float* __restrict__ out32) {
     extern __shared__ __align__(16) uint8_t smem[];
+    pdl_wait();
+    pdl_launch_dependents();
     const int h = blockIdx.x, b = blockIdx.y;
     const int n1 = a.n1, n = a.n1 + a.n2, n_pad = (n + 63) & ~63;
     bf16* Ks = reinterpret_cast<bf16*>(smem);
@@ -556,6 +558,8 @@ template <int NW>
 __global__ void __launch_bounds__(NW * 32, NW == 4 ? 3 : 1)     // text tiles: 3 CTAs per SM hold all B * heads CTAs in one wave
 attn_bwd_fused(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx) {
     extern __shared__ __align__(16) uint8_t smem[];
+    pdl_wait();
+    pdl_launch_dependents();
     const AttnFwd& a = gr.f;
     const int h = blockIdx.x, b = blockIdx.y;
     const int n1 = a.n1, n2 = a.n2, n = n1 + n2, n_pad = (n + 63) & ~63, Lq = a.Lq, Lq16 = (Lq + 15) & ~15;
@@ -759,7 +763,7 @@ int launch_attention_fwd(const AttnFwd& a, float* out32, cudaStream_t s) {
     const int n_pad = (a.n1 + a.n2 + 63) & ~63;
     const size_t smem = (size_t)2 * n_pad * LDS * 2 + (size_t)n_pad * 4;
     B2_TRY(set_smem(attn_fwd_mma, smem));
-    attn_fwd_mma<<<dim3(a.nh, a.B), WARPS * 32, smem, s>>>(a, out32);
+    CUDA_TRY(launch_pdl(attn_fwd_mma, dim3(a.nh, a.B), dim3(WARPS * 32), smem, s, a, out32));
     B2_LAUNCHED();
     return 0;
 }
@@ -779,10 +783,10 @@ int launch_attention_bwd(const AttnBwd& g, const bf16* ctx, long ldctx, float* d
         if (allow && smemf <= 200 * 1024) {
             if (a.Lq <= 64 && a.n1 + a.n2 <= 64) {
                 B2_TRY(set_smem(attn_bwd_fused<4>, smemf));
-                attn_bwd_fused<4><<<dim3(a.nh, a.B), 4 * 32, smemf, s>>>(g, ctx, ldctx);
+                CUDA_TRY(launch_pdl(attn_bwd_fused<4>, dim3(a.nh, a.B), dim3(4 * 32), smemf, s, g, ctx, ldctx));
             } else {
                 B2_TRY(set_smem(attn_bwd_fused<8>, smemf));
-                attn_bwd_fused<8><<<dim3(a.nh, a.B), 8 * 32, smemf, s>>>(g, ctx, ldctx);
+                CUDA_TRY(launch_pdl(attn_bwd_fused<8>, dim3(a.nh, a.B), dim3(8 * 32), smemf, s, g, ctx, ldctx));
             }
             B2_LAUNCHED();
             return 0;

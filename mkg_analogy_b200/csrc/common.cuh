@@ -64,6 +64,30 @@ inline DropCfg make_drop(float p, uint32_t seed, int site) {
     return d;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the two dependent chains is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs
+// may become resident (and run their prologue: barrier / tensor-memory set-up, index arithmetic) while the previous
+// kernel of the stream is still draining; pdl_wait() (griddepcontrol.wait) blocks until that kernel has completed and
+// its writes are visible, and MUST precede the kernel's first access to global memory.  pdl_launch_dependents() lets
+// the next kernel's CTAs be scheduled once every CTA of this grid has called it (or exited).  B200MART_PDL=0 turns the
+// attribute off (A/B runs); both instructions are no-ops for a kernel launched without it.
+int b200mart_pdl_enabled();
+#ifdef __CUDACC__
+#include <utility>
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = b200mart_pdl_enabled();
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 // multiplier of element `idx` at a dropout site: 0 (dropped) or 1 / (1 - p)

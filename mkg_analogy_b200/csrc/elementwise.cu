@@ -121,6 +121,8 @@ __device__ __forceinline__ void ln_row(float4 (&v)[MAXV], int nv, int H, const f
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float eps, float* y32, bf16* y16, float* mean,
                                      float* rstd, int M, int H) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -194,6 +196,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                      const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ add,
                      const bf16* __restrict__ dact_src, int dact, float* dx32, bf16* dx16, float* dgamma, float* dbeta,
                      float* dxsum, int M, int H, DropCfg dy_drop, DropCfg dx16_drop) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ float red[];  // [warps][H] x (2 or 3)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int nv = H / 128;
@@ -298,6 +302,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 // block = 32 x 8 threads over a 32-column x ROWS strip; coalesced row-major reads, one atomic per column per block.
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, long ld, float* out, int M, int N, int rows_per_block) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float part[8][33];
     const int col = blockIdx.x * 32 + threadIdx.x;
     const int r0 = blockIdx.y * rows_per_block;
@@ -494,7 +500,7 @@ int launch_text_embed_ln(const int64_t* ids, const int64_t* tt, const float* E, 
 int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y32, bf16* y16,
                          float* mean, float* rstd, int M, int H, cudaStream_t s) {
     B2_TRY(check_h(H));
-    layernorm_fwd_kernel<<<(M + 3) / 4, 128, 0, s>>>(x, gamma, beta, eps, y32, y16, mean, rstd, M, H);
+    CUDA_TRY(launch_pdl(layernorm_fwd_kernel, dim3((M + 3) / 4), dim3(128), 0, s, x, gamma, beta, eps, y32, y16, mean, rstd, M, H));
     B2_LAUNCHED();
     return 0;
 }
@@ -511,8 +517,8 @@ int launch_layernorm_bwd(const float* dy, const float* x, const float* mean, con
     const size_t smem = (size_t)(dxsum ? 3 : 2) * nw * H * sizeof(float);
     auto go = [&](auto kernel) -> int {
         CUDA_TRY(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<blocks, nw * 32, smem, s>>>(dy, x, mean, rstd, gamma, add, dact_src, dact_src ? dact : 0, dx32, dx16, dgamma, dbeta,
-                                            dxsum, M, H, dy_drop, dx16_drop);
+        CUDA_TRY(launch_pdl(kernel, dim3(blocks), dim3(nw * 32), smem, s, dy, x, mean, rstd, gamma, add, dact_src, dact_src ? dact : 0, dx32,
+                            dx16, dgamma, dbeta, dxsum, M, H, dy_drop, dx16_drop));
         return 0;
     };
     const bool small = H <= 768;       // register arrays sized for the hidden size: 6 (base) or 8 (large) float4 per lane
@@ -523,7 +529,7 @@ int launch_layernorm_bwd(const float* dy, const float* x, const float* mean, con
 }
 int launch_colsum_bf16(const bf16* x, long ld, float* out, int M, int N, cudaStream_t s) {
     const int rpb = 128;
-    colsum_kernel<bf16><<<dim3((N + 31) / 32, (M + rpb - 1) / rpb), dim3(32, 8), 0, s>>>(x, ld, out, M, N, rpb);
+    CUDA_TRY(launch_pdl(colsum_kernel<bf16>, dim3((N + 31) / 32, (M + rpb - 1) / rpb), dim3(32, 8), 0, s, x, ld, out, M, N, rpb));
     B2_LAUNCHED();
     return 0;
 }

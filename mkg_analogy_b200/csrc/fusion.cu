@@ -218,6 +218,8 @@ __device__ __forceinline__ void lane_row(const float (&acc)[GPW][4][4], int i, i
 __global__ void __launch_bounds__(FTHREADS, 1)
 fusion_fwd_kernel(const float* __restrict__ ctx, const float* __restrict__ vh, bf16* __restrict__ out, float* __restrict__ lse,
                   int L, int Nv, int H) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(16) float fs[];
     const int ldx = x_ld(H), Nvp = (Nv + 7) & ~7, ldS = s_ld(Nvp);
     float* xs = fs;                    // [FROWS][ldx]
@@ -276,6 +278,8 @@ __global__ void __launch_bounds__(FTHREADS, 1)
 fusion_bwd_rows_kernel(const float* __restrict__ dg, const float* __restrict__ ctx, const float* __restrict__ vh,
                        const float* __restrict__ lse, float* __restrict__ pbuf, float* __restrict__ dsbuf,
                        float* __restrict__ dctx, int L, int Nv, int H) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(16) float fs[];
     const int ldx = x_ld(H), Nvp = (Nv + 7) & ~7, ldS = s_ld(Nvp);
     float* xs = fs;                    // [FROWS][ldx]  ctx rows, later dG rows
@@ -344,6 +348,8 @@ __global__ void __launch_bounds__(FTHREADS, 1)
 fusion_bwd_keys_kernel(const float* __restrict__ dg, const float* __restrict__ ctx, const float* __restrict__ pbuf,
                        const float* __restrict__ dsbuf, const float* __restrict__ dvh_in, float* __restrict__ dvh32,
                        bf16* __restrict__ dvh16, int L, int Nv, int H) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(16) float fs[];
     const int Lp = (L + 7) & ~7, ldA = s_ld(Lp);
     float* Pk = fs;                     // [FROWS keys][ldA]  P^T
@@ -415,7 +421,7 @@ int launch_fusion_fwd(const float* ctx, const float* vh, bf16* out, float* lse, 
     B2_TRY(check_fusion(ctx, vh, out, B, L, Nv, H));
     const size_t smem = (size_t)(FROWS * x_ld(H) + FROWS * s_ld((Nv + 7) & ~7) + FWARPS * FROWS * SLAB_LD) * 4;
     B2_TRY(set_smem(fusion_fwd_kernel, smem));
-    fusion_fwd_kernel<<<dim3((L + FROWS - 1) / FROWS, B), FTHREADS, smem, s>>>(ctx, vh, out, lse, L, Nv, H);
+    CUDA_TRY(launch_pdl(fusion_fwd_kernel, dim3((L + FROWS - 1) / FROWS, B), dim3(FTHREADS), smem, s, ctx, vh, out, lse, L, Nv, H));
     B2_LAUNCHED();
     return 0;
 }
@@ -426,7 +432,7 @@ int launch_fusion_bwd_rows(const float* dg, const float* ctx, const float* vh, c
     B2_CHECK((reinterpret_cast<uintptr_t>(dctx) & 15) == 0, "fusion: dctx must be 16-byte aligned");
     const size_t smem = (size_t)(FROWS * x_ld(H) + 2 * FROWS * s_ld((Nv + 7) & ~7) + FWARPS * FROWS * SLAB_LD) * 4;
     B2_TRY(set_smem(fusion_bwd_rows_kernel, smem));
-    fusion_bwd_rows_kernel<<<dim3((L + FROWS - 1) / FROWS, B), FTHREADS, smem, s>>>(dg, ctx, vh, lse, pbuf, dsbuf, dctx, L, Nv, H);
+    CUDA_TRY(launch_pdl(fusion_bwd_rows_kernel, dim3((L + FROWS - 1) / FROWS, B), dim3(FTHREADS), smem, s, dg, ctx, vh, lse, pbuf, dsbuf, dctx, L, Nv, H));
     B2_LAUNCHED();
     return 0;
 }
@@ -437,7 +443,7 @@ int launch_fusion_bwd_keys(const float* dg, const float* ctx, const float* pbuf,
     B2_CHECK(((reinterpret_cast<uintptr_t>(dvh32) | reinterpret_cast<uintptr_t>(dvh16)) & 15) == 0, "fusion: dvh outputs must be 16-byte aligned");
     const size_t smem = (size_t)2 * FROWS * s_ld((L + 7) & ~7) * 4;
     B2_TRY(set_smem(fusion_bwd_keys_kernel, smem));
-    fusion_bwd_keys_kernel<<<dim3((Nv + FROWS - 1) / FROWS, B), FTHREADS, smem, s>>>(dg, ctx, pbuf, dsbuf, dvh_in, dvh32, dvh16, L, Nv, H);
+    CUDA_TRY(launch_pdl(fusion_bwd_keys_kernel, dim3((Nv + FROWS - 1) / FROWS, B), dim3(FTHREADS), smem, s, dg, ctx, pbuf, dsbuf, dvh_in, dvh32, dvh16, L, Nv, H));
     B2_LAUNCHED();
     return 0;
 }

@@ -374,6 +374,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     if (threadIdx.x == 0) stamp(p, ST_CLK_PROLOGUE);
+    pdl_wait();                  // everything above overlapped the previous kernel of the stream; global memory from here on
 
     // tile -> (m block, n block, k range).  m fastest: concurrently running CTAs share few B (weight) tiles.
     auto tile_coords = [&](int t, int& m0, int& n0, int& kb_begin, int& kb_end) {
@@ -427,6 +428,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (++stage == L::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
+            pdl_launch_dependents();   // all operand loads issued: the next kernel's CTAs may start their prologue
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
@@ -597,6 +599,7 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     if (threadIdx.x == 0) stamp(p, ST_CLK_PROLOGUE);
+    pdl_wait();                  // everything above overlapped the previous kernel of the stream; global memory from here on
 
     auto tile_coords = [&](int t, int& m0, int& n0, int& kb_begin, int& kb_end) {
         const int mb = t % p.mt;
@@ -645,6 +648,7 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     if (++stage == L::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
+            pdl_launch_dependents();   // all operand loads issued: the next kernel's CTAs may start their prologue
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread of the LEADER CTA) =====================

@@ -234,7 +234,7 @@ int gemm_plan_launch(const GemmPlan* p, cudaStream_t stream, const DropCfg* drop
         GemmDev dev = p->dev;
         if (drop) dev.drop = *drop;
         dev.prof = timeline_slot();
-        p->kernel<<<p->grid, GEMM_THREADS, p->smem, stream>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, dev);
+        CUDA_TRY(launch_pdl(p->kernel, p->grid, dim3(GEMM_THREADS), (size_t)p->smem, stream, p->tmA, p->tmB, p->tmA2, p->tmB2, dev));
         B2_LAUNCHED();
         return 0;
     }
@@ -247,11 +247,13 @@ int gemm_plan_launch(const GemmPlan* p, cudaStream_t stream, const DropCfg* drop
         cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
         cfg.dynamicSmemBytes = (size_t)p->smem;
         cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = b200mart_pdl_enabled();
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = 2;
         CUDA_TRY(cudaLaunchKernelEx(&cfg, p->kernel, p->tmA, p->tmB, p->tmA2, p->tmB2, dev));
         ++g_b200mart_launches;
         return 0;
@@ -259,9 +261,9 @@ int gemm_plan_launch(const GemmPlan* p, cudaStream_t stream, const DropCfg* drop
     if (drop) {   // per-step dropout seed: the plan (tensor maps, geometry) is reused, only the mask seed changes
         GemmDev dev = p->dev;
         dev.drop = *drop;
-        p->kernel<<<p->grid, GEMM_THREADS, p->smem, stream>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, dev);
+        CUDA_TRY(launch_pdl(p->kernel, p->grid, dim3(GEMM_THREADS), (size_t)p->smem, stream, p->tmA, p->tmB, p->tmA2, p->tmB2, dev));
     } else {
-        p->kernel<<<p->grid, GEMM_THREADS, p->smem, stream>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, p->dev);
+        CUDA_TRY(launch_pdl(p->kernel, p->grid, dim3(GEMM_THREADS), (size_t)p->smem, stream, p->tmA, p->tmB, p->tmA2, p->tmB2, p->dev));
     }
     B2_LAUNCHED();
     return 0;
