@@ -366,6 +366,18 @@ int dw_max_ctas() {
     return cap;
 }
 
+// bounds of the persistent GEMM grids of the vision / text chain while both chains run (B200MART_CAP_V / _T; 0 = none)
+int chain_cap(int which) {
+    static int cap[2] = {-1, -1};
+    if (cap[0] < 0) {
+        const char* v = getenv("B200MART_CAP_V"); const char* t = getenv("B200MART_CAP_T");
+        cap[0] = v ? atoi(v) : 0; cap[1] = t ? atoi(t) : 0;
+        if (cap[0] < 0) cap[0] = 0;
+        if (cap[1] < 0) cap[1] = 0;
+    }
+    return cap[which];
+}
+
 // split-K factor for weight-gradient GEMMs so that the grid covers the CTAs it may use (148 SMs, or the side-stream bound)
 int pick_split(int M, int N, int K, int ctas = 148) {
     const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
@@ -380,6 +392,7 @@ struct Run {
     b200mart_handle* h;
     const b200mart_buffers* bufs;
     cudaStream_t s;
+    int cap = 0;                                // bound of the persistent GEMM grids of this chain (0 = one CTA per SM)
     DropCfg drop_next = DropCfg{0u, 0u, 1.f};   // consumed by the next linear(): dropout before its residual add
     const float* p32(long off) const { return bufs->params32 + off; }
     const bf16* p16(long off) const { return reinterpret_cast<const bf16*>(bufs->params16) + off; }
@@ -400,6 +413,7 @@ struct Run {
         op.drop = drop_next;
         drop_next = DropCfg{0u, 0u, 1.f};
         op.out_f32 = out32; op.ldo32 = N; op.out_bf16 = out16; op.ldo16 = N;
+        op.max_ctas = cap;
         return run_gemm(h, op, s);
     }
     // dX = dY W  [* act'(dact_src)] [+ residual].  dY (M, N) bf16, W (N, K) -> B operand stored [K=N][N=K] (MN-major)
@@ -413,6 +427,7 @@ struct Run {
         if (colsum_off2 >= 0) op.colsum_out2 = g32(colsum_off2);
         op.residual = residual; op.ldr = K;
         op.out_f32 = out32; op.ldo32 = K; op.out_bf16 = out16; op.ldo16 = K;
+        op.max_ctas = cap;
         return run_gemm(h, op, s);
     }
     // dW (N, K) += dY^T X ; db (N) += colsum(dY).   dY (M, N) bf16 with leading dimension ldy, X (M, K) bf16.
@@ -626,6 +641,7 @@ extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* 
     B2_TRY(chains_begin(h, s, ch));
     const cudaStream_t sv = ch.v, stx = ch.t;          // vision chain / text chain
     Run rv{h, bufs, sv}, rt{h, bufs, stx};
+    if (ch.split) { rv.cap = chain_cap(0); rt.cap = chain_cap(1); }
     std::vector<cudaEvent_t> ev_tqkv(D, nullptr), ev_vout(D, nullptr);
     // dropout state of THIS forward (backward regenerates the same masks)
     h->cur_ph = h->training ? h->p_hidden : 0.f;
@@ -876,6 +892,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
     B2_TRY(chains_begin(h, s, ch));
     const cudaStream_t sv = ch.v, stx = ch.t, svw = ch.vw, stw = ch.tw;
     Run rv{h, bufs, sv}, rt{h, bufs, stx}, rvw{h, bufs, svw}, rtw{h, bufs, stw};
+    if (ch.split) { rv.cap = chain_cap(0); rt.cap = chain_cap(1); }
     std::vector<cudaEvent_t> ev_vdone(D + 1, nullptr), ev_tfus(D, nullptr), ev_tattn(D, nullptr);
     std::vector<cudaEvent_t> ev_tw_done(D + 2, nullptr), ev_vw_done(D + 2, nullptr);
     const float ph = h->cur_ph, pa = h->cur_pa;      // dropout of the forward whose activations are in the workspace
