@@ -225,8 +225,8 @@ def run_cuda(args):
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "peak_source": peak_src,
                 # DRAM bytes per launch from the committed ncu --set full capture of 40 GEMM launches of this step
-                # (profiles/gemm_full_r1d.txt); well below the algorithmic bytes because activations stay in the 126 MB L2
-                "traffic": 19605472.0, "traffic_source": "profiles/gemm_full_r1d.txt (ncu dram__bytes_read+write.sum, per-launch mean)",
+                # (profiles/gemm_full_r1f.txt); well below the algorithmic bytes because activations stay in the 126 MB L2
+                "traffic": 19614874.0, "traffic_source": "profiles/gemm_full_r1f.txt (ncu dram__bytes_read+write.sum, per-launch mean)",
                 "algorithmic_bytes_per_launch": trainer.engine.last_profile_gemm_bytes / gemm_n,
                 "launches_per_step": gemm_n // np_steps, "avg_launch_us": gemm_ms * 1e3 / gemm_n,
                 "gflop_per_launch": gemm_flops / gemm_n / 1e9,

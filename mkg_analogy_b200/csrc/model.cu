@@ -441,7 +441,9 @@ struct Run {
         static int wide = -1;
         if (wide < 0) { const char* e = getenv("B200MART_DW_WIDE"); wide = e ? atoi(e) : 0; }
         op.bn = (wide && (long)N * K >= 1500000L) ? 256 : 128;
-        if (!wide) { op.bn = 0; op.split_k = pick_split(N, K, M, dw_max_ctas() > 0 ? dw_max_ctas() : 148); }
+        // the bound only makes sense while other streams want the SMs: serial execution ("streams" = 0) uses the whole machine
+        const int dwcap = h->split_streams ? dw_max_ctas() : 0;
+        if (!wide) { op.bn = 0; op.split_k = pick_split(N, K, M, dwcap > 0 ? dwcap : 148); }
         else {
             const int tiles = ((N + 127) / 128) * ((K + op.bn - 1) / op.bn);
             const int kb = (M + 63) / 64;
@@ -453,7 +455,7 @@ struct Run {
         }
         // weight-gradient products run on side streams next to the two dependent chains: a bounded grid keeps SMs free for
         // the chains' kernels (a resident persistent CTA is never preempted, whatever the stream priorities)
-        op.max_ctas = dw_max_ctas();
+        op.max_ctas = dwcap;
         B2_TRY(run_gemm(h, op, s));
         if (b_off >= 0) B2_TRY(launch_colsum_bf16(dY, ldy, g32(b_off), M, N, s));
         return 0;
