@@ -109,6 +109,7 @@ class MartTrainer:
         self._grads_clean = False
         if self.overlap_comm:
             self._comm_stream = torch.cuda.Stream(device=self.device)
+            self._update_stream = torch.cuda.Stream(device=self.device)
             self._layer_events = [torch.cuda.Event() for _ in range(2 * cfg.layers)]
             for e in self._layer_events:
                 e.record()                       # materialise the CUDA event handles
@@ -153,12 +154,20 @@ class MartTrainer:
         main, comm = torch.cuda.current_stream(), self._comm_stream
         eng.backward(mb, layer_events=self._layer_events)
 
+        # N > 1: the exchange (NVLink-bound) and the update (HBM-bound) of consecutive layers overlap on two side streams
+        upd = self._update_stream if (self.world > 1 and update is not None) else comm
+
         def finish(b, e):
             if self.world > 1:
                 dist.all_reduce(g[b:e], op=dist.ReduceOp.AVG, group=self.pg)
             if update is not None:
-                eng.adamw(update[0], update[1], weight_decay=self.weight_decay, pretrain=self.pretrain, begin=b, end=e,
-                          zero_grads=True)
+                if upd is not comm:
+                    ev = torch.cuda.Event()
+                    ev.record(comm)
+                    upd.wait_event(ev)
+                with torch.cuda.stream(upd):
+                    eng.adamw(update[0], update[1], weight_decay=self.weight_decay, pretrain=self.pretrain, begin=b, end=e,
+                              zero_grads=True)
 
         with torch.cuda.stream(comm):
             for i in reversed(range(self.cfg.layers)):
@@ -171,6 +180,8 @@ class MartTrainer:
                 finish(0, lo)
             if hi < g.numel():
                 finish(hi, g.numel())
+        if upd is not comm:
+            main.wait_stream(upd)
         main.wait_stream(comm)
 
     # ------------------------------------------------------------------ public API
