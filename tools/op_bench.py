@@ -1,5 +1,7 @@
-"""Isolated timings (CUDA events, warm L2, median of N) of the non-GEMM operators at MKGformer-base step shapes.
-    python tools/op_bench.py [tag]   -> gpurun_out/op_bench_<tag>.txt"""
+"""Isolated kernel durations (CUPTI through torch.profiler, warm L2, mean of 10) of the non-GEMM operators at MKGformer-base
+step shapes.  Run with B200MART_PDL=0: under programmatic dependent launch a kernel starts while its predecessor drains and
+its CUPTI duration includes that wait.
+    B200MART_PDL=0 python tools/op_bench.py [tag]   -> gpurun_out/op_bench_<tag>.txt"""
 import os
 import sys
 
