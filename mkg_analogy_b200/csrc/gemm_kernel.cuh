@@ -22,6 +22,8 @@ namespace gemmk {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int GEMM_THREADS = 192;
+constexpr int PAIR_EPI_WARPS = 8;                       // CTA-pair kernel: two epilogue warps per TMEM lane quadrant
+constexpr int PAIR_THREADS = 64 + 32 * PAIR_EPI_WARPS;   // 320
 constexpr int EPI_COLS = 64;   // columns per epilogue pass
 constexpr int EPI_LD = 64;     // row of the per-warp transpose buffer (fp32 words; XOR-swizzled chunks instead of padding)
 
@@ -544,16 +546,19 @@ struct PairLayout {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN_CTA * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = 6;
+    // The epilogue paces this kernel at the model's shapes (K = 768: 3.5 us of MMA per 128 x 256 tile against 6-9 us of
+    // epilogue with four warps, profiles/gemm_timeline_r1f.txt), so the shared memory of one pipeline stage goes to the
+    // transpose buffers of a second set of four epilogue warps: 5 stages still cover the TMA round trip at 0.3 us per stage.
+    static constexpr int STAGES = 5;
     static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+    static constexpr int EPI_BYTES = PAIR_EPI_WARPS * 32 * EPI_LD * 4;
     static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
     static constexpr int TMEM_COLS = 2 * BN_TILE;       // 512: two accumulator buffers
 };
 
 template <bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
 gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                        const GemmDev p) {
@@ -584,7 +589,7 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), 1);
-            mbar_init(tempty_bar(b), 8);
+            mbar_init(tempty_bar(b), 2 * PAIR_EPI_WARPS);   // one arrive per epilogue warp of both CTAs
         }
         fence_barrier_init();
     }
@@ -689,8 +694,13 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
         }
     } else {
-        // ===================== epilogue (4 warps in each CTA) =====================
+        // ===================== epilogue (8 warps in each CTA) =====================
+        // warp w reads TMEM lanes 32 (w % 4) .. +31 (hardware rule); warps 2-5 take the first half of the tile's column
+        // passes, warps 6-9 the second half
         const int quad = warp & 3;
+        const int chalf = (warp - 2) >> 2;
+        constexpr int PASSES = L::BN_TILE / EPI_COLS / 2;       // column passes per warp
+        const int c_first = chalf * PASSES;
         float* stg = reinterpret_cast<float*>(smem_gen + L::EPI_OFFSET) + (warp - 2) * 32 * EPI_LD;
         int it = 0;
         for (int t = pair; t < num_tiles; t += npairs) {
@@ -704,18 +714,18 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const int nrows = min(32, p.M - row0);
             const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * L::BN_TILE);
             EpiIn<EPI> cur;
-            cur.load(p, row0, nrows, n0, lane);
+            cur.load(p, row0, nrows, n0 + c_first * EPI_COLS, lane);
             mbar_wait(tfull_bar(ab), aph);
             tc_fence_after();
             if (it == 1 && warp == 2 && lane == 0) stamp(p, ST_CLK_TFULL0);
 #pragma unroll 1
-            for (int c = 0; c < L::BN_TILE / EPI_COLS; ++c) {
-                if (c > 0) cur.load(p, row0, nrows, n0 + c * EPI_COLS, lane);
+            for (int c = c_first; c < c_first + PASSES; ++c) {
+                if (c > c_first) cur.load(p, row0, nrows, n0 + c * EPI_COLS, lane);
                 uint32_t r[EPI_COLS];
                 tmem_ld32(tacc + (uint32_t)(c * EPI_COLS), r);
                 tmem_ld32(tacc + (uint32_t)(c * EPI_COLS + 32), r + 32);
                 tmem_ld_wait();
-                if (c == L::BN_TILE / EPI_COLS - 1) {
+                if (c == c_first + PASSES - 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(tempty_bar(ab));

@@ -244,7 +244,7 @@ int gemm_plan_launch(const GemmPlan* p, cudaStream_t stream, const DropCfg* drop
         if (g_timeline) dev.prof = timeline_slot();
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = p->grid;
-        cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+        cfg.blockDim = dim3(PAIR_THREADS, 1, 1);
         cfg.dynamicSmemBytes = (size_t)p->smem;
         cfg.stream = stream;
         cudaLaunchAttribute attr[2];
