@@ -439,6 +439,41 @@ def test_async_host_step_equals_sync_host_step():
     assert d.max().item() <= 2 * 3 * 1e-3 + 1e-6 and d.mean().item() <= 2e-5
 
 
+def test_evaluation_epoch_hits_match_oracle():
+    """An evaluation epoch through MartTrainer (fused [MASK]-row head + rank kernel, ragged last batch) gives the ranks and the
+    Hits@k / MRR of the CPU oracle (transformer.py:115-193) on every sample whose top-1 margin exceeds the logit error —
+    i.e. Hits@1 is exact on the synthetic split wherever it is decidable in bf16."""
+    from mkg_analogy_b200.config import TINY
+    from mkg_analogy_b200.metrics import epoch_metrics, evaluate
+    from mkg_analogy_b200.trainer import MartTrainer
+    from oracle import mkgformer_oracle as O
+    params = init_params(TINY, 11)
+    tr = MartTrainer(TINY, TINY_VOCAB, total_steps=20, dropout=False)
+    tr.engine.load(params)
+    host = [make_finetune_batch(n, 24, TINY.image_size, TINY_VOCAB, seed=80 + i, min_len=16) for i, n in enumerate((4, 4, 3))]
+    dev = [to_cuda(b) for b in host]
+    metrics, ranks = evaluate(tr, dev)
+    torch.cuda.synchronize()
+    assert ranks.shape == (11,) and tr.engine.status() == 0
+    ref_ranks, stable, mine = [], [], []
+    for b, d in zip(host, dev):
+        r, ml, _ = tr.eval_step(d)
+        mine.append(r.reshape(-1).cpu())
+        with torch.no_grad():
+            _, x, _ = O.finetune_loss(params, TINY, b, TINY_VOCAB.analogy_entity_ids(), alpha=0.43, label_smoothing=0.1)
+        ref_ranks.append(O.ranks_of_gold(x, b["label"]))
+        err = (ml.cpu() - x).abs().max().item()
+        gold = x.gather(1, b["label"][:, None])
+        stable.append(((x - gold).abs() > 2 * err).sum(1) >= x.shape[1] - 1)
+    ref_ranks, stable, mine = torch.cat(ref_ranks), torch.cat(stable), torch.cat(mine)
+    assert torch.equal(ranks.cpu(), mine)                      # the epoch loop concatenates the per-batch ranks in order
+    assert torch.equal(mine[stable], ref_ranks[stable])
+    if bool(stable.all()):
+        assert metrics == epoch_metrics(ref_ranks)
+    assert set(metrics) == {f"Eval_entity/{k}" for k in ("hits1", "hits3", "hits5", "hits10", "hits20", "mean_rank", "mrr")}
+    assert 0.0 <= metrics["Eval_entity/hits1"] <= metrics["Eval_entity/hits20"] <= 1.0
+
+
 def test_bad_indices_flag_status_instead_of_faulting(tiny):
     """Out-of-range labels / relaxation positions / token ids set status bits (the reference raises IndexError)."""
     g, cfg, params, eng, batch = tiny
