@@ -298,6 +298,14 @@ int32_t b200mart_layernorm_bwd(const float* dy, const float* x, const float* mea
 int32_t b200mart_ls_ce(const float* logits, int32_t B, int32_t C, const int64_t* label, float eps, float* loss,
                        float* dlogits, void* stream);
 
+/* Input path.  Replaces the image half of the reference collator, MarT/data/data_module.py:127-160
+ * (`entity2visual_features[entities.index(name)]` per sample on the host, then a 38.5 MB host -> device copy per 32-example
+ * batch): the preprocessed entity images live on the device once (`table`: (n_entities, image_elems) fp32 or bf16) and a batch's
+ * pixel_values (n_images = 2 B images of image_elems = 3 S S floats) are gathered by entity index; idx < 0 = the all-zero
+ * "[PAD] image" (:141-142, :152-153).  idx >= n_entities sets bit 16 of *status (may be NULL) and yields zeros. */
+int32_t b200mart_gather_images(const void* table, int32_t table_is_bf16, const int64_t* idx, float* out, int32_t n_images,
+                               int64_t image_elems, int64_t n_entities, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -131,6 +131,7 @@ SYMBOLS = {
     "b200mart_layernorm_fwd": (i32, [vp, vp, vp, f32, vp, vp, vp, vp, i32, i32, vp]),
     "b200mart_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
     "b200mart_ls_ce": (i32, [vp, i32, i32, vp, f32, vp, vp, vp]),
+    "b200mart_gather_images": (i32, [vp, i32, vp, vp, i32, i64, i64, vp, vp]),
 }
 
 _lib = None

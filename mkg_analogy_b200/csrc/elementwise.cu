@@ -438,6 +438,35 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
     }
 }
 
+// ---------------------------------------------------------------- entity-image table gather (collator replacement)
+// out[i] = table[idx[i]] (one preprocessed image per entity, fp32 or bf16 storage), zeros for idx < 0 ("[PAD] image",
+// MarT/data/data_module.py:141-142).  One CTA row per image, 16-byte accesses; an index >= n_entities sets status bit 16
+// and yields zeros instead of faulting.
+template <typename T>
+__global__ void gather_images_kernel(const T* __restrict__ table, const int64_t* __restrict__ idx, float* __restrict__ out,
+                                     long image_elems, long n_entities, int* status) {
+    const int img = blockIdx.y;
+    const long e = idx[img];
+    const bool ok = e >= 0 && e < n_entities;
+    if (e >= n_entities && status && threadIdx.x == 0 && blockIdx.x == 0) atomicOr(status, 16);
+    const T* src = table + (ok ? e : 0) * image_elems;
+    float* dst = out + (long)img * image_elems;
+    for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < image_elems; i += (long)gridDim.x * blockDim.x * 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+            if (sizeof(T) == 4) {
+                v = ld4(reinterpret_cast<const float*>(src) + i);
+            } else {
+                const uint2 q = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(src) + i);
+                const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+                const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+                v = make_float4(a.x, a.y, b.x, b.y);
+            }
+        }
+        st4(dst + i, v);
+    }
+}
+
 inline int blocks_for(long n, int per_block, int cap = 148 * 16) {
     long b = (n + per_block - 1) / per_block;
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
@@ -584,6 +613,19 @@ int launch_adamw(float* p, float* g, float* m, float* v, bf16* p16, const AdamSe
     const long blocks = (end - begin + 4095) / 4096;
     adamw_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, g, m, v, p16, segs_dev, nseg, begin, end, zero_grads, lr, b1, b2, eps, wd,
                                                   bc1, bc2);
+    B2_LAUNCHED();
+    return 0;
+}
+int launch_gather_images(const void* table, int table_is_bf16, const int64_t* idx, float* out, int n_images, long image_elems,
+                         long n_entities, int* status, cudaStream_t s) {
+    B2_CHECK(table && idx && out && n_images > 0 && image_elems > 0 && n_entities > 0, "gather_images: bad arguments");
+    B2_CHECK(image_elems % 4 == 0, "gather_images: image size %ld must be a multiple of 4 elements", image_elems);
+    B2_CHECK(((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "gather_images: table / out must be 16-byte aligned");
+    long per = (image_elems / 4 + 255) / 256;
+    if (per > 64) per = 64;
+    const dim3 grid((unsigned)per, (unsigned)n_images);
+    if (table_is_bf16) gather_images_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(table), idx, out, image_elems, n_entities, status);
+    else gather_images_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(table), idx, out, image_elems, n_entities, status);
     B2_LAUNCHED();
     return 0;
 }

@@ -49,7 +49,11 @@ struct AdamSeg { long begin, end; int decay; int skip; };
 int launch_adamw(float* p, float* g, float* m, float* v, bf16* p16, const AdamSeg* segs_dev, int nseg, long begin, long end,
                  int zero_grads, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, cudaStream_t s);
 
-// ---- attention_mma.cu (self-attention) / attention.cu (fusion)
+// entity-image table gather (collator replacement, MarT/data/data_module.py:127-160): out[i] = table[idx[i]], zeros for idx < 0
+int launch_gather_images(const void* table, int table_is_bf16, const int64_t* idx, float* out, int n_images, long image_elems,
+                         long n_entities, int* status, cudaStream_t s);
+
+// ---- attention_mma.cu (self-attention) / fusion.cu (BertFusion)
 struct AttnFwd {
     DropCfg drop;                 // dropout on the attention probabilities (thresh 0 = off); element ((b*nh+h)*Lq+r)*n+c
     // Q rows: [B*Lq] rows of q (ldq), head h at column h*64. Keys: optional prefix source (n1 keys per sample) then own (n2).

@@ -1324,3 +1324,8 @@ extern "C" int32_t b200mart_ls_ce(const float* logits, int32_t B, int32_t C, con
     g.logits = logits; g.ld = C; g.C = C; g.dlogits32 = dlogits; g.ldd = C; g.select = 0;
     return launch_ls_ce(g, label, nullptr, eps, loss, B, nullptr, (cudaStream_t)stream);
 }
+
+extern "C" int32_t b200mart_gather_images(const void* table, int32_t table_is_bf16, const int64_t* idx, float* out, int32_t n_images,
+                                          int64_t image_elems, int64_t n_entities, int32_t* status, void* stream) {
+    return launch_gather_images(table, table_is_bf16, idx, out, n_images, (long)image_elems, (long)n_entities, status, (cudaStream_t)stream);
+}

@@ -160,3 +160,70 @@ def make_pretrain_batch(B, L, image_size=224, vocab: VocabLayout = MARS_VOCAB, s
     px[torch.rand(B, generator=g) < 0.4, 1] = 0.0
     return {"input_ids": ids, "attention_mask": att, "token_type_ids": tt, "pixel_values": px,
             "label": label, "pre_type": pre_type}
+
+
+class EntityImageTable:
+    """GPU-resident replacement of the image half of the reference collator.
+
+    Reference (MarT/data/data_module.py:127-160, MKGformer branch): for every sample the collator looks the head / tail
+    entity up with `entities.index(name)` (a linear scan of an ~11 k-element list, twice per sample), stacks the two
+    (3, S, S) fp32 feature tensors on the host — an all-zero "[PAD] image" for a missing entity — and the batch's
+    (B, 2, 3, S, S) pixel_values (38.5 MB at B = 32, S = 224) cross PCIe every step.  Here the table is uploaded once
+    (fp32, or bf16 to halve its 6.8 GB), names resolve through a dict, and a batch's pixel_values are gathered on the
+    device by `b200mart_gather_images` from a (B, 2) index tensor (-1 = zero image): 512 bytes per step instead of 38.5 MB.
+    """
+
+    def __init__(self, features, entities, device=None, dtype=torch.float32):
+        if features.dim() != 4 or features.shape[0] != len(entities):
+            raise ValueError("features must be (n_entities, C, S, S) with one row per entity name")
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("table dtype must be float32 or bfloat16")
+        self.image_shape = tuple(features.shape[1:])
+        self.n_entities = features.shape[0]
+        # first occurrence wins, like list.index (data_module.py:131-132)
+        self.index = {}
+        for i, name in enumerate(entities):
+            self.index.setdefault(name, i)
+        self.device = torch.device(device) if device is not None else None
+        self.table = features.to(device=self.device, dtype=dtype).contiguous() if self.device is not None else features.to(dtype).contiguous()
+
+    def indices(self, head_ent, tail_ent):
+        """(B, 2) int64 entity rows of the two images of every sample, -1 = all-zero image; the branch structure of
+        data_module.py:127-154: both entities given -> (head, tail); otherwise the one that is not None (head first),
+        or a zero image when that one is empty, followed by a zero image."""
+        rows = []
+        for head, tail in zip(head_ent, tail_ent):
+            if head and tail:
+                rows.append((self._row(head), self._row(tail)))
+            else:
+                entity = head if head is not None else tail
+                rows.append((self._row(entity) if entity else -1, -1))
+        return torch.tensor(rows, dtype=torch.int64).reshape(-1, 2)
+
+    def _row(self, name):
+        try:
+            return self.index[name]
+        except KeyError:
+            raise ValueError(f"{name!r} is not in list") from None      # what entities.index(name) raises
+
+    def gather(self, idx, out=None):
+        """pixel_values (B, 2, C, S, S) fp32 on the table's device for a (B, 2) int64 index tensor on that device."""
+        from . import _lib
+        if self.device is None or self.device.type != "cuda":
+            raise _lib.B200MartError("EntityImageTable.gather needs the table on a CUDA device (no CPU fallback)")
+        idx = idx.to(device=self.device, dtype=torch.int64).contiguous()
+        n = idx.numel()
+        if out is None:
+            out = torch.empty((idx.shape[0], 2) + self.image_shape, device=self.device, dtype=torch.float32)
+        elems = 1
+        for d in self.image_shape:
+            elems *= d
+        status = torch.zeros(1, device=self.device, dtype=torch.int32)
+        _lib.check(_lib.lib().b200mart_gather_images(self.table.data_ptr(), int(self.table.dtype == torch.bfloat16), idx.data_ptr(),
+                                                     out.data_ptr(), n, elems, self.n_entities, status.data_ptr(), _lib.cur_stream()))
+        self.last_status = status
+        return out
+
+    def collate_images(self, head_ent, tail_ent):
+        """pixel_values for a batch of (head, tail) entity names: host index lookup + device gather."""
+        return self.gather(self.indices(head_ent, tail_ent).to(self.device, non_blocking=True))

@@ -356,3 +356,24 @@ def linear_warmup_lr(step, total_steps, base_lr, warmup_ratio=0.1):
     if step < warm:
         return base_lr * float(step) / float(max(1, warm))
     return base_lr * max(0.0, float(total_steps - step) / float(max(1, total_steps - warm)))
+
+
+def collate_images(entity2visual_features, entities, head_ent, tail_ent):
+    """Image half of the reference collator, MarT/data/data_module.py:127-160 (tensor branch = MKGformer / FLAVA / ViLT):
+    per sample two (C, S, S) tensors — `entity2visual_features[entities.index(name)]`, or zeros for a missing entity —
+    stacked to (B, 2, C, S, S)."""
+    pixel_images = []
+    for head, tail in zip(head_ent, tail_ent):
+        pixel_image = []
+        if head and tail:                                            # :129-132
+            pixel_image.append(entity2visual_features[entities.index(head)])
+            pixel_image.append(entity2visual_features[entities.index(tail)])
+        else:                                                        # :138-145
+            entity = head if head is not None else tail
+            if entity:
+                pixel_image.append(entity2visual_features[entities.index(entity)])
+            else:
+                pixel_image.append(torch.zeros(entity2visual_features.shape[1:]))
+            pixel_image.append(torch.zeros(entity2visual_features.shape[1:]))
+        pixel_images.append(torch.stack(pixel_image))                # :156
+    return torch.stack(pixel_images)                                 # :161
