@@ -227,3 +227,65 @@ class EntityImageTable:
     def collate_images(self, head_ent, tail_ent):
         """pixel_values for a batch of (head, tail) entity names: host index lookup + device gather."""
         return self.gather(self.indices(head_ent, tail_ent).to(self.device, non_blocking=True))
+
+
+class MarsCollator:
+    """Batch assembly of the reference collator (`DataCollatorForSeq2Seq.__call__`, MarT/data/data_module.py:91-182) with the
+    image half served by an `EntityImageTable`.
+
+    Same output contract: the text fields right-padded to the longest sequence of the batch (`tokenizer.pad(padding=
+    "longest")`, :117-123), rounded up to `pad_to_multiple_of` (8 under `--precision 16`, :215), int64 tensors; `label`,
+    `pre_type`, `rel_idx`, `sep_idx`, `rel_label`, `q_head_idx`, `a_head_idx` as int64 tensors when present (:162-178);
+    any other per-sample field passed through as a list (:107-110, :180); keys in the reference's order.  Differences, on
+    purpose: the caller's feature dicts are not mutated (the reference pops from them); tensors can be allocated in pinned
+    memory (`pin_memory=True`; the reference's DataLoader uses pin_memory=False, :268) so that the host -> device copy of the
+    few KB of ids is asynchronous; and `images="index"` returns `pixel_idx` (B, 2) int64 rows of the table (-1 = zero image)
+    instead of `pixel_values`, for `table.gather(batch.pop("pixel_idx"))` on the training device."""
+
+    TEXT_KEYS = ("input_ids", "attention_mask", "token_type_ids")
+    TENSOR_KEYS = ("pre_type", "rel_idx", "sep_idx", "rel_label", "q_head_idx", "a_head_idx")      # order of :164-178
+    POPPED = ("label", "rel_label", "head_ent", "tail_ent", "pre_type", "rel_idx", "sep_idx", "q_head_idx", "a_head_idx")
+
+    def __init__(self, image_table, pad_token_id=0, pad_token_type_id=0, pad_to_multiple_of=None, pin_memory=False, images="device"):
+        if images not in ("device", "index"):
+            raise ValueError("images must be 'device' or 'index'")
+        self.table, self.pad_token_id, self.pad_token_type_id = image_table, pad_token_id, pad_token_type_id
+        self.pad_to_multiple_of, self.pin_memory, self.images = pad_to_multiple_of, pin_memory, images
+
+    def _tensor(self, rows):
+        t = torch.tensor(rows, dtype=torch.int64)
+        return t.pin_memory() if self.pin_memory else t
+
+    def __call__(self, features):
+        first = features[0]
+        col = {k: [f[k] for f in features] for k in self.POPPED if k in first}
+        extra = {k: [f[k] for f in features] for k in first if k not in self.TEXT_KEYS and k not in self.POPPED}
+        # ---- text: right-pad to the longest, rounded up to the multiple
+        longest = max(len(f["input_ids"]) for f in features)
+        m = self.pad_to_multiple_of
+        if m is not None and longest % m != 0:
+            longest = (longest // m + 1) * m
+        out = {}
+        text_keys = [k for k in first if k in self.TEXT_KEYS]
+        if "attention_mask" not in text_keys:
+            text_keys.insert(1, "attention_mask")               # tokenizer.pad creates it for BERT-family tokenizers
+        fill = {"input_ids": self.pad_token_id, "attention_mask": 0, "token_type_ids": self.pad_token_type_id}
+        for k in text_keys:
+            rows = []
+            for f in features:
+                seq = list(f[k]) if k in f else [1] * len(f["input_ids"])
+                rows.append(seq + [fill[k]] * (longest - len(seq)))
+            out[k] = self._tensor(rows)
+        # ---- images
+        idx = self.table.indices(col.get("head_ent", [None] * len(features)), col.get("tail_ent", [None] * len(features)))
+        if self.images == "index":
+            out["pixel_idx"] = idx.pin_memory() if self.pin_memory else idx
+        else:
+            out["pixel_values"] = self.table.gather(idx.to(self.table.device, non_blocking=True))
+        # ---- index / label tensors, then pass-through lists
+        out["label"] = self._tensor(col["label"])
+        for k in self.TENSOR_KEYS:
+            if col.get(k):
+                out[k] = self._tensor(col[k])
+        out.update(extra)
+        return out

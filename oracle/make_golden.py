@@ -256,8 +256,61 @@ def flava_case():
                 grads={n: prm[n].grad.clone() for n in names}, unused=unused)
 
 
+def collator_features(seed, n, pretrain):
+    """Synthetic per-sample features of the shape `get_dataset` hands the collator (processor.py): ragged token lists plus
+    the scalar / list fields the collator pops (data_module.py:96-105)."""
+    import random
+    rng = random.Random(seed)
+    ents = [f"Q{i}" for i in range(7)]
+    feats = []
+    for i in range(n):
+        ln = rng.randint(9, 29)
+        f = dict(input_ids=[2] + [rng.randint(5, 60) for _ in range(ln - 2)] + [3], attention_mask=[1] * ln, token_type_ids=[0] * ln,
+                 label=rng.randint(0, 6))
+        mode = i % 4
+        f["head_ent"] = ents[rng.randint(0, 6)] if mode in (0, 1) else (None if mode == 2 else "")
+        f["tail_ent"] = ents[rng.randint(0, 6)] if mode in (0, 2) else (None if mode == 1 else ents[rng.randint(0, 6)])
+        if pretrain:
+            f["pre_type"] = rng.randint(0, 2)
+            f["rel_label"] = rng.randint(0, 5)
+        else:
+            f["rel_idx"] = [rng.randint(1, 3), rng.randint(4, 6)]
+            f["sep_idx"] = sorted(rng.sample(range(1, ln), 6))
+            f["q_head_idx"] = 1
+            f["a_head_idx"] = rng.randint(2, ln - 1)
+        feats.append(f)
+    return feats
+
+
+def collator_case():
+    """Outputs of the reference collator itself (DataCollatorForSeq2Seq.__call__, data_module.py:91-182) on synthetic features:
+    fine-tune and pre-train field sets, with and without pad_to_multiple_of = 8 (`--precision 16`, :215)."""
+    import copy
+    import tempfile
+    DM = RL.load_collator()
+    tok = RL.make_bert_tokenizer(tempfile.mkdtemp())
+    ents = [f"Q{i}" for i in range(7)]
+    feats_img = torch.randn(7, 3, 8, 8, generator=torch.Generator().manual_seed(5))
+    DM.entities = ents
+    DM.entity2visual_features = feats_img
+    cases = {}
+    for tag, pretrain, mult, n in (("finetune", False, None, 6), ("finetune_mult8", False, 8, 5), ("pretrain", True, None, 4),
+                                   ("single", False, 8, 1)):
+        feats = collator_features(17 + len(cases), n, pretrain)
+        coll = DM.DataCollatorForSeq2Seq(tok, model=None, label_pad_token_id=tok.pad_token_id, pad_to_multiple_of=mult,
+                                         padding="longest", max_length=128, num_labels=len(ents))
+        out = coll(copy.deepcopy(feats))
+        cases[tag] = dict(features=feats, pad_to_multiple_of=mult, out={k: v.clone() for k, v in out.items()}, keys=list(out.keys()))
+    return dict(entities=ents, image_features=feats_img, pad_token_id=tok.pad_token_id, cases=cases)
+
+
 if __name__ == "__main__":
     assert RL.available(), "reference tree not found"
+    if "--collator" in sys.argv:     # only the collator fixture (the model fixtures are left untouched)
+        os.makedirs(GOLD, exist_ok=True)
+        torch.save(collator_case(), os.path.join(GOLD, "collator.pt"))
+        print("collator.pt", os.path.getsize(os.path.join(GOLD, "collator.pt")))
+        sys.exit(0)
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     torch.save(tiny_case(), os.path.join(GOLD, "mkgformer_tiny.pt"))
@@ -265,5 +318,6 @@ if __name__ == "__main__":
     torch.save(stack_case(), os.path.join(GOLD, "preln_stack.pt"))
     torch.save(vilt_case(), os.path.join(GOLD, "vilt_tiny.pt"))
     torch.save(flava_case(), os.path.join(GOLD, "flava_tiny.pt"))
+    torch.save(collator_case(), os.path.join(GOLD, "collator.pt"))
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))

@@ -151,3 +151,33 @@ def build_reference_lit(model, vocab_layout, alpha=0.43, label_smoothing=0.1, pr
                        relation_id_st=vocab_layout.relation_id_st, relation_id_ed=vocab_layout.relation_id_ed)
     lit = T.TransformerLitModel(model=model, args=args, tokenizer=tok, data_config=data_config)
     return lit
+
+
+def load_collator():
+    """The reference's data package imported in place (as `ref_data`), for its collator `DataCollatorForSeq2Seq`
+    (MarT/data/data_module.py:46-182).  The collator reads the module globals `entities` / `entity2visual_features`
+    (set by KGC.__init__, :195-209): callers assign them on the returned module."""
+    _install_shims()
+    pl = sys.modules["pytorch_lightning"]
+    if not hasattr(pl, "LightningDataModule"):
+        class _DM:
+            def __init__(self, *a, **k):
+                pass
+        pl.LightningDataModule = _DM
+    if "ref_data" not in sys.modules:
+        root = os.path.join(REF_ROOT, "data")
+        spec = importlib.util.spec_from_file_location("ref_data", os.path.join(root, "__init__.py"), submodule_search_locations=[root])
+        pkg = importlib.util.module_from_spec(spec)
+        sys.modules["ref_data"] = pkg
+        spec.loader.exec_module(pkg)
+    return sys.modules["ref_data.data_module"]
+
+
+def make_bert_tokenizer(tmpdir, n_words=60):
+    """A real HF BertTokenizer over a tiny vocabulary ([PAD] = 0, [MASK] = 4): supplies the genuine `tokenizer.pad`
+    the reference collator calls (data_module.py:117-123)."""
+    from transformers import BertTokenizer
+    path = os.path.join(tmpdir, "vocab.txt")
+    with open(path, "w") as f:
+        f.write("\n".join(["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + [f"w{i}" for i in range(n_words)]))
+    return BertTokenizer(path)
