@@ -133,7 +133,14 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
         // B200MART_GEMM_PAIR=0 switches it off (A/B runs).
         static int pref = -1;
         if (pref < 0) { const char* e = getenv("B200MART_GEMM_PAIR"); pref = e ? atoi(e) : 1; }
-        if (pref && op.bn == 0 && op.N >= 512 && op.M >= 512 && gemm_pick_kernel_pair(op.a_mn, op.b_mn, epi) != nullptr) bn = 512;
+        // B200MART_GEMM_SMALLN=n (default 0 = off, A/B switch for the next tuning step): products with N <= n keep the single-CTA
+        // kernel and the tile the cost model picked (128 x 128 at N = 768: 96-150 CTAs instead of 48-78).  Their epilogue is bound by
+        // the memory system (profiles/gemm_timeline_r1g.txt: 5.8-7.4 us for a 128 x 256 RES tile per CTA at ~56 GB/s per SM), so
+        // spreading it over twice the SMs may beat the pair kernel's lower operand traffic.
+        static int smalln = -1;
+        if (smalln < 0) { const char* e = getenv("B200MART_GEMM_SMALLN"); smalln = e ? atoi(e) : 0; }
+        const bool keep_single = smalln > 0 && op.N <= smalln && op.split_k == 1;
+        if (pref && !keep_single && op.bn == 0 && op.N >= 512 && op.M >= 512 && gemm_pick_kernel_pair(op.a_mn, op.b_mn, epi) != nullptr) bn = 512;
     }
     B2_CHECK(bn == 64 || bn == 128 || bn == 256 || bn == 512, "gemm: unsupported N tile %d (64, 128, 256, or 512 = 256x256 CTA pair)", bn);
     const bool pair = (bn == 512);
