@@ -108,6 +108,8 @@ class MartTrainer:
         self._comm_stream = self._layer_events = None
         self._grads_clean = False
         if self.overlap_comm:
+            import os
+            self._tail_chunks = max(1, int(os.environ.get("B200MART_TAIL_CHUNKS", "1")))
             self._comm_stream = torch.cuda.Stream(device=self.device)
             self._update_stream = torch.cuda.Stream(device=self.device)
             self._layer_events = [torch.cuda.Event() for _ in range(2 * cfg.layers)]
@@ -176,10 +178,12 @@ class MartTrainer:
                 finish(*self._extents[i])
             comm.wait_stream(main)               # the whole backward (embeddings included) is ordered before this point
             lo, hi = self._extents[0][0], self._extents[-1][1]
-            if lo > 0:
-                finish(0, lo)
-            if hi < g.numel():
-                finish(hi, g.numel())
+            # B200MART_TAIL_CHUNKS=n (default 1): the embedding / head extents, which only become final at the end of backward,
+            # go in n pieces so that (N > 1) the exchange of piece k+1 overlaps the update of piece k
+            for b0, e0 in ((0, lo), (hi, g.numel())):
+                if e0 > b0:
+                    for b, e in bucket_bounds(e0 - b0, self._tail_chunks):
+                        finish(b0 + b, b0 + e)
         if upd is not comm:
             main.wait_stream(upd)
         main.wait_stream(comm)
