@@ -277,6 +277,19 @@ class MartTrainer:
         loss, logits, ranks = eng.head_loss(mb, self._head(batch), compute_grad=False, want_logits=True, want_ranks=True)
         return ranks, logits, loss
 
+    # ------------------------------------------------------------------ checkpoints (reference layout, main.py:133-159)
+    def save_checkpoint(self, path):
+        """`{"state_dict": {"model." + name: tensor}}` as the reference's ModelCheckpoint(save_weights_only=True) writes it."""
+        from .checkpoint import save_checkpoint
+        torch.cuda.synchronize(self.device)
+        save_checkpoint(self.engine, path, global_step=self.steps_done)
+
+    def load_checkpoint(self, path, strict=False):
+        """main.py:134: load_state_dict(torch.load(path)["state_dict"], strict=False). Returns (missing, unexpected)."""
+        from .checkpoint import load_checkpoint
+        torch.cuda.synchronize(self.device)
+        return load_checkpoint(self.engine, path, strict=strict)
+
     @staticmethod
     def h2d_bytes(host_batch):
         return int(sum(v.numel() * v.element_size() for k, v in host_batch.items() if k in BATCH_KEYS))
