@@ -1141,6 +1141,7 @@ extern "C" int32_t b200mart_stack_create(const b200mart_stack_desc* desc, b200ma
              "stack: hidden %d must be heads * 64, a multiple of 128 and <= 1024", d.hidden);
     B2_CHECK(d.intermediate % 64 == 0 && d.layers > 0 && (d.act == 1 || d.act == 2), "stack: bad intermediate / layers / act");
     b200mart_stack* st = new b200mart_stack();
+    st->core.split_streams = false;     // one stream: nothing to share the SMs with, weight-gradient GEMMs use the whole machine
     st->d = d;
     b200mart_handle* h = &st->core;
     const long H = d.hidden, F = d.intermediate;
