@@ -166,6 +166,9 @@ typedef struct b200mart_head {
     const int64_t* a_head_idx;   /* (B) */
     float label_smoothing, alpha;
     int32_t mask_token_id;
+    const float* grad_scale;     /* device scalar multiplying every gradient this call seeds (NULL = 1): the incoming
+                                  * d(loss) of `loss.backward()` under loss scaling / gradient accumulation, read on the
+                                  * device so that no host synchronisation is needed; the returned loss is unscaled */
 } b200mart_head;
 
 int32_t b200mart_head_loss(b200mart_handle* h, const b200mart_buffers* bufs, const b200mart_batch* batch,

@@ -60,7 +60,7 @@ class Head(C.Structure):
     _fields_ = [("mode", i32), ("col_ids", vp), ("n_cols", i32),
                 ("ent_st", i32), ("ent_ed", i32), ("rel_st", i32), ("rel_ed", i32),
                 ("label", vp), ("pre_type", vp), ("rel_idx", vp), ("q_head_idx", vp), ("a_head_idx", vp),
-                ("label_smoothing", f32), ("alpha", f32), ("mask_token_id", i32)]
+                ("label_smoothing", f32), ("alpha", f32), ("mask_token_id", i32), ("grad_scale", vp)]
 
 
 class StackDesc(C.Structure):

@@ -33,7 +33,8 @@ def lightning_state_dict(engine, max_position=None, n_vision_positions=None):
 def save_checkpoint(engine, path, **extra):
     """Write a file `main.py:134` can restore (`extra` keys, e.g. epoch / global_step, are stored next to "state_dict")."""
     blob = dict(extra)
-    blob["state_dict"] = lightning_state_dict(engine)
+    # the full reference key set, position_ids buffers included, so that a strict load (main.py:159) succeeds
+    blob["state_dict"] = lightning_state_dict(engine, max_position=engine.cfg.max_position, n_vision_positions=engine.cfg.patches + 1)
     torch.save(blob, path)
 
 

@@ -249,6 +249,25 @@ __device__ __forceinline__ void stage_keys(const AttnFwd& a, int b, int h, bf16*
     }
 }
 
+// partial row sums of P_ij * mult_ij * dP_ij over one 16 x 64 chunk (s = raw QK^T accumulators, dp = dO V^T accumulators):
+// the softmax-backward delta that is consistent with the dP values the caller goes on to use
+__device__ __forceinline__ void consistent_delta(const AttnFwd& a, const Adapt& ad, const float (&s)[8][4], const float (&dp)[8][4],
+                                                 const float* madd, const float (&lse)[2], int kc, int r0, int g, int t, int n1, int n,
+                                                 int Lq, int b, int h, float (&acc)[2]) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int col = kc + nt * 8 + 2 * t + (e & 1);
+            const int row = r0 + g + 8 * (e >> 1);
+            const float f = afactor(ad, row, col - n1);
+            float p = (row < Lq) ? __expf(s[nt][e] * a.scale * f + madd[col] - lse[e >> 1]) : 0.f;
+            if (a.drop.thresh) p *= drop_mult(a.drop, (uint32_t)((((long)b * a.nh + h) * Lq + row) * n + col));
+            acc[e >> 1] = fmaf(p, dp[nt][e], acc[e >> 1]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(WARPS * 32)
 attn_fwd_mma(const AttnFwd a, float* __restrict__ out32) {
@@ -370,6 +389,26 @@ attn_bwd_rows_mma(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx, fl
             const int row = r0 + g + 8 * hh;
             lse[hh] = (row < a.Lq) ? a.lse[((long)b * a.nh + h) * a.Lq + row] : 0.f;
             if (t == 0 && row < a.Lq) delta[((long)b * a.nh + h) * a.Lq + row] = dl[hh];
+        }
+        if (ad.split >= 0) {   // adaptive scaling: delta consistent with this kernel's own dP (see attn_bwd_fused); the keys pass reads it
+            float acc[2] = {0.f, 0.f};
+            for (int kc = 0; kc < n_pad; kc += 64) {
+                float s[8][4], dp[8][4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+                    dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+                }
+                mma_a_bt(s, qa, Ks, kc, lane);
+                mma_a_bt(dp, doa, Vs, kc, lane);
+                consistent_delta(a, ad, s, dp, madd, lse, kc, r0, g, t, n1, n, a.Lq, b, h, acc);
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                dl[hh] = quad_sum(acc[hh]);
+                const int row = r0 + g + 8 * hh;
+                if (t == 0 && row < a.Lq) delta[((long)b * a.nh + h) * a.Lq + row] = dl[hh];
+            }
         }
         float dq[8][4];
 #pragma unroll
@@ -613,6 +652,26 @@ attn_bwd_fused(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx) {
         float dq[8][4];
 #pragma unroll
         for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+        // Adaptive scaling: dW0 / dW1 = sum dS * S_raw is a heavily cancelling sum (sum_j dS_ij = 0 in exact arithmetic), so
+        // delta must be CONSISTENT with the dP this kernel computes (bf16 dO, bf16 V): delta_i = sum_j P_ij dP_ij from the same
+        // registers, not rowsum(dO * O) with its independently rounded O - otherwise (delta error) x (row mean of S_raw) leaks
+        // into the two scalars.  More than one key chunk: a pre-pass over the chunks; one chunk: from the chunk's own registers.
+        const bool adaptive = ad.split >= 0;
+        if (adaptive && n_pad > 64) {
+            float acc[2] = {0.f, 0.f};
+            for (int kc = 0; kc < n_pad; kc += 64) {
+                float s[8][4], dp[8][4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+                    dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+                }
+                mma_a_bt(s, qa, Ks, kc, lane);
+                mma_a_bt(dp, doa, Vs, kc, lane);
+                consistent_delta(a, ad, s, dp, madd, lse, kc, r0, g, t, n1, n, Lq, b, h, acc);
+            }
+            dl[0] = quad_sum(acc[0]); dl[1] = quad_sum(acc[1]);
+        }
         for (int kc = 0; kc < n_pad; kc += 64) {
             float s[8][4], dp[8][4];
 #pragma unroll
@@ -622,6 +681,11 @@ attn_bwd_fused(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx) {
             }
             mma_a_bt(s, qa, Ks, kc, lane);
             mma_a_bt(dp, doa, Vs, kc, lane);
+            if (adaptive && n_pad <= 64) {
+                float acc[2] = {0.f, 0.f};
+                consistent_delta(a, ad, s, dp, madd, lse, kc, r0, g, t, n1, n, Lq, b, h, acc);
+                dl[0] = quad_sum(acc[0]); dl[1] = quad_sum(acc[1]);
+            }
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
                 float pd[4];

@@ -164,7 +164,7 @@ __global__ void text_embed_ln_kernel(const int64_t* __restrict__ ids, const int6
                                      const float* __restrict__ E, const float* __restrict__ pos,
                                      const float* __restrict__ type, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float eps, float* pre, float* out32, bf16* out16,
-                                     float* mean, float* rstd, int B, int L, int H, int V, int* status, DropCfg drop) {
+                                     float* mean, float* rstd, int B, int L, int H, int V, int TV, int* status, DropCfg drop) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= B * L) return;
@@ -172,7 +172,7 @@ __global__ void text_embed_ln_kernel(const int64_t* __restrict__ ids, const int6
     long id = ids[row];
     long ty = tt ? tt[row] : 0;
     if (id < 0 || id >= V) { if (lane == 0) atomicOr(status, 1); id = 0; }  // reference would raise IndexError
-    if (ty < 0 || ty > 1) { if (lane == 0) atomicOr(status, 2); ty = 0; }
+    if (ty < 0 || ty >= TV) { if (lane == 0) atomicOr(status, 2); ty = 0; }
     const int nv = H / 128;
     float4 v[MAXV];
 #pragma unroll
@@ -350,11 +350,14 @@ __global__ void mask_cast_colsum_kernel(const float* __restrict__ src, bf16* __r
 // ---------------------------------------------------------------- embedding backward
 __global__ void text_embed_bwd_kernel(const float* __restrict__ d, const int64_t* __restrict__ ids,
                                       const int64_t* __restrict__ tt, float* dE, float* dpos, float* dtype, int B, int L,
-                                      int H) {
+                                      int H, int V, int TV) {
     const int row = blockIdx.x;
     const int l = row % L;
-    const long id = ids[row];
-    const long ty = tt ? tt[row] : 0;
+    long id = ids[row];
+    long ty = tt ? tt[row] : 0;
+    // same clamp as the forward kernel (which raised the status bit): an out-of-range id must never index past the tables
+    if (id < 0 || id >= V) id = 0;
+    if (ty < 0 || ty >= TV) ty = 0;
     for (int c = threadIdx.x; c < H; c += blockDim.x) {
         const float v = d[(long)row * H + c];
         atomicAdd(dE + id * H + c, v);
@@ -378,24 +381,30 @@ __global__ void vision_embed_bwd_kernel(const float* __restrict__ dx0, float* dc
 }
 
 // ---------------------------------------------------------------- gathers / scatters
-__global__ void gather_rows_bf16_kernel(const bf16* __restrict__ src, const int64_t* __restrict__ idx, bf16* out, int R, int H) {
+// Row / element gathers and scatters by a caller-supplied index list (the analogy-entity columns of the score head): an index
+// outside [0, V) raises status bit 0 and reads row 0 (gathers) / is skipped (scatters) - never an out-of-bounds access.
+__global__ void gather_rows_bf16_kernel(const bf16* __restrict__ src, const int64_t* __restrict__ idx, bf16* out, int R, int H, long V,
+                                        int* status) {
     const int r = blockIdx.x;
-    const uint4* s = reinterpret_cast<const uint4*>(src + idx[r] * H);
+    long i = idx[r];
+    if (i < 0 || i >= V) { if (threadIdx.x == 0 && status) atomicOr(status, 1); i = 0; }
+    const uint4* s = reinterpret_cast<const uint4*>(src + i * H);
     uint4* o = reinterpret_cast<uint4*>(out + (long)r * H);
     for (int c = threadIdx.x; c < H / 8; c += blockDim.x) o[c] = s[c];
 }
-__global__ void gather_f32_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, float* out, int R) {
+__global__ void gather_f32_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, float* out, int R, long V) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < R) out[r] = src[idx[r]];
+    if (r < R) { const long i = idx[r]; out[r] = (i < 0 || i >= V) ? 0.f : src[i]; }
 }
-__global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, float* dst, int R, int H) {
+__global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, float* dst, int R, int H, long V) {
     const int r = blockIdx.x;
+    if (idx[r] < 0 || idx[r] >= V) return;
     const long o = idx[r] * H;
     for (int c = threadIdx.x; c < H; c += blockDim.x) atomicAdd(dst + o + c, src[(long)r * H + c]);
 }
-__global__ void scatter_add_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, float* dst, int R) {
+__global__ void scatter_add_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, float* dst, int R, long V) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < R) atomicAdd(dst + idx[r], src[r]);
+    if (r < R && idx[r] >= 0 && idx[r] < V) atomicAdd(dst + idx[r], src[r]);
 }
 
 // ---------------------------------------------------------------- AdamW (torch.optim.AdamW semantics)
@@ -519,10 +528,10 @@ int launch_vision_embed_ln(const float* patch_out, const float* cls, const float
 }
 int launch_text_embed_ln(const int64_t* ids, const int64_t* tt, const float* E, const float* pos, const float* type,
                          const float* gamma, const float* beta, float eps, float* pre, float* out_f32, bf16* out_bf16,
-                         float* mean, float* rstd, int B, int L, int H, int V, int* status, DropCfg drop, cudaStream_t s) {
+                         float* mean, float* rstd, int B, int L, int H, int V, int TV, int* status, DropCfg drop, cudaStream_t s) {
     B2_TRY(check_h(H));
     text_embed_ln_kernel<<<(B * L + 3) / 4, 128, 0, s>>>(ids, tt, E, pos, type, gamma, beta, eps, pre, out_f32, out_bf16,
-                                                        mean, rstd, B, L, H, V, status, drop);
+                                                        mean, rstd, B, L, H, V, TV, status, drop);
     B2_LAUNCHED();
     return 0;
 }
@@ -575,8 +584,8 @@ int launch_mask_cast_colsum(const float* src, bf16* dst, float* colsum, int M, i
     return 0;
 }
 int launch_text_embed_bwd(const float* d, const int64_t* ids, const int64_t* tt, float* dE, float* dpos, float* dtype,
-                          int B, int L, int H, cudaStream_t s) {
-    text_embed_bwd_kernel<<<B * L, 256, 0, s>>>(d, ids, tt, dE, dpos, dtype, B, L, H);
+                          int B, int L, int H, int V, int TV, cudaStream_t s) {
+    text_embed_bwd_kernel<<<B * L, 256, 0, s>>>(d, ids, tt, dE, dpos, dtype, B, L, H, V, TV);
     B2_LAUNCHED();
     return 0;
 }
@@ -586,24 +595,24 @@ int launch_vision_embed_bwd(const float* dx0, float* dcls, float* dpos, bf16* dp
     B2_LAUNCHED();
     return 0;
 }
-int launch_gather_rows_bf16(const bf16* src, const int64_t* idx, bf16* out, int R, int H, cudaStream_t s) {
+int launch_gather_rows_bf16(const bf16* src, const int64_t* idx, bf16* out, int R, int H, long V, int* status, cudaStream_t s) {
     B2_CHECK(H % 8 == 0, "gather_rows: H %d must be a multiple of 8", H);
-    gather_rows_bf16_kernel<<<R, 96, 0, s>>>(src, idx, out, R, H);
+    gather_rows_bf16_kernel<<<R, 96, 0, s>>>(src, idx, out, R, H, V, status);
     B2_LAUNCHED();
     return 0;
 }
-int launch_gather_f32(const float* src, const int64_t* idx, float* out, int R, cudaStream_t s) {
-    gather_f32_kernel<<<(R + 255) / 256, 256, 0, s>>>(src, idx, out, R);
+int launch_gather_f32(const float* src, const int64_t* idx, float* out, int R, long V, cudaStream_t s) {
+    gather_f32_kernel<<<(R + 255) / 256, 256, 0, s>>>(src, idx, out, R, V);
     B2_LAUNCHED();
     return 0;
 }
-int launch_scatter_add_rows_f32(const float* src, const int64_t* idx, float* dst, int R, int H, cudaStream_t s) {
-    scatter_add_rows_kernel<<<R, 256, 0, s>>>(src, idx, dst, R, H);
+int launch_scatter_add_rows_f32(const float* src, const int64_t* idx, float* dst, int R, int H, long V, cudaStream_t s) {
+    scatter_add_rows_kernel<<<R, 256, 0, s>>>(src, idx, dst, R, H, V);
     B2_LAUNCHED();
     return 0;
 }
-int launch_scatter_add_f32(const float* src, const int64_t* idx, float* dst, int R, cudaStream_t s) {
-    scatter_add_kernel<<<(R + 255) / 256, 256, 0, s>>>(src, idx, dst, R);
+int launch_scatter_add_f32(const float* src, const int64_t* idx, float* dst, int R, long V, cudaStream_t s) {
+    scatter_add_kernel<<<(R + 255) / 256, 256, 0, s>>>(src, idx, dst, R, V);
     B2_LAUNCHED();
     return 0;
 }

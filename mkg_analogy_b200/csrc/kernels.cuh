@@ -17,7 +17,7 @@ int launch_vision_embed_ln(const float* patch_out, const float* cls, const float
 // BertEmbeddings (modeling_unimo.py:152-186), dropout p = 0
 int launch_text_embed_ln(const int64_t* ids, const int64_t* tt, const float* E, const float* pos, const float* type,
                          const float* gamma, const float* beta, float eps, float* pre, float* out_f32, bf16* out_bf16,
-                         float* mean, float* rstd, int B, int L, int H, int V, int* status, DropCfg drop, cudaStream_t s);
+                         float* mean, float* rstd, int B, int L, int H, int V, int TV, int* status, DropCfg drop, cudaStream_t s);
 int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y32, bf16* y16,
                          float* mean, float* rstd, int M, int H, cudaStream_t s);
 // dx = LN'(dy) [* act'(dact_src)] [+ add];  dgamma += ..., dbeta += ...; dxsum[c] += sum_rows dx[:, c] when given
@@ -34,15 +34,16 @@ int launch_mask_cast_colsum(const float* src, bf16* dst, float* colsum, int M, i
 int launch_colsum_f32(const float* x, long ld, float* out, int M, int N, cudaStream_t s);
 // text embedding backward: dE[ids] += d, dtype[tt] += d, dpos[l] += d  (d = gradient wrt the pre-LN sum)
 int launch_text_embed_bwd(const float* d, const int64_t* ids, const int64_t* tt, float* dE, float* dpos, float* dtype,
-                          int B, int L, int H, cudaStream_t s);
+                          int B, int L, int H, int V, int TV, cudaStream_t s);   // ids / types clamped as in the forward kernel
 // vision embedding backward: dcls, dpos accumulate; dpatch_out bf16 [(B*2*P), H] (A^T operand of the dWp GEMM)
 int launch_vision_embed_bwd(const float* dx0, float* dcls, float* dpos, bf16* dpatch, int B, int P, int H,
                             cudaStream_t s);
 // gather rows: out[r, :] = src[idx[r], :]
-int launch_gather_rows_bf16(const bf16* src, const int64_t* idx, bf16* out, int R, int H, cudaStream_t s);
-int launch_gather_f32(const float* src, const int64_t* idx, float* out, int R, cudaStream_t s);
-int launch_scatter_add_rows_f32(const float* src, const int64_t* idx, float* dst, int R, int H, cudaStream_t s);
-int launch_scatter_add_f32(const float* src, const int64_t* idx, float* dst, int R, cudaStream_t s);
+// idx values outside [0, V): status bit 0 is raised and row 0 is read (gathers), the element is skipped (scatters)
+int launch_gather_rows_bf16(const bf16* src, const int64_t* idx, bf16* out, int R, int H, long V, int* status, cudaStream_t s);
+int launch_gather_f32(const float* src, const int64_t* idx, float* out, int R, long V, cudaStream_t s);
+int launch_scatter_add_rows_f32(const float* src, const int64_t* idx, float* dst, int R, int H, long V, cudaStream_t s);
+int launch_scatter_add_f32(const float* src, const int64_t* idx, float* dst, int R, long V, cudaStream_t s);
 // AdamW over a flat buffer with per-segment flags (lit_models/transformer.py:224-241)
 struct AdamSeg { long begin, end; int decay; int skip; };
 // over the flat range [begin, end); zero_grads: clear g after use
@@ -104,10 +105,10 @@ struct LossGroup {
 };
 // label-smoothed CE (lit_models/utils.py:42-66) or plain CE (eps = 0), mean over the group's rows; loss[0] += CE
 int launch_ls_ce(const LossGroup& g, const int64_t* label, const int64_t* pre_type, float eps, float* loss, int B,
-                 int* status, cudaStream_t s);   // status (may be null): bit 8 = label out of range
+                 int* status, cudaStream_t s, const float* grad_scale = nullptr);   // status (may be null): bit 8 = label out of range
 // relaxation loss (lit_models/transformer.py:103-108): loss[0] += alpha * mean(...); dz rows += gradient
 int launch_relaxation(const float* z, const int64_t* rel_idx, const int64_t* q_head, const int64_t* a_head, float alpha,
-                      float* loss, float* dz, int B, int L, int H, int* status, cudaStream_t s);
+                      float* loss, float* dz, int B, int L, int H, int* status, cudaStream_t s, const float* grad_scale = nullptr);
 // dz[b*L + mask_pos[b], :] += dzm[b, :]
 int launch_scatter_mask_rows(const float* dzm, const int* mask_pos, float* dz, int B, int L, int H, cudaStream_t s);
 // rank of gold = 1 + #{c : x[b,c] > x[b,label]}  (lit_models/transformer.py:162-164 without the double sort)

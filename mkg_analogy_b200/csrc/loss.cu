@@ -63,7 +63,7 @@ __device__ __forceinline__ bool row_selected(int select, const int64_t* pre_type
 // loss_b = (sum q) * logsumexp(x) - sum_c q_c x_c ;  dx = ((sum q) softmax(x) - q) / n_selected.
 __global__ void __launch_bounds__(256)
 ls_ce_kernel(const LossGroup g, const int64_t* __restrict__ label, const int64_t* __restrict__ pre_type, float eps, float* loss,
-             int B, int* status) {
+             int B, int* status, const float* __restrict__ grad_scale) {
     __shared__ float red[8];
     __shared__ int nsel_s;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -106,9 +106,10 @@ ls_ce_kernel(const LossGroup g, const int64_t* __restrict__ label, const int64_t
         const float l = qsum * lse - (q_lab * xl + q_other * (sx - xl));
         atomicAdd(loss, l * inv_n);
     }
+    const float gs = inv_n * (grad_scale ? *grad_scale : 1.0f);      // incoming d(loss), applied at the seed of the backward pass
     for (int c = tid; c < g.ldd; c += blockDim.x) {
         float d = 0.f;
-        if (c < C) d = (qsum * __expf(x[c] - lse) - (c == y ? q_lab : q_other)) * inv_n;
+        if (c < C) d = (qsum * __expf(x[c] - lse) - (c == y ? q_lab : q_other)) * gs;
         if (g.dlogits16) g.dlogits16[(long)b * g.ldd + c] = __float2bfloat16(d);
         if (g.dlogits32) g.dlogits32[(long)b * g.ldd + c] = d;
     }
@@ -117,7 +118,8 @@ ls_ce_kernel(const LossGroup g, const int64_t* __restrict__ label, const int64_t
 // one CTA (128 threads) per sample: relu(cos(z[qh], z[ah])) + 1 - cos(z[r0], z[r1]); torch cosine_similarity eps 1e-8
 __global__ void __launch_bounds__(128)
 relaxation_kernel(const float* __restrict__ z, const int64_t* __restrict__ rel_idx, const int64_t* __restrict__ q_head,
-                  const int64_t* __restrict__ a_head, float alpha, float* loss, float* dz, int B, int L, int H, int* status) {
+                  const int64_t* __restrict__ a_head, float alpha, float* loss, float* dz, int B, int L, int H, int* status,
+                  const float* __restrict__ grad_scale) {
     __shared__ float red[4];
     const int b = blockIdx.x, tid = threadIdx.x;
     long pq = q_head[b], pa = a_head[b], p0 = rel_idx[2 * b], p1 = rel_idx[2 * b + 1];
@@ -144,8 +146,9 @@ relaxation_kernel(const float* __restrict__ z, const int64_t* __restrict__ rel_i
     const float w = alpha / B;
     if (tid == 0) atomicAdd(loss, w * (fmaxf(cos_h, 0.f) + 1.0f - cos_r));
     if (!dz) return;
-    const float gh = cos_h > 0.f ? w : 0.f;   // d relu
-    const float gr = -w;
+    const float ws = w * (grad_scale ? *grad_scale : 1.0f);
+    const float gh = cos_h > 0.f ? ws : 0.f;   // d relu
+    const float gr = -ws;
     float* dq = dz + ((long)b * L + pq) * H;
     float* da = dz + ((long)b * L + pa) * H;
     float* d0 = dz + ((long)b * L + p0) * H;
@@ -195,16 +198,16 @@ int launch_gather_mask_rows(const bf16* z16, const int* mask_pos, bf16* zm, int 
     return 0;
 }
 int launch_ls_ce(const LossGroup& g, const int64_t* label, const int64_t* pre_type, float eps, float* loss, int B,
-                 int* status, cudaStream_t s) {
+                 int* status, cudaStream_t s, const float* grad_scale) {
     B2_CHECK(g.C > 0 && g.ldd >= g.C, "ls_ce: bad class count %d / gradient leading dimension %ld", g.C, g.ldd);
     B2_CHECK(g.select == 0 || pre_type != nullptr, "ls_ce: row selection needs pre_type");
-    ls_ce_kernel<<<B, 256, 0, s>>>(g, label, pre_type, eps, loss, B, status);
+    ls_ce_kernel<<<B, 256, 0, s>>>(g, label, pre_type, eps, loss, B, status, grad_scale);
     B2_LAUNCHED();
     return 0;
 }
 int launch_relaxation(const float* z, const int64_t* rel_idx, const int64_t* q_head, const int64_t* a_head, float alpha,
-                      float* loss, float* dz, int B, int L, int H, int* status, cudaStream_t s) {
-    relaxation_kernel<<<B, 128, 0, s>>>(z, rel_idx, q_head, a_head, alpha, loss, dz, B, L, H, status);
+                      float* loss, float* dz, int B, int L, int H, int* status, cudaStream_t s, const float* grad_scale) {
+    relaxation_kernel<<<B, 128, 0, s>>>(z, rel_idx, q_head, a_head, alpha, loss, dz, B, L, H, status, grad_scale);
     B2_LAUNCHED();
     return 0;
 }

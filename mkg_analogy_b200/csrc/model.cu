@@ -672,7 +672,7 @@ extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* 
     // ---- text embeddings (:152-186)
     B2_TRY(launch_text_embed_ln(batch->input_ids, batch->token_type_ids, rt.p32(l.word), rt.p32(l.tpos), rt.p32(l.ttype),
                                 rt.p32(l.eln_w), rt.p32(l.eln_b), d.text_eps, w.tpre, w.T32[0], w.T16[0], w.emean, w.erstd, B, L,
-                                H, d.vocab, w.status, make_drop(ph, seed, 0), stx));
+                                H, d.vocab, d.type_vocab, w.status, make_drop(ph, seed, 0), stx));
 
     for (int i = 0; i < D; ++i) {
         const bool fused = i >= d.fuse_from;
@@ -772,8 +772,8 @@ extern "C" int32_t b200mart_head_loss(b200mart_handle* h, const b200mart_buffers
     if (hd->mode == 0) {
         B2_CHECK(hd->col_ids && hd->n_cols > 0 && hd->n_cols <= d.vocab, "head_loss: fine-tune mode needs col_ids");
         B2_CHECK(hd->rel_idx && hd->q_head_idx && hd->a_head_idx, "head_loss: fine-tune mode needs rel_idx, q_head_idx, a_head_idx");
-        B2_TRY(launch_gather_rows_bf16(r.p16(l.word), hd->col_ids, w.esel16, hd->n_cols, H, s));
-        B2_TRY(launch_gather_f32(r.p32(l.dec_b), hd->col_ids, w.bias_sel, hd->n_cols, s));
+        B2_TRY(launch_gather_rows_bf16(r.p16(l.word), hd->col_ids, w.esel16, hd->n_cols, H, d.vocab, w.status, s));
+        B2_TRY(launch_gather_f32(r.p32(l.dec_b), hd->col_ids, w.bias_sel, hd->n_cols, d.vocab, s));
         groups[ng++] = Group{hd->n_cols, w.esel16, w.bias_sel, 0, 0, true, 0};
     } else {
         B2_CHECK(hd->pre_type, "head_loss: pre-train mode needs pre_type");
@@ -805,7 +805,7 @@ extern "C" int32_t b200mart_head_loss(b200mart_handle* h, const b200mart_buffers
         lg.logits = w.logits; lg.ld = Cp; lg.C = g.C;
         lg.dlogits16 = compute_grad ? w.dlogits16 : nullptr; lg.ldd = Cp;
         lg.select = g.select;
-        B2_TRY(launch_ls_ce(lg, hd->label, hd->pre_type, hd->label_smoothing, w.loss, B, w.status, s));
+        B2_TRY(launch_ls_ce(lg, hd->label, hd->pre_type, hd->label_smoothing, w.loss, B, w.status, s, compute_grad ? hd->grad_scale : nullptr));
         if (compute_grad) {
             // d zm += dlogits E_sel        (M = B, N = H, K = C; B operand stored [K = C][N = H])
             GemmOp op;
@@ -820,10 +820,10 @@ extern "C" int32_t b200mart_head_loss(b200mart_handle* h, const b200mart_buffers
             if (g.gathered) {
                 ow.out_f32 = w.desel; ow.ldo32 = H;
                 B2_TRY(run_gemm(h, ow, s));
-                B2_TRY(launch_scatter_add_rows_f32(w.desel, hd->col_ids, r.g32(l.word), g.C, H, s));
+                B2_TRY(launch_scatter_add_rows_f32(w.desel, hd->col_ids, r.g32(l.word), g.C, H, d.vocab, s));
                 CUDA_TRY(cudaMemsetAsync(w.dbias_sel, 0, sizeof(float) * g.C, s));
                 B2_TRY(launch_colsum_bf16(w.dlogits16, Cp, w.dbias_sel, B, g.C, s));
-                B2_TRY(launch_scatter_add_f32(w.dbias_sel, hd->col_ids, r.g32(l.dec_b), g.C, s));
+                B2_TRY(launch_scatter_add_f32(w.dbias_sel, hd->col_ids, r.g32(l.dec_b), g.C, d.vocab, s));
             } else {
                 ow.out_f32 = r.g32(l.word) + g.col0 * H; ow.ldo32 = H; ow.accumulate = 1;
                 B2_TRY(run_gemm(h, ow, s));
@@ -833,7 +833,7 @@ extern "C" int32_t b200mart_head_loss(b200mart_handle* h, const b200mart_buffers
     }
     if (hd->mode == 0)
         B2_TRY(launch_relaxation(w.z32, hd->rel_idx, hd->q_head_idx, hd->a_head_idx, hd->alpha, w.loss, compute_grad ? w.dz : nullptr,
-                                 B, L, H, w.status, s));
+                                 B, L, H, w.status, s, compute_grad ? hd->grad_scale : nullptr));
     if (compute_grad) B2_TRY(launch_scatter_mask_rows(w.dzm, w.mask_pos, w.dz, B, L, H, s));
     if (loss_out) CUDA_TRY(cudaMemcpyAsync(loss_out, w.loss, sizeof(float), cudaMemcpyDeviceToDevice, s));
     return 0;
@@ -1008,7 +1008,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
     // ---- embeddings
     B2_TRY(launch_layernorm_bwd(w.dT, w.tpre, w.emean, w.erstd, rt.p32(l.eln_w), nullptr, nullptr, 0, w.t32a, nullptr,
                                 rt.g32(l.eln_w), rt.g32(l.eln_b), nullptr, Mt, H, stx, make_drop(ph, seed, 0), nodrop));
-    B2_TRY(launch_text_embed_bwd(w.t32a, batch->input_ids, batch->token_type_ids, rt.g32(l.word), rt.g32(l.tpos), rt.g32(l.ttype), B, L, H, stx));
+    B2_TRY(launch_text_embed_bwd(w.t32a, batch->input_ids, batch->token_type_ids, rt.g32(l.word), rt.g32(l.tpos), rt.g32(l.ttype), B, L, H, d.vocab, d.type_vocab, stx));
     if (any_fusion) {
         B2_TRY(launch_layernorm_bwd(w.dV[1], w.vx0, w.vmean0, w.vrstd0, rv.p32(l.preln_w), nullptr, nullptr, 0, w.v32a, nullptr,
                                     rv.g32(l.preln_w), rv.g32(l.preln_b), nullptr, Mv, H, sv));

@@ -133,6 +133,46 @@ def make_finetune_batch(B, L, image_size=224, vocab: VocabLayout = MARS_VOCAB, s
     }
 
 
+def analogy_classes(vocab: VocabLayout = MARS_VOCAB, n_classes=16, tokens_per_class=4, seed=3):
+    """Class table of the decidable synthetic split: `n_classes` gold entities (as indices into
+    `vocab.analogy_entity_ids()`, i.e. label values) and, per class, a private set of filler word-pieces and three private
+    context entities (never gold entities)."""
+    g = torch.Generator().manual_seed(seed)
+    label_idx = torch.randperm(vocab.n_analogy_entities, generator=g)[:n_classes].sort().values
+    toks = vocab.filler_lo + torch.randperm(vocab.filler_hi - vocab.filler_lo, generator=g)[: n_classes * tokens_per_class]
+    gold = set((torch.as_tensor(vocab.analogy_entity_ids())[label_idx]).tolist())
+    ctx = [e for e in (vocab.entity_id_st + torch.randperm(vocab.n_entities, generator=g)).tolist() if e not in gold][: 3 * n_classes]
+    return label_idx, toks.view(n_classes, tokens_per_class), torch.as_tensor(ctx).view(n_classes, 3)
+
+
+def make_decidable_batch(B, L, image_size=224, vocab: VocabLayout = MARS_VOCAB, seed=1234, n_classes=16, class_seed=3, min_len=24):
+    """A fine-tune batch whose label can be read off its inputs (the "learnable synthetic task" of SURVEY.md §8 c5, used to
+    build an evaluation split with real top-1 margins): the prompt structure (lengths, separator / [MASK] / [R] positions,
+    padding, zero second images) varies per sample exactly as in `make_finetune_batch`, but a sample's filler word-pieces come
+    from the private 4-token set of its class (cyclically), its three context entities are the class's, its images are the
+    class's seeded image plus N(0, 0.1) noise, and label = the class's gold entity.  Gold entities never occur as input tokens, so their
+    embedding rows only act through the tied decoder."""
+    batch = make_finetune_batch(B, L, image_size, vocab, seed=seed, min_len=min_len)
+    label_idx, toks, ctx = analogy_classes(vocab, n_classes, seed=class_seed)
+    g = torch.Generator().manual_seed(seed + 7919)
+    cls = torch.randint(0, n_classes, (B,), generator=g)
+    ids, px = batch["input_ids"], batch["pixel_values"]
+    for b in range(B):
+        row, c = ids[b], int(cls[b])
+        fill = (row >= vocab.filler_lo) & (row < vocab.filler_hi)
+        row[fill] = toks[c][torch.arange(int(fill.sum())) % toks.shape[1]]
+        ent = ((row >= vocab.entity_id_st) & (row < vocab.entity_id_ed)).nonzero().flatten()
+        row[ent] = ctx[c][: ent.numel()]
+        base = torch.randn(2, 3, image_size, image_size, generator=torch.Generator().manual_seed(class_seed * 100003 + c))
+        zero2 = bool((px[b, 1] == 0).all())
+        px[b] = base + 0.1 * px[b]
+        if zero2:
+            px[b, 1] = 0.0
+    batch["label"] = label_idx[cls].clone()
+    batch["class"] = cls
+    return batch
+
+
 def make_pretrain_batch(B, L, image_size=224, vocab: VocabLayout = MARS_VOCAB, seed=4321, min_len=12):
     """Pre-train batch (transformer.py:72-90): no sep_idx; pre_type 1 = entity prediction over
     [entity_id_st, entity_id_ed), 2 = relation prediction over [relation_id_st, relation_id_ed)."""

@@ -92,6 +92,7 @@ class Engine:
         self.ws_key = None
         self.mirror_stale = True
         self.launches = 0   # bookkeeping for bench.py: C-ABI calls issued
+        self.forward_calls = 0   # the workspace holds the activations of forward number `forward_calls`
 
     def __del__(self):
         try:
@@ -200,6 +201,7 @@ class Engine:
         bufs = self._bufs(cb.B, cb.L)
         z = torch.empty(cb.B, cb.L, self.cfg.hidden, device=self.device) if want_z else None
         logits = torch.empty(cb.B, cb.L, self.cfg.vocab, device=self.device) if want_logits else None
+        self.forward_calls += 1
         _lib.check(self.l.b200mart_forward(self.h, C.byref(bufs), C.byref(cb), _lib.ptr(z), _lib.ptr(logits), _lib.cur_stream()))
         return z, logits
 
@@ -213,6 +215,10 @@ class Engine:
         hd.label = head["label"].data_ptr()
         hd.label_smoothing = float(head.get("label_smoothing", 0.1))
         hd.mask_token_id = int(head.get("mask_token_id", 103))
+        gs = head.get("grad_scale")                 # device scalar (fp32) multiplying every gradient seeded here; None = 1
+        if gs is not None:
+            assert gs.is_cuda and gs.dtype == torch.float32 and gs.numel() == 1
+        hd.grad_scale = _lib.ptr(gs)
         if head["mode"] == "finetune":
             hd.mode = 0
             hd.col_ids, hd.n_cols = head["col_ids"].data_ptr(), head["col_ids"].numel()

@@ -5,29 +5,38 @@ file edited.  The subclass is built against whatever base class the host environ
     # MarT/lit_models/__init__.py  (one added line)
     from mkg_analogy_b200.lit import make_fused_litmodel; B200TransformerLitModel = make_fused_litmodel(TransformerLitModel)
 
-`training_step` scores the [MASK] rows only and leaves the gradients in the module's flat gradient buffer; it returns a
-loss tensor whose `backward()` is a no-op hook-up, so Lightning's automatic optimisation keeps working unchanged.
+Order of events under Lightning's automatic optimisation (PL 1.3 and 2.x alike): `training_step` -> `optimizer.zero_grad()`
+-> `loss.backward()` -> `optimizer.step()`.  Gradients therefore must not exist before `zero_grad`: `training_step` runs the
+forward pass and the fused [MASK]-row head for the LOSS only; the returned tensor's `backward()` then produces the gradients
+(head + `b200mart_backward`), ACCUMULATING into the module's `.grad`s like autograd does, scaled on the device by the incoming
+d(loss) (1 normally; 1/N under `accumulate_grad_batches`, the loss scale under `--precision 16`).
 """
 import numpy as np
 import torch
 
 
-class _GradsReady(torch.autograd.Function):
-    """loss.backward() for the fused route: gradients were already produced by b200mart_backward inside training_step;
-    backward only attaches them to the parameters (scaled by the incoming factor, 1 under plain automatic optimisation)."""
+class _FusedBackward(torch.autograd.Function):
+    """`loss.backward()` of the fused route: runs the score head with gradients and the hand-derived backward pass on the
+    activations `training_step` left in the engine's workspace."""
 
     @staticmethod
-    def forward(ctx, anchor, loss, module):
-        ctx.module = module
+    def forward(ctx, anchor, loss, module, mb, head):
+        ctx.module, ctx.mb, ctx.head = module, mb, head
+        ctx.fwd_id = module.engine.forward_calls
         return loss.clone()
 
     @staticmethod
     def backward(ctx, g):
-        m = ctx.module
-        if float(g) != 1.0:
-            m.engine.grads32.mul_(g)
+        m, eng = ctx.module, ctx.module.engine
+        if eng.forward_calls != ctx.fwd_id:
+            raise RuntimeError("fused training_step: another forward ran before loss.backward(); the saved activations are gone")
+        m._prepare_grads()                             # keeps what zero_grad left (None -> cleared, tensors -> accumulated into)
+        head = dict(ctx.head)
+        head["grad_scale"] = g.detach().to(torch.float32).reshape(1).contiguous()   # device scalar: no host synchronisation
+        eng.head_loss(ctx.mb, head, compute_grad=True)
+        eng.backward(ctx.mb)
         m._attach_grads()
-        return None, None, None
+        return None, None, None, None, None
 
 
 def make_fused_litmodel(base_cls):
@@ -41,12 +50,14 @@ def make_fused_litmodel(base_cls):
             dev = self.model.engine.device
             if self.args.pretrain:
                 return dict(mode="pretrain", entity_range=(self.entity_id_st, self.entity_id_ed),
-                            relation_range=(self.relation_id_st, self.relation_id_ed), label=label, pre_type=extra["pre_type"],
+                            relation_range=(self.relation_id_st, self.relation_id_ed), label=label.to(dev).contiguous(),
+                            pre_type=extra["pre_type"].to(dev).contiguous(),
                             label_smoothing=self.args.label_smoothing, mask_token_id=self.tokenizer.mask_token_id)
             if not hasattr(self, "_col_ids"):
                 self._col_ids = torch.as_tensor(self.analogy_entity_ids, device=dev, dtype=torch.int64)
-            return dict(mode="finetune", col_ids=self._col_ids, label=label, rel_idx=extra["rel_idx"].contiguous(),
-                        q_head_idx=extra["q_head_idx"].contiguous(), a_head_idx=extra["a_head_idx"].contiguous(),
+            return dict(mode="finetune", col_ids=self._col_ids, label=label.to(dev).contiguous(),
+                        rel_idx=extra["rel_idx"].to(dev).contiguous(), q_head_idx=extra["q_head_idx"].to(dev).contiguous(),
+                        a_head_idx=extra["a_head_idx"].to(dev).contiguous(),
                         alpha=self.alpha, label_smoothing=self.args.label_smoothing, mask_token_id=self.tokenizer.mask_token_id)
 
         def _inputs(self, batch):
@@ -62,13 +73,15 @@ def make_fused_litmodel(base_cls):
             label, extra = self._split(batch)
             m, eng = self.model, self.model.engine
             mb = self._inputs(batch)
+            head = self._head(label, extra)
             eng.mirror_stale = True                        # a torch optimizer may have stepped the fp32 masters
             eng.train(True)
-            m._prepare_grads()
             eng.forward(mb, want_z=False)
-            loss, _, _ = eng.head_loss(mb, self._head(label, extra), compute_grad=True)
-            eng.backward(mb)
-            return _GradsReady.apply(m._anchor, loss.reshape(()), m)
+            loss, _, _ = eng.head_loss(mb, head, compute_grad=False)
+            st = getattr(self, "_status_every", 50)        # out-of-range ids / labels raise in the reference; here: polled
+            if st and batch_idx % st == 0 and eng.status():
+                raise IndexError(f"b200mart status flags {eng.status():#x}: token id / label / position out of range in this batch")
+            return _FusedBackward.apply(m._anchor, loss.reshape(()), m, mb, head)
 
         @torch.no_grad()
         def _eval(self, batch, batch_idx):                # reference: lit_models/transformer.py:115-166
@@ -79,6 +92,8 @@ def make_fused_litmodel(base_cls):
             eng.train(False)
             eng.forward(mb, want_z=False)
             _, _, ranks = eng.head_loss(mb, self._head(label, extra), compute_grad=False, want_ranks=True)
+            if eng.status():
+                raise IndexError(f"b200mart status flags {eng.status():#x}: token id / label / position out of range in this batch")
             ranks = ranks.cpu().numpy()
             if not self.args.pretrain:
                 return dict(entity_ranks=np.array(ranks))

@@ -10,8 +10,13 @@ modeling_vilt.py:370-375).  Embeddings and the MLM head are thin PyTorch plumbin
     sequence = [text, image 1, image 2]; modality embeddings 0 (text) / 1 (image).
     With the all-ones `pixel_mask` the reference builds when none is given (:834-835), its bilinear position-embedding resize
     is the identity and its `torch.multinomial` "selection" is a random PERMUTATION of the patches of each image; self-attention
-    is permutation-equivariant and only the text rows are read (:950), so the permutation is omitted here (outputs are equal,
-    not just in distribution).  A partial `pixel_mask` is not supported (the MarT pipeline never passes one);
+    is permutation-equivariant and only the text rows are read (:950), so WITHOUT `sep_idx` (pre-training) the permutation can be
+    omitted with equal outputs.  WITH `sep_idx` (fine-tuning) the adaptive scaling indexes rows `img_length+1 : s'` and columns
+    `>= s'` of the [text ; image] sequence (:373-375), which reaches image-token columns: the reference then scales a RANDOM
+    subset of the image-2 patches (whatever the permutation put last), this drop-in always the last raster-order patches, so
+    parity there holds up to the reference's own random patch order, not bit for bit.  A partial `pixel_mask` and a positive
+    `config.max_image_length` smaller than the patch count (which sub-samples patches in the reference, :166-178) are not
+    supported and raise;
   * `sep_idx + img_length` (:843-844) is applied to a copy — the reference mutates the caller's tensor in place;
   * final LayerNorm, first L rows (:950), head `ViltMLMHead` (:988-1004): returns (MaskedLMOutput(logits), trans_hidden).
 """
@@ -122,6 +127,11 @@ class ViltKGC(PretrainedMixin, nn.Module):
         cfg.update(overrides)
         if cfg.get("hidden_act", "gelu") != "gelu":
             raise ValueError("ViLT uses the erf GELU")
+        mil = getattr(config, "max_image_length", -1) if config is not None else overrides.get("max_image_length", -1)
+        n_patches = (cfg["image_size"] // cfg["patch_size"]) ** 2
+        if mil is not None and 0 < mil < n_patches:
+            raise NotImplementedError(f"config.max_image_length = {mil} < {n_patches} patches: the reference then sub-samples patches "
+                                      "(modeling_vilt.py:166-178); this drop-in keeps every patch")
         self.cfg = cfg
         if device is None:
             device = "cuda" if torch.cuda.is_available() else "cpu"

@@ -81,7 +81,7 @@ def init_weights_(engine: Engine, seed=0):
 class MartTrainer:
     def __init__(self, cfg: MKGformerConfig, vocab: VocabLayout, *, pretrain=False, lr=5e-5, weight_decay=0.01,
                  warmup_ratio=0.1, total_steps=1000, alpha=0.43, label_smoothing=0.1, device=None, process_group=None,
-                 grad_buckets=8, overlap_comm=True, dropout=True, seed=0):
+                 grad_buckets=8, overlap_comm=True, dropout=True, seed=0, status_every=200):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.cfg, self.vocab, self.pretrain = cfg, vocab, bool(pretrain)
@@ -91,6 +91,10 @@ class MartTrainer:
         self.alpha, self.label_smoothing = alpha, label_smoothing
         self.col_ids = torch.as_tensor(vocab.analogy_entity_ids(), device=self.device, dtype=torch.int64)
         self.steps_done = 0
+        # device-side index guards (token id / type, label, relaxation position, [MASK] count) only raise status bits; the
+        # reference raises IndexError / asserts on the spot, so the flags are polled every `status_every` training steps,
+        # at every evaluation step and before a checkpoint is written (one stream synchronisation each)
+        self.status_every = int(status_every)
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
@@ -188,6 +192,15 @@ class MartTrainer:
             main.wait_stream(upd)
         main.wait_stream(comm)
 
+    def check_status(self):
+        """Raise IndexError (as the reference's indexing would) when a device-side guard fired since the last forward."""
+        flags = self.engine.status()
+        if flags:
+            names = [n for bit, n in ((1, "token id / score-head column out of range"), (2, "token type out of range"),
+                                      (4, "a row without exactly one [MASK]"), (8, "label or relaxation position out of range"))
+                     if flags & bit]
+            raise IndexError(f"b200mart status flags {flags:#x}: " + "; ".join(names))
+
     # ------------------------------------------------------------------ public API
     def train_step(self, batch):
         """One optimizer step on a device-resident batch. Returns the loss as a device tensor (1,)."""
@@ -207,6 +220,8 @@ class MartTrainer:
             eng.backward(mb)
             self.allreduce_grads()
             eng.adamw(self.steps_done, lr, weight_decay=self.weight_decay, pretrain=self.pretrain)
+        if self.status_every and self.steps_done % self.status_every == 0:
+            self.check_status()
         return loss
 
     def train_step_host(self, host_batch):
@@ -275,12 +290,14 @@ class MartTrainer:
         eng.train(False)
         eng.forward(mb, want_z=False)
         loss, logits, ranks = eng.head_loss(mb, self._head(batch), compute_grad=False, want_logits=True, want_ranks=True)
+        self.check_status()
         return ranks, logits, loss
 
     # ------------------------------------------------------------------ checkpoints (reference layout, main.py:133-159)
     def save_checkpoint(self, path):
         """`{"state_dict": {"model." + name: tensor}}` as the reference's ModelCheckpoint(save_weights_only=True) writes it."""
         from .checkpoint import save_checkpoint
+        self.check_status()
         torch.cuda.synchronize(self.device)
         save_checkpoint(self.engine, path, global_step=self.steps_done)
 

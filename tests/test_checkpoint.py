@@ -21,6 +21,9 @@ def test_round_trip_through_a_lightning_style_file(tmp_path):
     blob = torch.load(path, weights_only=False)
     assert blob["epoch"] == 3 and all(k.startswith("model.") for k in blob["state_dict"])
     assert "model.cls.predictions.decoder.weight" in blob["state_dict"]          # tied aliases, as the reference saves them
+    # the two position_ids buffers too: a strict load into the reference module (main.py:159) needs the full key set
+    assert blob["state_dict"]["model.unimo.text_embeddings.position_ids"].shape == (1, a.cfg.max_position)
+    assert blob["state_dict"]["model.unimo.vision_embeddings.position_ids"].shape == (1, a.cfg.patches + 1)
     missing, unexpected = CK.load_checkpoint(b, path, strict=True)
     assert missing == [] and unexpected == [] and b.mirror_stale
     for n in a.by_name:

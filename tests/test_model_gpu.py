@@ -290,6 +290,58 @@ def test_fused_litmodel_shim_matches_engine(tiny):
     assert ranks.shape == (g["B"],) and (ranks >= 1).all()
 
 
+@pytest.mark.parametrize("set_to_none", [True, False])
+def test_fused_litmodel_follows_lightning_order(tiny, set_to_none):
+    """Lightning's automatic optimisation calls training_step -> optimizer.zero_grad() -> loss.backward() -> optimizer.step()
+    (ADVICE r1): gradients must be produced by loss.backward(), survive either zero_grad flavour, not pile up across steps,
+    and honour the incoming d(loss) (accumulate_grad_batches scales each micro-batch loss by 1/N)."""
+    g, cfg, params, _, batch = tiny
+    from argparse import Namespace
+    from mkg_analogy_b200.lit import make_fused_litmodel
+    from mkg_analogy_b200.modeling import MKGformerKGC
+
+    class Base(torch.nn.Module):
+        def __init__(self, model, args, tokenizer, data_config):
+            super().__init__()
+            self.model, self.args, self.tokenizer, self.alpha = model, args, tokenizer, args.alpha
+            self.__dict__.update(data_config)
+
+    model = MKGformerKGC(cfg, device="cuda")
+    model.engine.set_dropout(0.0, 0.0)
+    model.load_state_dict({**model.state_dict(), **params})
+    lit = make_fused_litmodel(Base)(model, Namespace(pretrain=0, label_smoothing=0.1, alpha=0.43), Namespace(mask_token_id=103),
+                                    dict(analogy_entity_ids=TINY_VOCAB.analogy_entity_ids()))
+    named = dict(model.named_parameters())
+    opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=0.0)    # lr 0: every step sees the same weights
+    probe = ("unimo.encoder.text_layer.9.attention.self.query.weight", "unimo.text_embeddings.word_embeddings.weight",
+             "unimo.encoder.vision_layers.8.mlp.fc1.weight", "cls.predictions.bias")
+    seen = []
+    for step in range(3):
+        loss = lit.training_step({k: v.clone() for k, v in batch.items()}, step)
+        opt.zero_grad(set_to_none=set_to_none)
+        loss.backward()
+        seen.append({n: named[n].grad.detach().clone() for n in probe})
+        opt.step()
+    _, _, ref_grads = _oracle_grads(cfg, params, batch)
+    for n in probe:
+        assert rel(seen[0][n], ref_grads[n]) <= 6e-2, n
+        for k in (1, 2):       # fresh every step: neither zeroed away nor accumulated (g1 + g2 + ...)
+            assert rel(seen[k][n], seen[0][n]) <= 1e-3, (n, k, rel(seen[k][n], seen[0][n]))
+    # accumulate_grad_batches = 2: zero_grad once, two micro-batches whose losses arrive scaled by 1/2
+    opt.zero_grad(set_to_none=set_to_none)
+    for micro in range(2):
+        loss = lit.training_step({k: v.clone() for k, v in batch.items()}, micro)
+        (loss * 0.5).backward()
+    for n in probe:
+        assert rel(named[n].grad, seen[0][n]) <= 1e-3, (n, rel(named[n].grad, seen[0][n]))
+    # a forward between training_step and backward invalidates the saved activations: loud error, not silent garbage
+    loss = lit.training_step({k: v.clone() for k, v in batch.items()}, 0)
+    with torch.no_grad():
+        model(**{k: batch[k] for k in ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "sep_idx")}, return_dict=True)
+    with pytest.raises(RuntimeError):
+        loss.backward()
+
+
 def test_training_mode_dropout_matches_oracle_with_same_masks(tiny):
     """Training-mode graph (dropout p = 0.1 at modeling_unimo.py:185, :362, :389, :476): the CUDA path's stateless hash
     masks are rebuilt in torch (oracle.hash_dropout) and fed to the oracle, so forward, loss and every gradient are
@@ -489,6 +541,32 @@ def test_bad_indices_flag_status_instead_of_faulting(tiny):
     eng.head_loss(bad, ft_head(bad, TINY_VOCAB), compute_grad=True)
     torch.cuda.synchronize()
     assert eng.status() == (1 | 8)
+    # backward with the bad token id / type still in the batch: clamped like the forward pass, nothing written out of bounds
+    guard = eng.grads32.numel()
+    bad["token_type_ids"] = batch["token_type_ids"].clone()
+    bad["token_type_ids"][0, 2] = 5
+    eng.forward(bad, want_z=False)
+    eng.head_loss(bad, ft_head(bad, TINY_VOCAB), compute_grad=True)
+    eng.backward(bad)
+    torch.cuda.synchronize()
+    assert eng.status() == (1 | 2 | 8) and eng.grads32.numel() == guard and bool(torch.isfinite(eng.grads32).all())
+    # an out-of-range score-head column: status bit, no fault
+    cols = torch.as_tensor(TINY_VOCAB.analogy_entity_ids(), device="cuda")
+    cols[3] = cfg.vocab + 11
+    eng.forward(batch, want_z=False)
+    eng.head_loss(batch, ft_head(batch, TINY_VOCAB, col_ids=cols), compute_grad=True)
+    eng.backward(batch)
+    torch.cuda.synchronize()
+    assert eng.status() == 1 and bool(torch.isfinite(eng.grads32).all())
+    # the trainer turns the flags into the reference's IndexError
+    from mkg_analogy_b200.trainer import MartTrainer
+    tr = MartTrainer(cfg, TINY_VOCAB, total_steps=10, dropout=False, status_every=1)
+    tr.engine.load(params)
+    bad2 = dict(batch)
+    bad2["label"] = batch["label"].clone()
+    bad2["label"][0] = -7
+    with pytest.raises(IndexError):
+        tr.train_step(bad2)
     eng.forward(batch, want_z=False)
     eng.head_loss(batch, ft_head(batch, TINY_VOCAB), compute_grad=False)
     assert eng.status() == 0

@@ -191,3 +191,66 @@ def test_flava_dropin_plumbing_vs_reference_golden():
     assert m.get_output_embeddings().weight is m.get_input_embeddings().weight
     emb = m.resize_token_embeddings(305)
     assert emb.weight.shape[0] == 305 and m.get_output_embeddings().weight is emb.weight and m.cls.bias.shape[0] == 305
+
+
+# ------------------------------------------------------------------------------------------ base size (the benchmarked shape)
+@pytest.fixture(scope="module")
+def base_fixture():
+    from mkg_analogy_b200.config import BASE
+    g = torch.load(os.path.join(GOLD, "mkgformer_base.pt"), weights_only=False)
+    params = init_params(BASE, g["seed_w"])
+    chk = float(sum(params[k].double().abs().sum().item() for k in
+                    ("unimo.text_embeddings.word_embeddings.weight", "unimo.encoder.text_layer.11.output.dense.weight")))
+    assert abs(chk - g["param_checksum"]) < 1e-6 * g["param_checksum"], "seeded weights drifted from the fixture"
+    return g, BASE, params
+
+
+def test_base_config1_oracle_vs_reference_fixture(base_fixture):
+    """BASELINE.json config 1 (MKGformer-base, 4 synthetic MARS examples): the oracle reproduces the reference's [MASK]-row
+    logits over the whole vocabulary, trans_hidden_states, training_step loss, ranks and gradient norms."""
+    from mkg_analogy_b200.data import MARS_VOCAB
+    g, cfg, P = base_fixture
+    d = g["c1"]
+    batch = make_finetune_batch(d["B"], d["L"], cfg.image_size, MARS_VOCAB, seed=d["seed_b"], min_len=d["min_len"])
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    logits, z = O.forward(Pg, cfg, batch, full_logits=True)
+    mpos = O.mask_positions(batch["input_ids"])
+    assert torch.allclose(z.detach(), d["trans"], atol=5e-5, rtol=1e-4)
+    assert torch.allclose(logits.detach()[torch.arange(d["B"]), mpos], d["mask_logits_full"], atol=5e-5, rtol=1e-4)
+    del logits
+    loss, x, _ = O.finetune_loss(Pg, cfg, batch, MARS_VOCAB.analogy_entity_ids(), alpha=0.43, label_smoothing=0.1)
+    assert abs(loss.item() - d["loss"].item()) < 2e-5
+    assert torch.equal(O.ranks_of_gold(x.detach(), batch["label"]), d["ranks"].to(torch.int64))
+    loss.backward()
+    for name, ref_norm in d["grad_norm"].items():
+        if name.startswith("cls.predictions.decoder"):
+            continue
+        gr = Pg[name].grad
+        if ref_norm is None:
+            assert gr is None or gr.abs().max().item() == 0.0, name
+        elif ref_norm >= 1e-7:
+            assert abs(gr.norm().item() - ref_norm) <= 5e-4 * ref_norm + 1e-8, (name, gr.norm().item(), ref_norm)
+    for name, ref in d["grad_full"].items():
+        if "adaptive_weight" in name:
+            assert torch.allclose(Pg[name].grad, ref, atol=1e-7, rtol=2e-3), (name, Pg[name].grad, ref)
+
+
+def test_base_eval_split_oracle_ranks_first_batch(base_fixture):
+    """The held-out decidable split: oracle ranks == reference `_eval` ranks (fixture) on the first batch, Hits@1 = 1."""
+    from mkg_analogy_b200.data import MARS_VOCAB, make_decidable_batch
+    g, cfg, P = base_fixture
+    s = torch.load(os.path.join(GOLD, "base_eval_split.pt"), weights_only=False)
+    P = dict(P)
+    E = P["unimo.text_embeddings.word_embeddings.weight"].clone()
+    bias = P["cls.predictions.bias"].clone()
+    E[s["gold_token_ids"]] = s["rows"]
+    bias[s["gold_token_ids"]] = s["bias"]
+    P["unimo.text_embeddings.word_embeddings.weight"], P["cls.predictions.bias"] = E, bias
+    b = make_decidable_batch(s["bs"], s["L"], cfg.image_size, MARS_VOCAB, seed=s["eval_seed0"], n_classes=s["n_classes"])
+    chk = float(b["input_ids"].double().abs().sum().item())
+    assert abs(chk - s["batch_checksum"]) < 1e-6 * s["batch_checksum"]
+    with torch.no_grad():
+        _, x, _ = O.finetune_loss(P, cfg, b, MARS_VOCAB.analogy_entity_ids(), alpha=0.43, label_smoothing=0.1)
+    r = O.ranks_of_gold(x, b["label"])
+    assert torch.equal(r, s["ranks"][: s["bs"]].to(torch.int64))
+    assert s["gold_margin"].min().item() > 0.25 and bool((s["ranks"] == 1).all())     # the split is decidable by construction
