@@ -201,6 +201,13 @@ int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* params16, floa
  * relaxation-loss position out of range (the reference raises IndexError / asserts in these cases). */
 int32_t b200mart_status(b200mart_handle* h, const b200mart_buffers* bufs, void* stream, int32_t* flags_out);
 
+/* Layer-by-layer parity hook (what `output_hidden_states=True` gives for the reference, modeling_unimo.py:603-647): copies the
+ * fp32 residual stream saved by the last b200mart_forward on this workspace into `out`.  stream_kind 0 = text hidden state
+ * entering text layer `layer` (layer = layers: the encoder output), (B, L, hidden); 1 = vision hidden state entering vision
+ * layer `layer` (layer = layers: the vision output), (B, 1 + 2 * patches, hidden). */
+int32_t b200mart_read_hidden(b200mart_handle* h, const b200mart_buffers* bufs, int32_t stream_kind, int32_t layer, float* out,
+                             void* stream);
+
 /* Optional device timing by kernel family, for roofline reporting: between begin and end every tensor-core GEMM
  * (index 0), fused attention (1) and fusion (2) launch is bracketed by CUDA events on the launching stream.
  * end synchronises the stream; gemm_flops = sum of 2*M*N*K over the GEMM launches. Never used in a timed region. */

@@ -626,6 +626,18 @@ extern "C" int32_t b200mart_status(b200mart_handle* h, const b200mart_buffers* b
     return 0;
 }
 
+extern "C" int32_t b200mart_read_hidden(b200mart_handle* h, const b200mart_buffers* bufs, int32_t stream_kind, int32_t layer, float* out,
+                                        void* stream) {
+    B2_CHECK(h && bufs && out && h->ws_base == bufs->workspace && h->ws.B > 0, "read_hidden: run forward on this workspace first");
+    B2_CHECK((stream_kind == 0 || stream_kind == 1) && layer >= 0 && layer <= h->d.layers, "read_hidden: bad stream kind %d / layer %d",
+             stream_kind, layer);
+    const Workspace& w = h->ws;
+    const size_t rows = (size_t)w.B * (stream_kind == 0 ? w.L : h->Nv);
+    const float* src = stream_kind == 0 ? w.T32[layer] : w.V32[layer];
+    CUDA_TRY(cudaMemcpyAsync(out, src, sizeof(float) * rows * h->d.hidden, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
 // --------------------------------------------------------------------------------------- forward
 extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* bufs, const b200mart_batch* batch, float* z_out,
                                     float* logits_out, void* stream) {

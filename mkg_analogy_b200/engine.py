@@ -238,6 +238,17 @@ class Engine:
                                              _lib.ptr(ranks), int(compute_grad), _lib.cur_stream()))
         return loss, ml, ranks
 
+    def read_hidden(self, kind, layer):
+        """fp32 residual stream saved by the last forward: kind "text" (B, L, H) / "vision" (B, Nv, H) entering layer `layer`
+        (layer == cfg.layers: the stream's output) — the reference's `output_hidden_states`."""
+        B, L = self.ws_key
+        rows = L if kind == "text" else self.cfg.vision_tokens
+        out = torch.empty(B, rows, self.cfg.hidden, device=self.device)
+        bufs = self._bufs(B, L)
+        _lib.check(self.l.b200mart_read_hidden(self.h, C.byref(bufs), 0 if kind == "text" else 1, int(layer), out.data_ptr(),
+                                               _lib.cur_stream()))
+        return out
+
     def layer_extents(self):
         """[(begin, end)] flat extents of each layer index's parameters (vision + text layer)."""
         out = []

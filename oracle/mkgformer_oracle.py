@@ -87,6 +87,30 @@ def vision_layer(P, cfg, i, x, text_kv):
     return x + F.linear(h, P[p + "mlp.fc2.weight"], P[p + "mlp.fc2.bias"])
 
 
+# When set to a list, text_layer appends (layer, raw attention scores) with retain_grad(): the gradient of an adaptive weight
+# is sum(dS * S_raw) over its block, a heavily cancelling sum whose forward-error bound is eps * sum(|dS * S_raw|).
+SCORE_TAP = None
+
+
+def adaptive_weight_conditioning(tap, sep_split, w0s, w1s):
+    """{layer: ((dw0, sum|terms|), (dw1, sum|terms|))} from the tapped raw scores and their gradients (call after backward):
+    terms = dS_scaled * S_raw = S_raw.grad * S_raw / factor over rows < s x cols >= s (w0) and rows >= s x cols >= s (w1)."""
+    out = {}
+    for (i, sc), w0, w1 in zip(tap, w0s, w1s):
+        B, nh, L, _ = sc.shape
+        ar = torch.arange(L, device=sc.device)
+        s = sep_split.view(B, 1, 1, 1)
+        col = ar.view(1, 1, 1, L) >= s
+        row_lo = ar.view(1, 1, L, 1) < s
+        res = []
+        for blk, w, lo, hi in ((col & row_lo, w0, 0.0, 0.5), (col & ~row_lo, w1, 0.5, 1.0)):
+            f = torch.clamp(w.detach(), lo, hi)
+            t = (sc.grad * sc.detach() / f) * blk
+            res.append((t.sum().item(), t.abs().sum().item()))
+        out[i] = tuple(res)
+    return out
+
+
 def adaptive_scale(scores, sep_split, w0, w1):
     """modeling_unimo.py:342-349 without the per-sample Python loop: rows < s, cols >= s are multiplied by
     clamp(w0, 0, 0.5); rows >= s, cols >= s by clamp(w1, 0.5, 1).  Applied BEFORE the additive mask."""
@@ -112,6 +136,9 @@ def text_layer(P, cfg, i, x, ext_mask, vis, sep_split, drop=None):
     k = _heads(F.linear(x, P[p + "attention.self.key.weight"], P[p + "attention.self.key.bias"]), nh)
     v = _heads(F.linear(x, P[p + "attention.self.value.weight"], P[p + "attention.self.value.bias"]), nh)
     sc = (q @ k.transpose(-1, -2)) / math.sqrt(d)
+    if SCORE_TAP is not None and sc.requires_grad:      # tests: raw scores + their gradient -> conditioning of d adaptive_weight
+        sc.retain_grad()
+        SCORE_TAP.append((i, sc))
     if sep_split is not None:
         sc = adaptive_scale(sc, sep_split, P[p + "attention.self.adaptive_weight.0"],
                             P[p + "attention.self.adaptive_weight.1"])
@@ -138,14 +165,39 @@ def text_layer(P, cfg, i, x, ext_mask, vis, sep_split, drop=None):
     return out, (k, v)
 
 
-def encoder(P, cfg, vis, txt, ext_mask, sep_split, drop=None):
+def encoder(P, cfg, vis, txt, ext_mask, sep_split, drop=None, hidden=None):
     """UnimoEncoder.forward :589-658: interleaved loop; layer idx >= fuse_from: the vision layer gets the
-    (K, V) of text layer idx-1 and the text layer fuses with the vision OUTPUT of layer idx."""
+    (K, V) of text layer idx-1 and the text layer fuses with the vision OUTPUT of layer idx.
+    hidden: optional dict; receives the lists "text" / "vision" of the hidden states entering each layer plus the final ones
+    (`output_hidden_states`, :603-647)."""
     kv = None
+    if hidden is not None:
+        hidden["text"], hidden["vision"] = [txt], [vis]
     for i in range(cfg.layers):
         vis = vision_layer(P, cfg, i, vis, kv if i >= cfg.fuse_from else None)
         txt, kv = text_layer(P, cfg, i, txt, ext_mask, vis if i >= cfg.fuse_from else None, sep_split, drop)
+        if hidden is not None:
+            hidden["text"].append(txt)
+            hidden["vision"].append(vis)
     return vis, txt
+
+
+class bf16_operands:
+    """Context manager: every dense product of the oracle (F.linear, the patch convolution) rounds BOTH operands to bf16 and
+    accumulates in fp32 - the arithmetic contract of a bf16 tensor-core implementation, everything else staying fp32.  Used by
+    the parity tests to separate 'what bf16 operands cost on this model' from implementation error."""
+
+    def __enter__(self):
+        self.lin, self.conv = F.linear, F.conv2d
+        r = lambda t: t.to(torch.bfloat16).to(torch.float32)
+        lin, conv = self.lin, self.conv
+        F.linear = lambda x, w, b=None: lin(r(x), r(w), b)
+        F.conv2d = lambda x, w, *a, **k: conv(r(x), r(w), *a, **k)
+        return self
+
+    def __exit__(self, *exc):
+        F.linear, F.conv2d = self.lin, self.conv
+        return False
 
 
 def head_transform(P, cfg, x):
@@ -156,7 +208,7 @@ def head_transform(P, cfg, x):
                       cfg.text_eps)
 
 
-def forward(P, cfg, batch, full_logits=True, drop=None):
+def forward(P, cfg, batch, full_logits=True, drop=None, hidden=None):
     """UnimoForMaskedLM.forward :848-893.  Returns (logits (B, L, V) or None, trans_hidden (B, L, H))."""
     ids, att = batch["input_ids"], batch["attention_mask"]
     tt = batch.get("token_type_ids")
@@ -166,7 +218,7 @@ def forward(P, cfg, batch, full_logits=True, drop=None):
     vis = vision_embed(P, cfg, batch["pixel_values"])
     txt = text_embed(P, cfg, ids, tt, drop)
     ext_mask = (1.0 - att[:, None, None, :].to(txt.dtype)) * -10000.0        # get_extended_attention_mask :21-57
-    _, txt = encoder(P, cfg, vis, txt, ext_mask, None if sep is None else sep[:, 2], drop)
+    _, txt = encoder(P, cfg, vis, txt, ext_mask, None if sep is None else sep[:, 2], drop, hidden)
     z = head_transform(P, cfg, txt)
     logits = None
     if full_logits:
