@@ -298,6 +298,127 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     }
 }
 
+// Second design of the LayerNorm backward (default; B200MART_LNB=1 selects the one above).  The first keeps the per-column
+// accumulators of dgamma / dbeta / column sums in registers (72 of its 226): one 8-warp block per SM, 12 % of the warp slots, an
+// issue rate of 13-18 % and a third of the HBM rate (profiles/ln_bwd_r2.txt) - pure latency, no memory-level parallelism to hide it.
+// Here the accumulators live in per-warp shared-memory rows (read-modify-write of the lane's own 16-byte slots: conflict-free),
+// gamma is staged in shared memory, the optional `add` / saved-derivative inputs are loaded after the row reduction: <= 128
+// registers, two blocks (16 warps) per SM; the per-block column totals leave as 4-wide vector reductions (a quarter of the
+// L2 atomic operations per block).
+__device__ __forceinline__ void red_add4(float* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+template <bool COLSUM, int NV>
+__global__ void __launch_bounds__(256, 2)
+layernorm_bwd2_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                      const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ add,
+                      const bf16* __restrict__ dact_src, int dact, float* dx32, bf16* dx16, float* dgamma, float* dbeta,
+                      float* dxsum, int M, int H, DropCfg dy_drop, DropCfg dx16_drop) {
+    extern __shared__ float red[];  // [2 or 3][warps][H] accumulators, then gamma [H]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nv = H / 128;
+    float* rg = red + warp * H;
+    float* rb = red + (nw + warp) * H;
+    float* rc = red + (2 * nw + warp) * H;
+    float* gs = red + (COLSUM ? 3 : 2) * nw * H;
+    for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) st4(gs + c, ld4(gamma + c));     // parameters: not written by the predecessor
+#pragma unroll
+    for (int t = 0; t < NV; ++t)
+        if (t < nv) {
+            const int c = lane * 4 + t * 128;
+            st4(rg + c, make_float4(0, 0, 0, 0));
+            st4(rb + c, make_float4(0, 0, 0, 0));
+            if (COLSUM) st4(rc + c, make_float4(0, 0, 0, 0));
+        }
+    __syncthreads();
+    pdl_wait();
+    pdl_launch_dependents();
+    for (int row = blockIdx.x * nw + warp; row < M; row += gridDim.x * nw) {
+        const float mu = mean[row], rs = rstd[row];
+        float4 d[NV], xh[NV];
+#pragma unroll
+        for (int t = 0; t < NV; ++t)
+            if (t < nv) {
+                const long off = (long)row * H + lane * 4 + t * 128;
+                d[t] = ld4(dy + off);
+                xh[t] = ld4(x + off);
+            }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < NV; ++t)
+            if (t < nv) {
+                const int c = lane * 4 + t * 128;
+                if (dy_drop.thresh) {   // this LayerNorm's output went through dropout: dy arrives wrt the dropped output
+                    const uint32_t e = (uint32_t)((long)row * H + c);
+                    d[t].x *= drop_mult(dy_drop, e); d[t].y *= drop_mult(dy_drop, e + 1);
+                    d[t].z *= drop_mult(dy_drop, e + 2); d[t].w *= drop_mult(dy_drop, e + 3);
+                }
+                xh[t] = make_float4((xh[t].x - mu) * rs, (xh[t].y - mu) * rs, (xh[t].z - mu) * rs, (xh[t].w - mu) * rs);
+                float4 ab = ld4(rb + c), ag = ld4(rg + c);
+                ab.x += d[t].x; ab.y += d[t].y; ab.z += d[t].z; ab.w += d[t].w;
+                ag.x += d[t].x * xh[t].x; ag.y += d[t].y * xh[t].y; ag.z += d[t].z * xh[t].z; ag.w += d[t].w * xh[t].w;
+                st4(rb + c, ab);
+                st4(rg + c, ag);
+                const float4 g = ld4(gs + c);
+                d[t].x *= g.x; d[t].y *= g.y; d[t].z *= g.z; d[t].w *= g.w;
+                s1 += d[t].x + d[t].y + d[t].z + d[t].w;
+                s2 += d[t].x * xh[t].x + d[t].y * xh[t].y + d[t].z * xh[t].z + d[t].w * xh[t].w;
+            }
+        s1 = warp_sum(s1) / H;
+        s2 = warp_sum(s2) / H;
+#pragma unroll
+        for (int t = 0; t < NV; ++t)
+            if (t < nv) {
+                const int c = lane * 4 + t * 128;
+                const long off = (long)row * H + c;
+                float4 o;
+                o.x = rs * (d[t].x - s1 - xh[t].x * s2);
+                o.y = rs * (d[t].y - s1 - xh[t].y * s2);
+                o.z = rs * (d[t].z - s1 - xh[t].z * s2);
+                o.w = rs * (d[t].w - s1 - xh[t].w * s2);
+                if (dact) {
+                    const uint2 q = *reinterpret_cast<const uint2*>(dact_src + off);
+                    const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+                    const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+                    if (dact == 1) {
+                        o.x *= gelu_erf_grad(f0.x); o.y *= gelu_erf_grad(f0.y); o.z *= gelu_erf_grad(f1.x); o.w *= gelu_erf_grad(f1.y);
+                    } else {
+                        o.x *= quick_gelu_grad(f0.x); o.y *= quick_gelu_grad(f0.y); o.z *= quick_gelu_grad(f1.x); o.w *= quick_gelu_grad(f1.y);
+                    }
+                }
+                if (add) {
+                    const float4 a = ld4(add + off);
+                    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                }
+                if (dx32) st4(dx32 + off, o);      // full gradient: the residual path
+                if (dx16_drop.thresh) {            // the dense branch fed this LayerNorm through dropout: mask its gradient
+                    const uint32_t e = (uint32_t)off;
+                    o.x *= drop_mult(dx16_drop, e); o.y *= drop_mult(dx16_drop, e + 1);
+                    o.z *= drop_mult(dx16_drop, e + 2); o.w *= drop_mult(dx16_drop, e + 3);
+                }
+                if (COLSUM) {
+                    float4 ac = ld4(rc + c);
+                    ac.x += o.x; ac.y += o.y; ac.z += o.z; ac.w += o.w;
+                    st4(rc + c, ac);
+                }
+                if (dx16) st4_bf16(dx16 + off, o);
+            }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
+        float4 sg = make_float4(0, 0, 0, 0), sb = sg, sc = sg;
+        for (int w = 0; w < nw; ++w) {
+            const float4 a = ld4(red + w * H + c), b = ld4(red + (nw + w) * H + c);
+            sg.x += a.x; sg.y += a.y; sg.z += a.z; sg.w += a.w;
+            sb.x += b.x; sb.y += b.y; sb.z += b.z; sb.w += b.w;
+            if (COLSUM) { const float4 q = ld4(red + (2 * nw + w) * H + c); sc.x += q.x; sc.y += q.y; sc.z += q.z; sc.w += q.w; }
+        }
+        red_add4(dgamma + c, sg);
+        red_add4(dbeta + c, sb);
+        if (COLSUM) red_add4(dxsum + c, sc);
+    }
+}
+
 // ---------------------------------------------------------------- column sums (bias gradients)
 // block = 32 x 8 threads over a 32-column x ROWS strip; coalesced row-major reads, one atomic per column per block.
 template <typename T>
@@ -560,6 +681,24 @@ int launch_layernorm_bwd(const float* dy, const float* x, const float* mean, con
         return 0;
     };
     const bool small = H <= 768;       // register arrays sized for the hidden size: 6 (base) or 8 (large) float4 per lane
+    static int design = -1;
+    if (design < 0) { const char* e = getenv("B200MART_LNB"); design = e ? atoi(e) : 2; }
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (design == 2 && al16(dgamma) && al16(dbeta) && (!dxsum || al16(dxsum)) && al16(gamma)) {
+        blocks = (M + nw - 1) / nw;
+        if (blocks > 148 * 2) blocks = 148 * 2;
+        const size_t smem2 = ((size_t)(dxsum ? 3 : 2) * nw + 1) * H * sizeof(float);
+        auto go2 = [&](auto kernel) -> int {
+            CUDA_TRY(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            CUDA_TRY(launch_pdl(kernel, dim3(blocks), dim3(nw * 32), smem2, s, dy, x, mean, rstd, gamma, add, dact_src, dact_src ? dact : 0,
+                                dx32, dx16, dgamma, dbeta, dxsum, M, H, dy_drop, dx16_drop));
+            return 0;
+        };
+        if (dxsum) { B2_TRY(small ? go2(layernorm_bwd2_kernel<true, 6>) : go2(layernorm_bwd2_kernel<true, 8>)); }
+        else { B2_TRY(small ? go2(layernorm_bwd2_kernel<false, 6>) : go2(layernorm_bwd2_kernel<false, 8>)); }
+        B2_LAUNCHED();
+        return 0;
+    }
     if (dxsum) { B2_TRY(small ? go(layernorm_bwd_kernel<true, 6>) : go(layernorm_bwd_kernel<true, 8>)); }
     else { B2_TRY(small ? go(layernorm_bwd_kernel<false, 6>) : go(layernorm_bwd_kernel<false, 8>)); }
     B2_LAUNCHED();

@@ -35,6 +35,8 @@ struct GemmOp {
     int split_k = 1;
     int bn = 0;                           // N tile (0 = auto: 128)
     int max_ctas = 0;                     // bound of the persistent grid (0 = one CTA per SM): leaves SMs to concurrent streams
+    int b_static = 0;                     // B (and B2) is not written by the preceding kernel of the stream (model weights): its first
+                                          // tiles are requested BEFORE griddepcontrol.wait, under the predecessor's tail
 };
 
 struct GemmPlan;  // opaque: encoded tensor maps + launch geometry

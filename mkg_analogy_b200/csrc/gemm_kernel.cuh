@@ -56,6 +56,7 @@ struct GemmDev {
     float* colsum_out; float* colsum_out2;   // EPI_DACT: += column sums of the output (bias gradient of the producing layer)
     unsigned long long* prof;   // b200mart_gemm_timeline: 16 stamps per CTA (null = off), see GemmStamp
     int debug;   // B200MART_GEMM_DEBUG bitmask (bring-up only): 1 no epilogue global access, 2 no TMA, 4 no MMA
+    int b_static;   // GemmOp::b_static
 };
 
 
@@ -119,39 +120,44 @@ __device__ __forceinline__ float act_grad(int act, float x) { return act == 1 ? 
 // Per-warp transpose buffer of one epilogue pass: 32 rows x 64 columns fp32, NO padding; the 16-byte chunk c of row r lives
 // at chunk (c ^ (r & 15)).  Writers (lane = row, 16 chunks) and readers (16 lanes = the 16 chunks of one row) both touch
 // eight different 4-bank groups per quarter warp, so every 128-bit shared-memory access is conflict-free.
-__device__ __forceinline__ int stg_off(int row, int chunk) { return row * EPI_LD + ((chunk ^ (row & 15)) << 2); }
+// (EC = 32 columns per pass, the half-footprint kernels: rows of 8 chunks, chunk c of row r at c ^ (r & 7), same property.)
+template <int EC = EPI_COLS>
+__device__ __forceinline__ int stg_off(int row, int chunk) { return row * EC + ((chunk ^ (row & (EC / 4 - 1))) << 2); }
 
 // Epilogue work split of a pass: lane = (row parity hr = lane >> 4, column quad c = lane & 15); iteration i handles row
 // 2 i + hr, columns 4 c .. 4 c + 3, so each warp-wide access covers two full 256-byte (fp32) / 128-byte (bf16) row segments.
 // Per-pass inputs that come from HBM (residual / saved activation derivative): 16 vector loads per lane, all issued back to
 // back before the TMEM read + transpose of the pass (pass 0: before the accumulator-ready wait).
-template <int EPI>
+// EC columns per pass: LPR = EC / 4 lanes cover one row segment, RPI = 32 / LPR rows per warp-wide access, IT = 32 / RPI
+// iterations per pass (EC = 64: 16 lanes / 2 rows / 16 iterations; EC = 32: 8 lanes / 4 rows / 8 iterations).
+template <int EPI, int EC = EPI_COLS>
 struct EpiIn {
     static constexpr bool kRes = (EPI == EPI_RES), kDact = (EPI == EPI_DACT);
-    float4 rs[kRes ? 16 : 1];
-    uint2 xs[kDact ? 16 : 1];
+    static constexpr int LPR = EC / 4, RPI = 32 / LPR, IT = 32 / RPI;
+    float4 rs[kRes ? IT : 1];
+    uint2 xs[kDact ? IT : 1];
     template <bool FULL>
     __device__ __forceinline__ void load_t(const GemmDev& p, int row0, int nrows, int col, int hr) {
         if (kRes) {
             const float* rp = p.residual + (long)(row0 + hr) * p.ldr + col;
-            const int ld2 = 2 * (int)p.ldr;
+            const int ld2 = RPI * (int)p.ldr;
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (FULL || 2 * i + hr < nrows) rs[i] = *reinterpret_cast<const float4*>(rp + i * ld2);
+            for (int i = 0; i < IT; ++i)
+                if (FULL || RPI * i + hr < nrows) rs[i] = *reinterpret_cast<const float4*>(rp + i * ld2);
         }
         if (kDact) {
             const bf16* xp = p.dact_src + (long)(row0 + hr) * p.ldx + col;
-            const int ld2 = 2 * (int)p.ldx;
+            const int ld2 = RPI * (int)p.ldx;
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (FULL || 2 * i + hr < nrows) xs[i] = *reinterpret_cast<const uint2*>(xp + i * ld2);
+            for (int i = 0; i < IT; ++i)
+                if (FULL || RPI * i + hr < nrows) xs[i] = *reinterpret_cast<const uint2*>(xp + i * ld2);
         }
     }
     __device__ __forceinline__ void load(const GemmDev& p, int row0, int nrows, int col0, int lane) {
-        const int col = col0 + 4 * (lane & 15);
+        const int col = col0 + 4 * (lane % LPR);
         if (!(kRes || kDact) || col >= p.N) return;
-        if (nrows >= 32) load_t<true>(p, row0, nrows, col, lane >> 4);
-        else load_t<false>(p, row0, nrows, col, lane >> 4);
+        if (nrows >= 32) load_t<true>(p, row0, nrows, col, lane / LPR);
+        else load_t<false>(p, row0, nrows, col, lane / LPR);
     }
 };
 
@@ -192,25 +198,26 @@ __device__ __forceinline__ uint2 pack_bf16x4(float4 v) { return make_uint2(pack_
 // One 32-row x 64-column block of the output from the transpose buffer.  FULL: all 32 rows valid -> no predicates, the
 // 16 iterations are independent straight-line chains the scheduler interleaves (the epilogue warps have no other latency
 // hiding: one warp per scheduler).  DROP / OUT16 / SAVEG: runtime flags hoisted to compile time.
-template <int EPI, int ACT, bool FULL, bool DROP, bool OUT16, bool SAVEG>
-__device__ __forceinline__ void epilogue_rows_t(const GemmDev& p, const float* stg, const EpiIn<EPI>& in, int row0, int nrows,
+template <int EPI, int ACT, bool FULL, bool DROP, bool OUT16, bool SAVEG, int EC = EPI_COLS>
+__device__ __forceinline__ void epilogue_rows_t(const GemmDev& p, const float* stg, const EpiIn<EPI, EC>& in, int row0, int nrows,
                                                 int col, float4 b, int lane) {
     constexpr bool kF32 = (EPI == EPI_RES || EPI == EPI_F32 || EPI == EPI_ACC);
     constexpr bool k16 = (EPI == EPI_BF16 || EPI == EPI_ACT || EPI == EPI_DACT || (EPI == EPI_RES && OUT16));
-    const int hr = lane >> 4, c = lane & 15;
+    constexpr int LPR = EC / 4, RPI = 32 / LPR, IT = 32 / RPI;
+    const int hr = lane / LPR, c = lane % LPR;
     float* o32 = kF32 ? p.out_f32 + (long)(row0 + hr) * p.ldo32 + col : nullptr;
     bf16* o16 = k16 ? p.out_bf16 + (long)(row0 + hr) * p.ldo16 + col : nullptr;
     bf16* opre = (EPI == EPI_ACT) ? p.out_preact + (long)(row0 + hr) * p.ldp + col : nullptr;
-    const int ld32 = 2 * (int)p.ldo32, ld16 = 2 * (int)p.ldo16, ldp = 2 * (int)p.ldp;
+    const int ld32 = RPI * (int)p.ldo32, ld16 = RPI * (int)p.ldo16, ldp = RPI * (int)p.ldp;
     const float alpha = p.alpha;
     const uint32_t e0 = (uint32_t)(row0 + hr) * (uint32_t)p.N + (uint32_t)col;
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-    constexpr int kUnroll = (EPI == EPI_ACT) ? 4 : 16;
+    constexpr int kUnroll = (EPI == EPI_ACT) ? 4 : IT;
 #pragma unroll(kUnroll)
-    for (int i = 0; i < 16; ++i) {
-        const int rl = 2 * i + hr;
+    for (int i = 0; i < IT; ++i) {
+        const int rl = RPI * i + hr;
         if (!FULL && rl >= nrows) continue;
-        const float4 a = *reinterpret_cast<const float4*>(stg + stg_off(rl, c));
+        const float4 a = *reinterpret_cast<const float4*>(stg + stg_off<EC>(rl, c));
         float4 v = make_float4(fmaf(a.x, alpha, b.x), fmaf(a.y, alpha, b.y), fmaf(a.z, alpha, b.z), fmaf(a.w, alpha, b.w));
         if (EPI == EPI_BF16) {
             *reinterpret_cast<uint2*>(o16 + i * ld16) = pack_bf16x4(v);
@@ -225,18 +232,18 @@ __device__ __forceinline__ void epilogue_rows_t(const GemmDev& p, const float* s
             *reinterpret_cast<uint2*>(o16 + i * ld16) = pack_bf16x4(y);
         } else if (EPI == EPI_RES) {
             if (DROP) {   // BertSelfOutput :389 / BertOutput :476: dropout(dense(x)) + residual
-                const uint32_t e = e0 + (uint32_t)(2 * i) * (uint32_t)p.N;
+                const uint32_t e = e0 + (uint32_t)(RPI * i) * (uint32_t)p.N;
                 v.x *= drop_mult(p.drop, e); v.y *= drop_mult(p.drop, e + 1);
                 v.z *= drop_mult(p.drop, e + 2); v.w *= drop_mult(p.drop, e + 3);
             }
-            const float4 r = in.rs[EpiIn<EPI>::kRes ? i : 0];
+            const float4 r = in.rs[EpiIn<EPI, EC>::kRes ? i : 0];
             v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
             *reinterpret_cast<float4*>(o32 + i * ld32) = v;
             if (OUT16) *reinterpret_cast<uint2*>(o16 + i * ld16) = pack_bf16x4(v);
         } else if (EPI == EPI_F32) {
             *reinterpret_cast<float4*>(o32 + i * ld32) = v;
         } else if (EPI == EPI_DACT) {
-            const uint2 xs = in.xs[EpiIn<EPI>::kDact ? i : 0];
+            const uint2 xs = in.xs[EpiIn<EPI, EC>::kDact ? i : 0];
             const float2 x0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs.x));
             const float2 x1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs.y));
             v.x *= x0.x; v.y *= x0.y; v.z *= x1.x; v.w *= x1.y;
@@ -246,9 +253,12 @@ __device__ __forceinline__ void epilogue_rows_t(const GemmDev& p, const float* s
             red_add_v4(o32 + i * ld32, v);
         }
     }
-    if (EPI == EPI_DACT) {     // column sums of this block: fold the two row parities, then one vector reduction per column quad
-        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
-        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+    if (EPI == EPI_DACT) {     // column sums of this block: fold the row groups, then one vector reduction per column quad
+#pragma unroll
+        for (int o = 16; o >= LPR; o >>= 1) {
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+        }
         if (hr == 0) {
             if (p.colsum_out) red_add_v4(p.colsum_out + col, cs);
             if (p.colsum_out2) red_add_v4(p.colsum_out2 + col, cs);
@@ -256,30 +266,30 @@ __device__ __forceinline__ void epilogue_rows_t(const GemmDev& p, const float* s
     }
 }
 
-template <int EPI, int ACT, bool FULL>
-__device__ __forceinline__ void epilogue_rows(const GemmDev& p, const float* stg, const EpiIn<EPI>& in, int row0, int nrows,
+template <int EPI, int ACT, bool FULL, int EC = EPI_COLS>
+__device__ __forceinline__ void epilogue_rows(const GemmDev& p, const float* stg, const EpiIn<EPI, EC>& in, int row0, int nrows,
                                               int col, float4 b, int lane) {
     if (EPI == EPI_RES) {
         const bool drop = p.drop.thresh != 0, o16 = p.out_bf16 != nullptr;
-        if (drop && o16) epilogue_rows_t<EPI, ACT, FULL, true, true, false>(p, stg, in, row0, nrows, col, b, lane);
-        else if (drop) epilogue_rows_t<EPI, ACT, FULL, true, false, false>(p, stg, in, row0, nrows, col, b, lane);
-        else if (o16) epilogue_rows_t<EPI, ACT, FULL, false, true, false>(p, stg, in, row0, nrows, col, b, lane);
-        else epilogue_rows_t<EPI, ACT, FULL, false, false, false>(p, stg, in, row0, nrows, col, b, lane);
+        if (drop && o16) epilogue_rows_t<EPI, ACT, FULL, true, true, false, EC>(p, stg, in, row0, nrows, col, b, lane);
+        else if (drop) epilogue_rows_t<EPI, ACT, FULL, true, false, false, EC>(p, stg, in, row0, nrows, col, b, lane);
+        else if (o16) epilogue_rows_t<EPI, ACT, FULL, false, true, false, EC>(p, stg, in, row0, nrows, col, b, lane);
+        else epilogue_rows_t<EPI, ACT, FULL, false, false, false, EC>(p, stg, in, row0, nrows, col, b, lane);
     } else if (EPI == EPI_ACT) {
-        if (p.save_grad) epilogue_rows_t<EPI, ACT, FULL, false, false, true>(p, stg, in, row0, nrows, col, b, lane);
-        else epilogue_rows_t<EPI, ACT, FULL, false, false, false>(p, stg, in, row0, nrows, col, b, lane);
+        if (p.save_grad) epilogue_rows_t<EPI, ACT, FULL, false, false, true, EC>(p, stg, in, row0, nrows, col, b, lane);
+        else epilogue_rows_t<EPI, ACT, FULL, false, false, false, EC>(p, stg, in, row0, nrows, col, b, lane);
     } else {
-        epilogue_rows_t<EPI, ACT, FULL, false, false, false>(p, stg, in, row0, nrows, col, b, lane);
+        epilogue_rows_t<EPI, ACT, FULL, false, false, false, EC>(p, stg, in, row0, nrows, col, b, lane);
     }
 }
 
-template <int EPI>
-__device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* stg, const EpiIn<EPI>& in, int row0, int nrows,
+template <int EPI, int EC = EPI_COLS>
+__device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* stg, const EpiIn<EPI, EC>& in, int row0, int nrows,
                                                int col0, int lane) {
     if (EPI == EPI_GENERIC) {
         // scalar, any flags: lane handles columns col0+lane and col0+32+lane
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < EC / 32; ++half) {
             const int cl = half * 32 + lane;
             const int col = col0 + cl;
             if (col >= p.N) continue;
@@ -289,7 +299,7 @@ __device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* st
 #pragma unroll 1
             for (int rr = 0; rr < nrows; ++rr) {
                 const long row = row0 + rr;
-                float v = stg[stg_off(rr, cl >> 2) + (cl & 3)] * p.alpha + badd;
+                float v = stg[stg_off<EC>(rr, cl >> 2) + (cl & 3)] * p.alpha + badd;
                 if (p.out_preact) p.out_preact[row * p.ldp + col] = __float2bfloat16((p.save_grad && p.act) ? act_grad(p.act, v) : v);
                 v = act_fwd(p.act, v);
                 if (p.dact) {
@@ -307,7 +317,7 @@ __device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* st
         }
         return;
     }
-    const int col = col0 + 4 * (lane & 15);       // N % 4 == 0 -> the quad is valid or invalid together
+    const int col = col0 + 4 * (lane % (EC / 4));       // N % 4 == 0 -> the quad is valid or invalid together
     if (col >= p.N) return;
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (EPI == EPI_BF16 || EPI == EPI_ACT || EPI == EPI_RES || EPI == EPI_F32) {
@@ -319,15 +329,15 @@ __device__ __forceinline__ void epilogue_block(const GemmDev& p, const float* st
     }
     if (EPI == EPI_ACT) {
         if (nrows >= 32) {
-            if (p.act == 1) epilogue_rows<EPI, 1, true>(p, stg, in, row0, nrows, col, b, lane);
-            else epilogue_rows<EPI, 2, true>(p, stg, in, row0, nrows, col, b, lane);
+            if (p.act == 1) epilogue_rows<EPI, 1, true, EC>(p, stg, in, row0, nrows, col, b, lane);
+            else epilogue_rows<EPI, 2, true, EC>(p, stg, in, row0, nrows, col, b, lane);
         } else {
-            if (p.act == 1) epilogue_rows<EPI, 1, false>(p, stg, in, row0, nrows, col, b, lane);
-            else epilogue_rows<EPI, 2, false>(p, stg, in, row0, nrows, col, b, lane);
+            if (p.act == 1) epilogue_rows<EPI, 1, false, EC>(p, stg, in, row0, nrows, col, b, lane);
+            else epilogue_rows<EPI, 2, false, EC>(p, stg, in, row0, nrows, col, b, lane);
         }
     } else {
-        if (nrows >= 32) epilogue_rows<EPI, 0, true>(p, stg, in, row0, nrows, col, b, lane);
-        else epilogue_rows<EPI, 0, false>(p, stg, in, row0, nrows, col, b, lane);
+        if (nrows >= 32) epilogue_rows<EPI, 0, true, EC>(p, stg, in, row0, nrows, col, b, lane);
+        else epilogue_rows<EPI, 0, false, EC>(p, stg, in, row0, nrows, col, b, lane);
     }
 }
 
@@ -540,31 +550,53 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //   empty[s]  both CTAs:   multicast tcgen05.commit from the leader frees the stage in both
 //   tfull[b]  both CTAs:   multicast commit when the accumulator of a tile is complete
 //   tempty[b] leader only: 8 arrivals (4 epilogue warps x 2 CTAs) before the MMA thread may overwrite buffer b
-struct PairLayout {
+// Two footprints of the same kernel (template parameter L):
+//   PairWide  one CTA per SM: 5 stages, TWO accumulator buffers (512 TMEM columns), 8 epilogue warps, 64-column passes.
+//             The epilogue paces this kernel at the model's shapes (K = 768: 3.5 us of MMA per 128 x 256 tile against 6-9 us
+//             of epilogue with four warps, profiles/gemm_timeline_r1f.txt), hence the second set of four epilogue warps.
+//   PairHalf  TWO CTAs per SM: 3 stages (96 KB), ONE accumulator buffer (256 TMEM columns), 4 epilogue warps, 32-column
+//             passes (16 KB of transpose buffers), <= 168 registers.  The step is a stream of small dependent GEMMs on several
+//             CUDA streams; with whole-SM CTAs every prologue, pipeline fill and epilogue of one launch keeps an SM's tensor core
+//             idle and a waiting kernel's CTAs out (profiles/timeline_r1_s5.txt).  At half footprint the second slot of every SM
+//             takes a CTA of another launch (the other chain, a weight-gradient product, or - with programmatic dependent launch -
+//             the prologue of the next kernel of the same stream), whose main loop runs under this CTA's prologue / epilogue.
+template <int STAGES_, int NACC_, int EPIW_, int EC_, int MINB_>
+struct PairLayoutT {
     static constexpr int BN_CTA = 128;                  // B rows loaded per CTA
     static constexpr int BN_TILE = 256;                 // accumulator columns per CTA
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN_CTA * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    // The epilogue paces this kernel at the model's shapes (K = 768: 3.5 us of MMA per 128 x 256 tile against 6-9 us of
-    // epilogue with four warps, profiles/gemm_timeline_r1f.txt), so the shared memory of one pipeline stage goes to the
-    // transpose buffers of a second set of four epilogue warps: 5 stages still cover the TMA round trip at 0.3 us per stage.
-    static constexpr int STAGES = 5;
+    static constexpr int STAGES = STAGES_;
+    static constexpr int NACC = NACC_;                  // accumulator buffers in tensor memory
+    static constexpr int EPI_WARPS = EPIW_;
+    static constexpr int EC = EC_;                      // columns per epilogue pass
+    static constexpr int MINB = MINB_;                  // CTAs per SM the footprint allows
+    static constexpr int THREADS = 64 + 32 * EPIW_;
     static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int EPI_BYTES = PAIR_EPI_WARPS * 32 * EPI_LD * 4;
+    static constexpr int EPI_BYTES = EPI_WARPS * 32 * EC * 4;
     static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
-    static constexpr int TMEM_COLS = 2 * BN_TILE;       // 512: two accumulator buffers
+    // alignment slack: the dynamic shared-memory window starts 1024-byte aligned in practice; the half footprint has no room
+    // for a kilobyte of slack (2 x 115,712 bytes per SM), so it keeps 64 bytes and the kernel traps if the base is misaligned
+    static constexpr int TOTAL = BAR_OFFSET + 256 + (MINB_ > 1 ? 64 : 1024);
+    static constexpr int TMEM_COLS = NACC * BN_TILE;
 };
+using PairLayout = PairLayoutT<5, 2, PAIR_EPI_WARPS, EPI_COLS, 1>;
+using PairHalf = PairLayoutT<3, 1, 4, 32, 2>;
+// 16 epilogue warps (four per scheduler) on 32-column passes: the fused epilogues are instruction-issue bound (ncu source page,
+// profiles/gemm_epilogue_r2.txt: dropout hashes, GELU, packing - not memory), and two warps per scheduler leave half of the issue
+// slots to dependency stalls; same shared-memory footprint as PairLayout (16 x 4 KB of transpose buffers), <= 113 registers.
+using PairWide16 = PairLayoutT<5, 2, 16, 32, 1>;
+static_assert(PairHalf::TOTAL <= 115712, "two CTAs of the half-footprint kernel must fit one SM (228 KB - 2 x 1 KB reserved)");
 
-template <bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(PAIR_THREADS, 1)
+template <bool A_MN, bool B_MN, int EPI, class L = PairLayout>
+__global__ void __launch_bounds__(L::THREADS, L::MINB)
 gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                        const GemmDev p) {
-    using L = PairLayout;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    if (L::MINB > 1 && smem_base != smem_u32(smem_raw)) __trap();      // no slack in the half footprint (see PairLayoutT::TOTAL)
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t bar_base = smem_base + L::BAR_OFFSET;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -587,9 +619,9 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < L::NACC; ++b) {
             mbar_init(tfull_bar(b), 1);
-            mbar_init(tempty_bar(b), 2 * PAIR_EPI_WARPS);   // one arrive per epilogue warp of both CTAs
+            mbar_init(tempty_bar(b), 2 * L::EPI_WARPS);     // one arrive per epilogue warp of both CTAs
         }
         fence_barrier_init();
     }
@@ -604,7 +636,11 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     if (threadIdx.x == 0) stamp(p, ST_CLK_PROLOGUE);
-    pdl_wait();                  // everything above overlapped the previous kernel of the stream; global memory from here on
+    // Everything above overlapped the previous kernel of the stream.  griddepcontrol.wait (pdl_wait) must precede the first access
+    // to memory that kernel may have written: every role waits below - except that the producer first requests the B tiles
+    // of its first pipeline stages when B is static (model weights), so that the pipeline fill runs under the predecessor's tail.
+    const bool b_early = p.b_static != 0 && (warp == 0 && lane == 0);
+    if (!b_early) pdl_wait();
 
     auto tile_coords = [&](int t, int& m0, int& n0, int& kb_begin, int& kb_end) {
         const int mb = t % p.mt;
@@ -620,6 +656,32 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
         if (lane == 0) {
+            auto load_b = [&](int stage, int kb, int nb0) {
+                const uint32_t sB = smem_base + stage * L::STAGE_BYTES + L::A_BYTES;
+                const bool second = kb >= p.kb1;
+                const CUtensorMap* mb = second ? &tmB2 : &tmB;
+                const int k0 = (second ? kb - p.kb1 : kb) * BK;
+                if (!B_MN) {
+                    tma_load_2d_2cta(sB, mb, full_bar(stage), k0, nb0);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < L::BN_CTA / 64; ++c)
+                        tma_load_2d_2cta(sB + c * (BK * 128), mb, full_bar(stage), nb0 + c * 64, k0);
+                }
+            };
+            int early = 0;      // stages of the FIRST tile whose barrier is armed and whose B half is already in flight
+            if (b_early) {
+                if (pair < num_tiles) {
+                    int m0, n0, kb_begin, kb_end;
+                    tile_coords(pair, m0, n0, kb_begin, kb_end);
+                    const int nb0 = n0 + (int)rank * L::BN_CTA;
+                    for (int kb = kb_begin; kb < kb_end && early < L::STAGES; ++kb, ++early) {
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar(early), 2 * L::STAGE_BYTES);   // fresh barriers: no empty wait
+                        load_b(early, kb, nb0);
+                    }
+                }
+                pdl_wait();
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int t = pair; t < num_tiles; t += npairs) {
@@ -627,13 +689,13 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 tile_coords(t, m0, n0, kb_begin, kb_end);
                 const int nb0 = n0 + (int)rank * L::BN_CTA;      // this CTA's half of the B tile
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const bool pre = early > 0;                  // this stage was armed (and its B requested) before the wait
+                    if (pre) --early;
+                    else mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sA = smem_base + stage * L::STAGE_BYTES;
-                    const uint32_t sB = sA + L::A_BYTES;
-                    if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
+                    if (!pre && rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
                     const bool second = kb >= p.kb1;
                     const CUtensorMap* ma = second ? &tmA2 : &tmA;
-                    const CUtensorMap* mb = second ? &tmB2 : &tmB;
                     const int k0 = (second ? kb - p.kb1 : kb) * BK;
                     if (!A_MN) {
                         tma_load_2d_2cta(sA, ma, full_bar(stage), k0, m0);
@@ -642,13 +704,7 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         for (int c = 0; c < BM / 64; ++c)
                             tma_load_2d_2cta(sA + c * (BK * 128), ma, full_bar(stage), m0 + c * 64, k0);
                     }
-                    if (!B_MN) {
-                        tma_load_2d_2cta(sB, mb, full_bar(stage), k0, nb0);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < L::BN_CTA / 64; ++c)
-                            tma_load_2d_2cta(sB + c * (BK * 128), mb, full_bar(stage), nb0 + c * 64, k0);
-                    }
+                    if (!pre) load_b(stage, kb, nb0);
                     if (t == pair && kb == kb_begin) stamp(p, ST_CLK_TMA0);
                     if (++stage == L::STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -666,8 +722,8 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 int m0, n0, kb_begin, kb_end;
                 tile_coords(t, m0, n0, kb_begin, kb_end);
                 if (kb_end <= kb_begin) continue;
-                const int ab = it & 1;
-                const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+                const int ab = it % L::NACC;
+                const uint32_t aph = (uint32_t)(it / L::NACC) & 1u;
                 ++it;
                 mbar_wait(tempty_bar(ab), aph ^ 1u);
                 tc_fence_after();
@@ -694,50 +750,51 @@ gemm_bf16_tcgen05_pair(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
         }
     } else {
-        // ===================== epilogue (8 warps in each CTA) =====================
-        // warp w reads TMEM lanes 32 (w % 4) .. +31 (hardware rule); warps 2-5 take the first half of the tile's column
-        // passes, warps 6-9 the second half
+        // ===================== epilogue (8 or 4 warps in each CTA) =====================
+        // warp w reads TMEM lanes 32 (w % 4) .. +31 (hardware rule); with 8 warps, warps 2-5 take the first half of the tile's
+        // column passes, warps 6-9 the second half
+        constexpr int EC = L::EC;
         const int quad = warp & 3;
         const int chalf = (warp - 2) >> 2;
-        constexpr int PASSES = L::BN_TILE / EPI_COLS / 2;       // column passes per warp
+        constexpr int PASSES = L::BN_TILE / EC / (L::EPI_WARPS / 4);       // column passes per warp
         const int c_first = chalf * PASSES;
-        float* stg = reinterpret_cast<float*>(smem_gen + L::EPI_OFFSET) + (warp - 2) * 32 * EPI_LD;
+        float* stg = reinterpret_cast<float*>(smem_gen + L::EPI_OFFSET) + (warp - 2) * 32 * EC;
         int it = 0;
         for (int t = pair; t < num_tiles; t += npairs) {
             int m0, n0, kb_begin, kb_end;
             tile_coords(t, m0, n0, kb_begin, kb_end);
             if (kb_end <= kb_begin) continue;
-            const int ab = it & 1;
-            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            const int ab = it % L::NACC;
+            const uint32_t aph = (uint32_t)(it / L::NACC) & 1u;
             ++it;
             const int row0 = m0 + quad * 32;
             const int nrows = min(32, p.M - row0);
             const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * L::BN_TILE);
-            EpiIn<EPI> cur;
-            cur.load(p, row0, nrows, n0 + c_first * EPI_COLS, lane);
+            EpiIn<EPI, EC> cur;
+            cur.load(p, row0, nrows, n0 + c_first * EC, lane);
             mbar_wait(tfull_bar(ab), aph);
             tc_fence_after();
             if (it == 1 && warp == 2 && lane == 0) stamp(p, ST_CLK_TFULL0);
 #pragma unroll 1
             for (int c = c_first; c < c_first + PASSES; ++c) {
-                if (c > c_first) cur.load(p, row0, nrows, n0 + c * EPI_COLS, lane);
-                uint32_t r[EPI_COLS];
-                tmem_ld32(tacc + (uint32_t)(c * EPI_COLS), r);
-                tmem_ld32(tacc + (uint32_t)(c * EPI_COLS + 32), r + 32);
+                if (c > c_first) cur.load(p, row0, nrows, n0 + c * EC, lane);
+                uint32_t r[EC];
+                tmem_ld32(tacc + (uint32_t)(c * EC), r);
+                if (EC > 32) tmem_ld32(tacc + (uint32_t)(c * EC + 32), r + 32);
                 tmem_ld_wait();
                 if (c == c_first + PASSES - 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(tempty_bar(ab));
                 }
-                const int col0 = n0 + c * EPI_COLS;
+                const int col0 = n0 + c * EC;
                 if (col0 >= p.N || nrows <= 0) continue;
 #pragma unroll
-                for (int q = 0; q < EPI_COLS / 4; ++q)
-                    *reinterpret_cast<float4*>(stg + stg_off(lane, q)) = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                                                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                for (int q = 0; q < EC / 4; ++q)
+                    *reinterpret_cast<float4*>(stg + stg_off<EC>(lane, q)) = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                                                       __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
                 __syncwarp();
-                epilogue_block<EPI>(p, stg, cur, row0, nrows, col0, lane);
+                epilogue_block<EPI, EC>(p, stg, cur, row0, nrows, col0, lane);
                 __syncwarp();
             }
             if (warp == 2 && lane == 0) stamp(p, it == 1 ? ST_CLK_EPI0 : ST_CLK_EPI_LAST);
@@ -810,6 +867,51 @@ inline GemmKernel pick_kernel_pair(int a_mn, int b_mn, int epi) {
     return nullptr;
 }
 
+// half-footprint CTA-pair kernels (two CTAs per SM): same (layout, epilogue) set
+inline GemmKernel pick_kernel_pair_half(int a_mn, int b_mn, int epi) {
+    if (!a_mn && !b_mn) {
+        switch (epi) {
+            case EPI_BF16: return gemm_bf16_tcgen05_pair<false, false, EPI_BF16, PairHalf>;
+            case EPI_ACT: return gemm_bf16_tcgen05_pair<false, false, EPI_ACT, PairHalf>;
+            case EPI_RES: return gemm_bf16_tcgen05_pair<false, false, EPI_RES, PairHalf>;
+            case EPI_F32: return gemm_bf16_tcgen05_pair<false, false, EPI_F32, PairHalf>;
+            default: return nullptr;
+        }
+    }
+    if (!a_mn && b_mn) {
+        switch (epi) {
+            case EPI_DACT: return gemm_bf16_tcgen05_pair<false, true, EPI_DACT, PairHalf>;
+            case EPI_RES: return gemm_bf16_tcgen05_pair<false, true, EPI_RES, PairHalf>;
+            case EPI_F32: return gemm_bf16_tcgen05_pair<false, true, EPI_F32, PairHalf>;
+            default: return nullptr;
+        }
+    }
+    if (a_mn && b_mn && epi == EPI_ACC) return gemm_bf16_tcgen05_pair<true, true, EPI_ACC, PairHalf>;
+    return nullptr;
+}
+
+inline GemmKernel pick_kernel_pair16(int a_mn, int b_mn, int epi) {
+    if (!a_mn && !b_mn) {
+        switch (epi) {
+            case EPI_BF16: return gemm_bf16_tcgen05_pair<false, false, EPI_BF16, PairWide16>;
+            case EPI_ACT: return gemm_bf16_tcgen05_pair<false, false, EPI_ACT, PairWide16>;
+            case EPI_RES: return gemm_bf16_tcgen05_pair<false, false, EPI_RES, PairWide16>;
+            case EPI_F32: return gemm_bf16_tcgen05_pair<false, false, EPI_F32, PairWide16>;
+            default: return nullptr;
+        }
+    }
+    if (!a_mn && b_mn) {
+        switch (epi) {
+            case EPI_DACT: return gemm_bf16_tcgen05_pair<false, true, EPI_DACT, PairWide16>;
+            case EPI_RES: return gemm_bf16_tcgen05_pair<false, true, EPI_RES, PairWide16>;
+            case EPI_F32: return gemm_bf16_tcgen05_pair<false, true, EPI_F32, PairWide16>;
+            default: return nullptr;
+        }
+    }
+    if (a_mn && b_mn && epi == EPI_ACC) return gemm_bf16_tcgen05_pair<true, true, EPI_ACC, PairWide16>;
+    return nullptr;
+}
+
 // true when pick_kernel_bn has a specialised kernel for this combination
 inline bool has_specialised(int a_mn, int b_mn, int epi) {
     if (epi == EPI_GENERIC) return true;
@@ -826,3 +928,5 @@ gemmk::GemmKernel gemm_pick_kernel_64(int a_mn, int b_mn, int epi);
 gemmk::GemmKernel gemm_pick_kernel_128(int a_mn, int b_mn, int epi);
 gemmk::GemmKernel gemm_pick_kernel_256(int a_mn, int b_mn, int epi);
 gemmk::GemmKernel gemm_pick_kernel_pair(int a_mn, int b_mn, int epi);   // gemm_inst_pair.cu
+gemmk::GemmKernel gemm_pick_kernel_pair_half(int a_mn, int b_mn, int epi);   // gemm_inst_pair_half.cu
+gemmk::GemmKernel gemm_pick_kernel_pair16(int a_mn, int b_mn, int epi);       // gemm_inst_pair16.cu

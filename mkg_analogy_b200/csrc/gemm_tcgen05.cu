@@ -71,6 +71,7 @@ struct GemmPlan {
     GemmKernel kernel;
     double flops;
     bool pair;      // CTA-pair kernel: launched as 2-CTA clusters
+    int threads;    // CTA size of the pair kernel (wide: 320, half footprint: 192)
 };
 
 int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
@@ -180,6 +181,7 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
     d.colsum_out = op.colsum_out; d.colsum_out2 = op.colsum_out2;
     d.drop = op.drop;
     { const char* e = getenv("B200MART_GEMM_DEBUG"); d.debug = e ? atoi(e) : 0; }
+    { static int be = -1; if (be < 0) { const char* e = getenv("B200MART_GEMM_BEARLY"); be = e ? atoi(e) : 1; } d.b_static = be ? op.b_static : 0; }
     int split = op.split_k;
     if (split > d.kb_total) split = d.kb_total;
     d.kb_per = (d.kb_total + split - 1) / split;
@@ -194,13 +196,26 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
     p->grid = dim3((unsigned)(tiles < cap ? tiles : cap), 1, 1);
     p->pair = pair;
     if (pair) {
+        // B200MART_GEMM_HALF=1: the half-footprint variant (two CTAs per SM; see PairLayoutT in gemm_kernel.cuh).
+        // B200MART_GEMM_HALF_SLOTS = CTAs per SM ONE launch may occupy (default 2: a launch with more tiles than SM pairs runs them
+        // side by side, the main loop of one under the epilogue of the other; 1 leaves the second slot to other launches).
+        static int half = -1, slots = -1;
+        if (half < 0) { const char* e = getenv("B200MART_GEMM_HALF"); half = e ? atoi(e) : 0; }
+        if (slots < 0) { const char* e = getenv("B200MART_GEMM_HALF_SLOTS"); slots = e ? atoi(e) : 2; if (slots < 1) slots = 1; if (slots > 2) slots = 2; }
+        const bool use_half = half && gemm_pick_kernel_pair_half(op.a_mn, op.b_mn, epi) != nullptr;
         d.mt = (op.M + 2 * BM - 1) / (2 * BM);
         d.nt = (op.N + PairLayout::BN_TILE - 1) / PairLayout::BN_TILE;
         const long ptiles = (long)d.mt * d.nt * split;
-        const long pairs = cap / 2;
+        long pairs = cap / 2;
+        if (use_half && !(op.max_ctas > 0 && op.max_ctas < num_sms()) && !(grid_cap() > 0)) pairs *= slots;
         p->grid = dim3((unsigned)(2 * (ptiles < pairs ? ptiles : pairs)), 1, 1);
-        p->kernel = gemm_pick_kernel_pair(op.a_mn, op.b_mn, epi);
-        p->smem = PairLayout::TOTAL;
+        static int epi16 = -1;      // B200MART_GEMM_EPI16: 16 epilogue warps (PairWide16); bitmask by epilogue kind, -1 = all
+        if (epi16 == -1) { const char* e = getenv("B200MART_GEMM_EPI16"); epi16 = e ? atoi(e) : 0; if (epi16 < 0) epi16 = 0xffff; }
+        const bool use16 = !use_half && ((epi16 >> epi) & 1) && gemm_pick_kernel_pair16(op.a_mn, op.b_mn, epi) != nullptr;
+        p->kernel = use_half ? gemm_pick_kernel_pair_half(op.a_mn, op.b_mn, epi)
+                             : (use16 ? gemm_pick_kernel_pair16(op.a_mn, op.b_mn, epi) : gemm_pick_kernel_pair(op.a_mn, op.b_mn, epi));
+        p->smem = use_half ? PairHalf::TOTAL : (use16 ? PairWide16::TOTAL : PairLayout::TOTAL);
+        p->threads = use_half ? PairHalf::THREADS : (use16 ? PairWide16::THREADS : PairLayout::THREADS);
     } else if (bn == 64) { p->kernel = gemm_pick_kernel_64(op.a_mn, op.b_mn, epi); p->smem = SmemLayout<64>::TOTAL; }
     else if (bn == 128) { p->kernel = gemm_pick_kernel_128(op.a_mn, op.b_mn, epi); p->smem = SmemLayout<128>::TOTAL; }
     else { p->kernel = gemm_pick_kernel_256(op.a_mn, op.b_mn, epi); p->smem = SmemLayout<256>::TOTAL; }
@@ -251,7 +266,7 @@ int gemm_plan_launch(const GemmPlan* p, cudaStream_t stream, const DropCfg* drop
         if (g_timeline) dev.prof = timeline_slot();
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = p->grid;
-        cfg.blockDim = dim3(PAIR_THREADS, 1, 1);
+        cfg.blockDim = dim3(p->threads, 1, 1);
         cfg.dynamicSmemBytes = (size_t)p->smem;
         cfg.stream = stream;
         cudaLaunchAttribute attr[2];

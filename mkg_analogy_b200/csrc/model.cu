@@ -328,6 +328,7 @@ int run_gemm(b200mart_handle* h, const GemmOp& op, cudaStream_t s) {
     key[k++] = (long)op.out_f32; key[k++] = op.ldo32; key[k++] = (long)op.out_bf16; key[k++] = op.ldo16;
     key[k++] = op.accumulate; key[k++] = op.split_k; key[k++] = op.bn; key[k++] = op.save_grad;
     key[k++] = (long)op.colsum_out; key[k++] = (long)op.colsum_out2; key[k++] = op.drop.thresh; key[k++] = op.max_ctas;
+    key[k++] = op.b_static;
     std::string ks(reinterpret_cast<const char*>(key), k * sizeof(long));
     auto it = h->plans.find(ks);
     GemmPlan* plan = nullptr;
@@ -414,6 +415,7 @@ struct Run {
         drop_next = DropCfg{0u, 0u, 1.f};
         op.out_f32 = out32; op.ldo32 = N; op.out_bf16 = out16; op.ldo16 = N;
         op.max_ctas = cap;
+        op.b_static = 1;     // B = weights from the bf16 mirror: last written by the previous step's optimizer
         return run_gemm(h, op, s);
     }
     // dX = dY W  [* act'(dact_src)] [+ residual].  dY (M, N) bf16, W (N, K) -> B operand stored [K=N][N=K] (MN-major)
@@ -428,6 +430,7 @@ struct Run {
         op.residual = residual; op.ldr = K;
         op.out_f32 = out32; op.ldo32 = K; op.out_bf16 = out16; op.ldo16 = K;
         op.max_ctas = cap;
+        op.b_static = 1;     // this layer's weights are only updated after both chains have left the layer
         return run_gemm(h, op, s);
     }
     // dW (N, K) += dY^T X ; db (N) += colsum(dY).   dY (M, N) bf16 with leading dimension ldy, X (M, K) bf16.
