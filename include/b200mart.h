@@ -114,6 +114,10 @@ int32_t b200mart_set_dropout(b200mart_handle* h, float p_hidden, float p_attn, u
 uint32_t b200mart_last_dropout_seed(const b200mart_handle* h);
 /* params16[i] = bf16(params32[i]) over the whole flat buffer */
 int32_t b200mart_cast_params(const b200mart_handle* h, const float* params32, void* params16, void* stream);
+/* the same over the flat range [begin, end): refreshes the mirror of parameters another rank's optimizer shard just delivered
+ * (reduce-scatter -> AdamW on the local shard -> all-gather of the fp32 masters) */
+int32_t b200mart_cast_params_range(const b200mart_handle* h, const float* params32, void* params16, int64_t begin, int64_t end,
+                                   void* stream);
 
 /* Workspace: activations saved for backward + scratch, for a batch of B samples x L text tokens. */
 int64_t b200mart_workspace_bytes(const b200mart_handle* h, int32_t B, int32_t L);

@@ -106,6 +106,7 @@ SYMBOLS = {
     "b200mart_param_info": (i32, [vp, i32, C.POINTER(C.c_char_p), C.POINTER(i64), C.POINTER(i32), C.POINTER(i64 * 4),
                                   C.POINTER(i32), C.POINTER(i32)]),
     "b200mart_cast_params": (i32, [vp, vp, vp, vp]),
+    "b200mart_cast_params_range": (i32, [vp, vp, vp, i64, i64, vp]),
     "b200mart_workspace_bytes": (i64, [vp, i32, i32]),
     "b200mart_forward": (i32, [vp, C.POINTER(Buffers), C.POINTER(Batch), vp, vp, vp]),
     "b200mart_head_loss": (i32, [vp, C.POINTER(Buffers), C.POINTER(Batch), C.POINTER(Head), vp, vp, vp, i32, vp]),

@@ -613,6 +613,14 @@ extern "C" int32_t b200mart_cast_params(const b200mart_handle* h, const float* p
     return launch_cast_bf16(p32, reinterpret_cast<bf16*>(p16), h->lay.total, (cudaStream_t)stream);
 }
 
+extern "C" int32_t b200mart_cast_params_range(const b200mart_handle* h, const float* p32, void* p16, int64_t begin, int64_t end,
+                                              void* stream) {
+    B2_CHECK(h && p32 && p16 && begin >= 0 && begin <= end && end <= h->lay.total, "cast_params_range: bad arguments [%ld, %ld)",
+             (long)begin, (long)end);
+    if (end == begin) return 0;
+    return launch_cast_bf16(p32 + begin, reinterpret_cast<bf16*>(p16) + begin, end - begin, (cudaStream_t)stream);
+}
+
 extern "C" int64_t b200mart_workspace_bytes(const b200mart_handle* h, int32_t B, int32_t L) {
     if (!h || B <= 0 || L <= 0) return 0;
     Workspace w;

@@ -152,6 +152,12 @@ class Engine:
         _lib.check(self.l.b200mart_cast_params(self.h, self.params32.data_ptr(), self.params16.data_ptr(), _lib.cur_stream()))
         self.mirror_stale = False
 
+    def cast_range(self, begin, end):
+        """bf16 mirror of params32[begin:end) (parameters delivered by another rank's optimizer shard)."""
+        if end > begin:
+            _lib.check(self.l.b200mart_cast_params_range(self.h, self.params32.data_ptr(), self.params16.data_ptr(), int(begin),
+                                                         int(end), _lib.cur_stream()))
+
     def zero_grad(self):
         self.grads32.zero_()
 

@@ -193,7 +193,8 @@ class FlavaKGC(PretrainedMixin, nn.Module):
         return new
 
     def forward(self, input_ids=None, pixel_values=None, attention_mask=None, token_type_ids=None, sep_idx=None, return_dict=None,
-                **unused):
+                output_logits=True, **unused):
+        """output_logits=False skips the dense (B, L, V) decoder product (the fused route scores the [MASK] rows only)."""
         fl = self.flava
         dev = fl.multimodal_model.cls_token.device
         ids = input_ids.to(dev)
@@ -206,5 +207,5 @@ class FlavaKGC(PretrainedMixin, nn.Module):
                            fl.text_to_mm_projection(txt)], dim=1)
         mm = fl.multimodal_model.layernorm(fl.multimodal_model.encoder(mm_in))
         trans = self.cls.transform(mm[:, -L:])
-        logits = F.linear(trans, self.cls.decoder.weight, self.cls.bias)
+        logits = F.linear(trans, self.cls.decoder.weight, self.cls.bias) if output_logits else None
         return MaskedLMOutput(logits=logits), trans

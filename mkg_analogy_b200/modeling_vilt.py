@@ -177,7 +177,8 @@ class ViltKGC(PretrainedMixin, nn.Module):
         return new
 
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, pixel_values=None, pixel_mask=None, sep_idx=None,
-                return_dict=None, **unused):
+                return_dict=None, output_logits=True, **unused):
+        """output_logits=False skips the dense (B, L, V) decoder product (the fused route scores the [MASK] rows only)."""
         if pixel_mask is not None and not bool(pixel_mask.all()):
             raise NotImplementedError("partial pixel masks are not part of the MarT path")
         emb = self.vilt.embeddings
@@ -201,5 +202,5 @@ class ViltKGC(PretrainedMixin, nn.Module):
         y = self.vilt.encoder(x, attention_mask=mask, sep_idx=sep, row_lo=img_length + 1)
         seq = self.vilt.layernorm(y)[:, :L]
         trans = self.mlm_score.transform(seq)
-        logits = F.linear(trans, self.mlm_score.decoder.weight, self.mlm_score.bias)
+        logits = F.linear(trans, self.mlm_score.decoder.weight, self.mlm_score.bias) if output_logits else None
         return MaskedLMOutput(logits=logits), trans

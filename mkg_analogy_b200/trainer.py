@@ -12,8 +12,8 @@ from .config import MKGformerConfig
 from .data import VocabLayout
 from .engine import Engine
 
-BATCH_KEYS = ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "sep_idx", "label", "rel_idx", "q_head_idx",
-              "a_head_idx", "pre_type")
+BATCH_KEYS = ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "pixel_idx", "sep_idx", "label", "rel_idx",
+              "q_head_idx", "a_head_idx", "pre_type")
 
 
 def linear_warmup_lr(step, total_steps, base_lr, warmup_ratio):
@@ -81,7 +81,7 @@ def init_weights_(engine: Engine, seed=0):
 class MartTrainer:
     def __init__(self, cfg: MKGformerConfig, vocab: VocabLayout, *, pretrain=False, lr=5e-5, weight_decay=0.01,
                  warmup_ratio=0.1, total_steps=1000, alpha=0.43, label_smoothing=0.1, device=None, process_group=None,
-                 grad_buckets=8, overlap_comm=True, dropout=True, seed=0, status_every=200):
+                 grad_buckets=8, overlap_comm=True, dropout=True, seed=0, status_every=200, shard_optimizer=True):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.cfg, self.vocab, self.pretrain = cfg, vocab, bool(pretrain)
@@ -100,6 +100,10 @@ class MartTrainer:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self.grad_buckets = grad_buckets
+        # N > 1: reduce-scatter -> AdamW on this rank's 1/N of each extent -> all-gather of the fp32 masters:
+        # same bytes on NVLink as the all-reduce it replaces, 1/N of the optimizer's HBM traffic per GPU
+        self.shard_optimizer = bool(shard_optimizer) and self.world > 1
+        self.rank = torch.distributed.get_rank(process_group) if self.world > 1 else 0
         self._dev_batch = None
         # training-mode dropout of the BERT stream (reference: hidden 0.1, attention 0.1); per-rank seed
         self.dropout = bool(dropout)
@@ -164,6 +168,32 @@ class MartTrainer:
         upd = self._update_stream if (self.world > 1 and update is not None) else comm
 
         def finish(b, e):
+            if self.shard_optimizer and update is not None and (e - b) % (8 * self.world) == 0:
+                # sharded update of the extent [b, e): this rank owns [sb, se)
+                S = (e - b) // self.world
+                sb, se = b + self.rank * S, b + (self.rank + 1) * S
+                dist.reduce_scatter_tensor(g[sb:se], g[b:e], op=dist.ReduceOp.AVG, group=self.pg)
+                ev = torch.cuda.Event()
+                ev.record(comm)
+                upd.wait_event(ev)
+                with torch.cuda.stream(upd):
+                    eng.adamw(update[0], update[1], weight_decay=self.weight_decay, pretrain=self.pretrain, begin=sb, end=se,
+                              zero_grads=True)
+                    if sb > b:
+                        g[b:sb].zero_()              # the other ranks' shards of the (consumed) local gradient
+                    if se < e:
+                        g[se:e].zero_()
+                    ev2 = torch.cuda.Event()
+                    ev2.record(upd)
+                comm.wait_event(ev2)
+                dist.all_gather_into_tensor(eng.params32[b:e], eng.params32[sb:se], group=self.pg)
+                ev3 = torch.cuda.Event()
+                ev3.record(comm)
+                upd.wait_event(ev3)
+                with torch.cuda.stream(upd):         # bf16 mirror of what the other ranks delivered (AdamW wrote this rank's part)
+                    eng.cast_range(b, sb)
+                    eng.cast_range(se, e)
+                return
             if self.world > 1:
                 dist.all_reduce(g[b:e], op=dist.ReduceOp.AVG, group=self.pg)
             if update is not None:
@@ -224,9 +254,29 @@ class MartTrainer:
             self.check_status()
         return loss
 
+    def attach_image_table(self, table):
+        """Serve `pixel_values` from a device-resident `EntityImageTable`: host batches then carry `pixel_idx`
+        (B, 2) int64 table rows (-1 = the all-zero "[PAD] image", as `MarsCollator(images="index")` produces) instead of 38.5 MB
+        of pixels; the gather runs on the training stream right before the step."""
+        self.image_table = table
+        self._px = {}
+
+    def _resolve_images(self, batch, slot=0):
+        if "pixel_idx" not in batch or "pixel_values" in batch:
+            return batch
+        if getattr(self, "image_table", None) is None:
+            raise ValueError("the batch carries pixel_idx: attach an EntityImageTable first (attach_image_table)")
+        idx = batch["pixel_idx"]
+        shape = (idx.shape[0], 2) + self.image_table.image_shape
+        if slot not in self._px or self._px[slot].shape != shape:
+            self._px[slot] = torch.empty(shape, device=self.device, dtype=torch.float32)
+        out = dict(batch)
+        out["pixel_values"] = self.image_table.gather(idx, out=self._px[slot])
+        return out
+
     def train_step_host(self, host_batch):
         """End-to-end step from (pinned) host tensors: H2D copies, step, D2H read of the loss. Returns a float."""
-        return float(self.train_step(self.to_device(host_batch)).item())
+        return float(self.train_step(self._resolve_images(self.to_device(host_batch))).item())
 
     def train_step_host_async(self, host_batch):
         """Pipelined end-to-end step (what a training loop with asynchronous logging does): this step's inputs are copied
@@ -243,7 +293,8 @@ class MartTrainer:
             self._n_async = 0
         k = self._n_async & 1
         main = torch.cuda.current_stream()
-        if self._stage[k] is None or any(self._stage[k][n].shape != v.shape for n, v in host_batch.items() if n in self._stage[k]):
+        keys = {n for n in host_batch if n in BATCH_KEYS}
+        if self._stage[k] is None or set(self._stage[k]) != keys or any(self._stage[k][n].shape != host_batch[n].shape for n in keys):
             self._stage[k] = {n: torch.empty(v.shape, dtype=v.dtype, device=self.device) for n, v in host_batch.items() if n in BATCH_KEYS}
             # The caching allocator may hand out blocks that tensors freed on the main stream used moments ago while work
             # reading / writing them is still queued there; the copy stream is not ordered behind that work.  One full
@@ -255,7 +306,7 @@ class MartTrainer:
             for n, d in self._stage[k].items():
                 d.copy_(host_batch[n], non_blocking=True)
         main.wait_stream(self._copy_stream)
-        loss = self.train_step(self._stage[k])
+        loss = self.train_step(self._resolve_images(self._stage[k], slot=k))
         self._stage_free[k] = torch.cuda.Event()
         self._stage_free[k].record(main)
         self._loss_host[k].copy_(loss, non_blocking=True)
@@ -275,7 +326,8 @@ class MartTrainer:
         return float(self._loss_host[k].item())
 
     def to_device(self, host_batch):
-        if self._dev_batch is None or any(self._dev_batch[k].shape != v.shape for k, v in host_batch.items() if k in self._dev_batch):
+        keys = {k for k in host_batch if k in BATCH_KEYS}
+        if self._dev_batch is None or set(self._dev_batch) != keys or any(self._dev_batch[k].shape != host_batch[k].shape for k in keys):
             self._dev_batch = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host_batch.items()
                                if k in BATCH_KEYS}
         for k, d in self._dev_batch.items():

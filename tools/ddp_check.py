@@ -43,16 +43,25 @@ scale = mean.abs().max().item()
 e_plain = (grads[False] - mean).abs().max().item()
 e_over = (grads[True] - mean).abs().max().item()
 assert e_plain <= 1e-5 * scale and e_over <= 2e-4 * scale, (e_plain, e_over, scale)   # atomics: summation order only
-# replicas stay identical through optimizer steps
-tr = MartTrainer(TINY, TINY_VOCAB, total_steps=100, overlap_comm=True)
-tr.engine.load(params)
-for step in range(3):
-    b = {k: v.cuda() for k, v in make_finetune_batch(4, 24, TINY.image_size, TINY_VOCAB, seed=shard_seed(50, rank, step), min_len=16).items()}
-    tr.train_step(b)
-torch.cuda.synchronize()
-p0 = tr.engine.params32.clone()
-dist.broadcast(p0, src=0)
-assert torch.equal(p0, tr.engine.params32), "replicas diverged"
+# replicas stay identical through optimizer steps, with the sharded optimizer (reduce-scatter -> shard AdamW -> all-gather) and
+# with the replicated one (all-reduce -> full AdamW); both give the same parameters (summation order of the collective aside)
+final = {}
+for shard in (True, False):
+    tr = MartTrainer(TINY, TINY_VOCAB, total_steps=100, lr=1e-3, overlap_comm=True, shard_optimizer=shard, dropout=False)
+    tr.engine.load(params)
+    for step in range(3):
+        b = {k: v.cuda() for k, v in make_finetune_batch(4, 24, TINY.image_size, TINY_VOCAB, seed=shard_seed(50, rank, step), min_len=16).items()}
+        tr.train_step(b)
+    torch.cuda.synchronize()
+    p0 = tr.engine.params32.clone()
+    dist.broadcast(p0, src=0)
+    assert torch.equal(p0, tr.engine.params32), f"replicas diverged (shard_optimizer={shard})"
+    assert torch.equal(tr.engine.params16.float(), tr.engine.params32.bfloat16().float()), "bf16 mirror out of date"
+    assert tr.engine.grads32.abs().max().item() == 0.0, "gradients not cleared"
+    final[shard] = tr.engine.params32.clone()
+d = (final[True] - final[False]).abs()
+assert d.max().item() <= 2 * 3 * 1e-3 + 1e-6 and d.mean().item() <= 2e-5, (d.max().item(), d.mean().item())
 if rank == 0:
-    print(f"ddp_check ok: world {world}, plain err {e_plain:.2e}, overlapped err {e_over:.2e} (scale {scale:.2e})")
+    print(f"ddp_check ok: world {world}, plain err {e_plain:.2e}, overlapped err {e_over:.2e} (scale {scale:.2e}); "
+          f"sharded vs replicated optimizer: max |dp| {d.max().item():.2e}, mean {d.mean().item():.2e}")
 dist.destroy_process_group()
