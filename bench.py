@@ -57,8 +57,7 @@ def config_dict(name, n_gpus, extra=None):
          "image": "2x3x384x384" if name == "vilt" else "2x3x224x224",
          "score_head": "entity (11292) + relation (192) column groups of a 42007-token vocab" if name == "vilt"
          else "2063 analogy entities of a 42007-token vocab",
-         "parallelism": f"dp{n_gpus}" + ("" if n_gpus == 1 else " (per layer extent: reduce-scatter of the fp32 gradients -> AdamW on the rank's "
-                                         "1/N shard -> all-gather of the fp32 masters, pipelined behind backward)"),
+         "parallelism": f"dp{n_gpus}",
          "optimizer": "AdamW per layer extent, pipelined behind the backward of the layers below",
          "dropout": "hidden 0.1 / attention 0.1 (BERT stream, as the reference trains)" if name in ("base", "large") else "off (HF defaults of the family)",
          "l2": "per-step working set (bf16 weights + >1 GB activations) exceeds the 126 MB L2; 4 rotating batches"}
@@ -234,7 +233,12 @@ def run_mkgformer(args):
     Bp, L = w["B"], w["L"]
     K, W = args.steps, max(args.warmup, 3)
     trainer = MartTrainer(cfg, MARS_VOCAB, total_steps=10 * (K + W) * 4, device=dev, overlap_comm=not args.no_overlap,
-                          shard_optimizer=not args.no_shard)
+                          shard_optimizer=args.shard, multicast=False if args.no_multicast else None)
+    exchange = "none (1 GPU)" if world == 1 else (
+        "NVSwitch multicast: per layer extent ONE kernel = multimem.ld_reduce of the rank's gradient shard + AdamW + multimem.st of the "
+        "new fp32 / bf16 parameters to every replica (no collective library on the path)" if trainer._mc is not None else
+        ("NCCL reduce-scatter -> AdamW on the rank's shard -> NCCL all-gather, per layer extent" if trainer.shard_optimizer else
+         "NCCL mean all-reduce per layer extent, replicated AdamW"))
     init_weights_(trainer.engine, seed=0)                     # identical replicas on every rank
     nb = 4
     host = [make_finetune_batch(Bp, L, cfg.image_size, MARS_VOCAB, seed=1234 + rank * 100 + i) for i in range(nb)]
@@ -363,7 +367,8 @@ def run_mkgformer(args):
     if rank == 0:
         line = {"metric": w["metric"], "value": Bp * world * K / (ms_total * 1e-3), "unit": "examples/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_dict(name, world),
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": config_dict(name, world, {"parallelism": f"dp{world}", "gradient_exchange": exchange}),
                 "clocks": clocks, "gpu_launches": int(launches), "final_loss": loss_val,
                 "e2e": {"value": e2e_rate, "unit": "examples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "api": "MartTrainer.train_step_host_async (pinned host batch in: ids / masks / labels + (B, 2) rows of the "
@@ -528,7 +533,8 @@ def main():
     ap.add_argument("--config", default="base", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / gpu_eager_baseline legs (profiling runs)")
     ap.add_argument("--no-overlap", action="store_true", help="run the gradient exchange / AdamW after backward instead of pipelined per layer")
-    ap.add_argument("--no-shard", action="store_true", help="N > 1: all-reduce + replicated AdamW instead of reduce-scatter + sharded AdamW + all-gather")
+    ap.add_argument("--shard", action="store_true", help="N > 1, NCCL route: reduce-scatter + sharded AdamW + all-gather instead of all-reduce + replicated AdamW")
+    ap.add_argument("--no-multicast", action="store_true", help="N > 1: exchange through NCCL instead of the fused NVSwitch-multicast optimizer kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -200,10 +200,27 @@ int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* params16, floa
                        float* exp_avg_sq, int32_t step, float lr, float beta1, float beta2, float eps,
                        float weight_decay, int32_t pretrain, int64_t begin, int64_t end, int32_t zero_grads, void* stream);
 
+/* The optimizer step with the data-parallel exchange fused in, over NVSwitch multicast (one kernel = reduce-scatter + AdamW +
+ * all-gather): for this rank's shard [begin, end) the mean gradient is pulled with multimem.ld_reduce from grads_mc (multicast
+ * address of the symmetric gradient buffers, every rank's local gradients complete), AdamW runs on the rank's own masters /
+ * moments, and the new fp32 parameters and their bf16 mirror are stored through multimem.st to params32_mc / params16_mc
+ * (multicast addresses of the symmetric parameter buffers): every replica receives the same bits.  The caller runs a cross-rank
+ * barrier before the call (every rank's local gradients of the range are complete) and one after it (every shard has been read:
+ * each rank may now clear its own gradient replica; every new parameter has been delivered). */
+int32_t b200mart_adamw_multicast(b200mart_handle* h, const float* params32, float* exp_avg, float* exp_avg_sq,
+                                 float* grads_mc, float* params32_mc, void* params16_mc, int32_t step, float lr,
+                                 float beta1, float beta2, float eps, float weight_decay, int32_t pretrain, int64_t begin,
+                                 int64_t end, int32_t world, void* stream);
+
 /* Device-side status flags of the last calls on this workspace (synchronises the stream):
  * bit0 token id out of range, bit1 token type out of range, bit2 a row without exactly one [MASK], bit3 a label or a
  * relaxation-loss position out of range (the reference raises IndexError / asserts in these cases). */
 int32_t b200mart_status(b200mart_handle* h, const b200mart_buffers* bufs, void* stream, int32_t* flags_out);
+
+/* NVSwitch multicast reduction (data-parallel gradient exchange without a collective library): mc_dst is the MULTICAST address
+ * of a buffer replicated on every GPU of the group (CUDA multicast object / torch symmetric memory); every replica receives
+ * mc_dst[i] += scale * src[i] (multimem.red.add.v4.f32: one send per GPU, reduced in the switch).  n % 4 == 0, 16-byte aligned. */
+int32_t b200mart_multimem_add(const float* src, float* mc_dst, int64_t n, float scale, void* stream);
 
 /* Layer-by-layer parity hook (what `output_hidden_states=True` gives for the reference, modeling_unimo.py:603-647): copies the
  * fp32 residual stream saved by the last b200mart_forward on this workspace into `out`.  stream_kind 0 = text hidden state

@@ -607,6 +607,78 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
     }
 }
 
+// AdamW over this rank's shard of a flat range with the data-parallel exchange fused in, over NVSwitch multicast:
+//   gradient  = mean over the ranks, pulled with multimem.ld_reduce.add from the multicast address of the (symmetric)
+//               gradient buffers - the switch reads the element from every replica and returns the sum: the reduce-scatter;
+//   update    = torch.optim.AdamW on the rank's own fp32 master / exp_avg / exp_avg_sq (1/N of the optimizer's HBM traffic);
+//   broadcast = the new fp32 parameter and its bf16 mirror leave through multimem.st on the multicast addresses of the
+//               (symmetric) parameter buffers - one send per rank, replicated by the switch: the all-gather.
+// Every element is reduced once, by one rank, and the same bits are stored in every replica: replicas stay identical.
+// The caller brackets the launch with two cross-rank barriers (gradients complete before / all reads done after).
+__device__ __forceinline__ float4 mc_ld_reduce4(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st4(float* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mc_st2(void* mc, float a, float b) {     // 8 bytes of payload (four packed bf16)
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc), "f"(a), "f"(b) : "memory");
+}
+constexpr int MCQ = 8;     // 16-byte multimem.ld_reduce requests in flight per thread
+constexpr int MCT = 1024;  // threads per CTA: 128 KB of gradient requests in flight per SM the kernel occupies
+__global__ void __launch_bounds__(MCT, 1) adamw_mc_kernel(const float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float* g_mc,
+                                float* p_mc, bf16* p16_mc, const AdamSeg* __restrict__ segs, int nseg, long begin, long n,
+                                float inv_world, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2) {
+  // bounded persistent grid (the exchange is NVLink-latency bound, not HBM bound: a few CTAs with deep request queues keep the
+  // link busy and leave the SMs to the backward pass, the way a collective library bounds its channels)
+  for (long chunk = blockIdx.x; begin + chunk * (4L * MCT * MCQ) < n; chunk += gridDim.x) {
+    const long base = begin + chunk * (4L * MCT * MCQ);
+    // all MCQ gradient quads of the thread are requested before any is used: the NVLink round trip (~4 us) is paid once
+    float4 gq[MCQ];
+    bool live[MCQ];
+#pragma unroll
+    for (int it = 0; it < MCQ; ++it) {
+        const long i = base + ((long)it * blockDim.x + threadIdx.x) * 4;
+        live[it] = i < n;
+        if (live[it]) gq[it] = mc_ld_reduce4(g_mc + i);
+    }
+#pragma unroll
+    for (int it = 0; it < MCQ; ++it) {
+        const long i = base + ((long)it * blockDim.x + threadIdx.x) * 4;
+        if (!live[it]) continue;
+        float4 gv = gq[it];
+        // (clearing the consumed gradients through multimem.st as well was measured and rejected: another 4 bytes per parameter
+        //  on NVLink; every rank clears its own replica with a local memset after the closing barrier of the extent instead)
+        int lo = 0, hi = nseg - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (segs[mid].end <= i) lo = mid + 1; else hi = mid;
+        }
+        const AdamSeg sg = segs[lo];
+        if (sg.skip || i < sg.begin) continue;            // never-updated parameters: identical on every replica already
+        gv.x *= inv_world; gv.y *= inv_world; gv.z *= inv_world; gv.w *= inv_world;
+        float4 pv = ld4(p + i), mv = ld4(m + i), vv = ld4(v + i);
+        const float decay = sg.decay ? (1.0f - lr * wd) : 1.0f;
+        const float step = lr / bc1;
+        const float inv_sqrt_bc2 = rsqrtf(bc2);
+#define ADAM1(P, G, Mm, Vv)                                                   \
+    P *= decay; Mm = b1 * Mm + (1.0f - b1) * G; Vv = b2 * Vv + (1.0f - b2) * G * G; \
+    P -= step * Mm / (sqrtf(Vv) * inv_sqrt_bc2 + eps);
+        ADAM1(pv.x, gv.x, mv.x, vv.x)
+        ADAM1(pv.y, gv.y, mv.y, vv.y)
+        ADAM1(pv.z, gv.z, mv.z, vv.z)
+        ADAM1(pv.w, gv.w, mv.w, vv.w)
+#undef ADAM1
+        st4(m + i, mv); st4(v + i, vv);
+        mc_st4(p_mc + i, pv);
+        mc_st2(p16_mc + i, __uint_as_float(pack_bf16x2(pv.x, pv.y)), __uint_as_float(pack_bf16x2(pv.z, pv.w)));
+    }
+  }
+}
+
 // ---------------------------------------------------------------- entity-image table gather (collator replacement)
 // out[i] = table[idx[i]] (one preprocessed image per entity, fp32 or bf16 storage), zeros for idx < 0 ("[PAD] image",
 // MarT/data/data_module.py:141-142).  One CTA row per image, 16-byte accesses; an index >= n_entities sets status bit 16
@@ -645,6 +717,25 @@ inline int blocks_for(long n, int per_block, int cap = 148 * 16) {
 
 int launch_cast_bf16(const float* src, bf16* dst, long n, cudaStream_t s) {
     cast_bf16_kernel<<<blocks_for(n, 256 * 8), 256, 0, s>>>(src, dst, n);
+    B2_LAUNCHED();
+    return 0;
+}
+// every replica of the multicast buffer: dst[i] += scale * src[i]  (reduced in the NVSwitch)
+__global__ void multimem_add_kernel(const float* __restrict__ src, float* mc_dst, long n4, float scale) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (; i < n4; i += stride) {
+        const float4 v = ld4(src + 4 * i);
+        asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_dst + 4 * i), "f"(v.x * scale),
+                     "f"(v.y * scale), "f"(v.z * scale), "f"(v.w * scale)
+                     : "memory");
+    }
+}
+int launch_multimem_add(const float* src, float* mc_dst, long n, float scale, cudaStream_t s) {
+    B2_CHECK(n % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(mc_dst) & 15) == 0,
+             "multimem_add: n %ld must be a multiple of 4 and the buffers 16-byte aligned", n);
+    if (n == 0) return 0;
+    multimem_add_kernel<<<blocks_for(n / 4, 1024), 256, 0, s>>>(src, mc_dst, n / 4, scale);
     B2_LAUNCHED();
     return 0;
 }
@@ -800,6 +891,20 @@ int launch_scatter_add_f32(const float* src, const int64_t* idx, float* dst, int
     B2_LAUNCHED();
     return 0;
 }
+int launch_adamw_mc(const float* p, float* m, float* v, float* g_mc, float* p_mc, bf16* p16_mc, const AdamSeg* segs_dev,
+                    int nseg, long begin, long end, float inv_world, float lr, float b1, float b2, float eps, float wd, float bc1,
+                    float bc2, cudaStream_t s) {
+    B2_CHECK(begin % 8 == 0 && end % 8 == 0 && begin < end, "adamw_mc: range [%ld, %ld) must be non-empty and 8-aligned", begin, end);
+    long blocks = (end - begin + 4L * MCT * MCQ - 1) / (4L * MCT * MCQ);
+    static int cap = -1;       // B200MART_MC_CTAS: bound of the grid (0 = one block per 32768 elements)
+    if (cap < 0) { const char* e = getenv("B200MART_MC_CTAS"); cap = e ? atoi(e) : 32; if (cap < 0) cap = 0; }
+    if (cap > 0 && blocks > cap) blocks = cap;
+    adamw_mc_kernel<<<(unsigned)blocks, MCT, 0, s>>>(p, m, v, g_mc, p_mc, p16_mc, segs_dev, nseg, begin, end, inv_world, lr, b1, b2,
+                                                    eps, wd, bc1, bc2);
+    B2_LAUNCHED();
+    return 0;
+}
+
 int launch_adamw(float* p, float* g, float* m, float* v, bf16* p16, const AdamSeg* segs_dev, int nseg, long begin, long end,
                  int zero_grads, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, cudaStream_t s) {
     B2_CHECK(begin % 8 == 0 && end % 8 == 0 && begin < end, "adamw: range [%ld, %ld) must be non-empty and 8-aligned", begin, end);

@@ -5,6 +5,7 @@
 
 // ---- elementwise.cu
 int launch_cast_bf16(const float* src, bf16* dst, long n, cudaStream_t s);
+int launch_multimem_add(const float* src, float* mc_dst, long n, float scale, cudaStream_t s);
 int launch_fill_f32(float* dst, float v, long n, cudaStream_t s);
 int launch_axpy_f32(const float* src, float* dst, long n, cudaStream_t s);   // dst += src
 int launch_cast_pad_bf16(const float* src, long ld_src, bf16* dst, long ld_dst, int rows, int cols, cudaStream_t s);
@@ -49,6 +50,11 @@ struct AdamSeg { long begin, end; int decay; int skip; };
 // over the flat range [begin, end); zero_grads: clear g after use
 int launch_adamw(float* p, float* g, float* m, float* v, bf16* p16, const AdamSeg* segs_dev, int nseg, long begin, long end,
                  int zero_grads, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, cudaStream_t s);
+
+// the same on this rank's shard with the exchange fused in (multimem.ld_reduce of the gradients, multimem.st of the result)
+int launch_adamw_mc(const float* p, float* m, float* v, float* g_mc, float* p_mc, bf16* p16_mc, const AdamSeg* segs_dev,
+                    int nseg, long begin, long end, float inv_world, float lr, float b1, float b2, float eps, float wd, float bc1,
+                    float bc2, cudaStream_t s);
 
 // entity-image table gather (collator replacement, MarT/data/data_module.py:127-160): out[i] = table[idx[i]], zeros for idx < 0
 int launch_gather_images(const void* table, int table_is_bf16, const int64_t* idx, float* out, int n_images, long image_elems,

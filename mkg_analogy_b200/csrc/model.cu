@@ -621,6 +621,11 @@ extern "C" int32_t b200mart_cast_params_range(const b200mart_handle* h, const fl
     return launch_cast_bf16(p32 + begin, reinterpret_cast<bf16*>(p16) + begin, end - begin, (cudaStream_t)stream);
 }
 
+extern "C" int32_t b200mart_multimem_add(const float* src, float* mc_dst, int64_t n, float scale, void* stream) {
+    B2_CHECK(src && mc_dst && n >= 0, "multimem_add: bad arguments");
+    return launch_multimem_add(src, mc_dst, (long)n, scale, (cudaStream_t)stream);
+}
+
 extern "C" int64_t b200mart_workspace_bytes(const b200mart_handle* h, int32_t B, int32_t L) {
     if (!h || B <= 0 || L <= 0) return 0;
     Workspace w;
@@ -1059,6 +1064,24 @@ extern "C" int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* par
     const float bc1 = (float)bc1d, bc2 = (float)bc2d;
     return launch_adamw(params32, grads32, exp_avg, exp_avg_sq, reinterpret_cast<bf16*>(params16), h->segs_dev[mode],
                         h->nseg, begin, end, zero_grads, lr, beta1, beta2, eps, weight_decay, bc1, bc2, (cudaStream_t)stream);
+}
+
+extern "C" int32_t b200mart_adamw_multicast(b200mart_handle* h, const float* params32, float* exp_avg, float* exp_avg_sq,
+                                            float* grads_mc, float* params32_mc, void* params16_mc, int32_t step, float lr,
+                                            float beta1, float beta2, float eps, float weight_decay, int32_t pretrain, int64_t begin,
+                                            int64_t end, int32_t world, void* stream) {
+    B2_CHECK(h && params32 && exp_avg && exp_avg_sq && grads_mc && params32_mc && params16_mc && step >= 1 && world >= 1,
+             "adamw_multicast: bad arguments");
+    B2_CHECK(begin >= 0 && begin < end && end <= h->lay.total, "adamw_multicast: bad range [%ld, %ld)", (long)begin, (long)end);
+    const int mode = pretrain ? 1 : 0;
+    if (!h->segs_dev[mode]) {
+        CUDA_TRY(cudaMalloc(&h->segs_dev[mode], sizeof(AdamSeg) * h->nseg));
+        CUDA_TRY(cudaMemcpy(h->segs_dev[mode], h->segs_host[mode].data(), sizeof(AdamSeg) * h->nseg, cudaMemcpyHostToDevice));
+    }
+    const double bc1d = 1.0 - pow((double)beta1, (double)step), bc2d = 1.0 - pow((double)beta2, (double)step);
+    return launch_adamw_mc(params32, exp_avg, exp_avg_sq, grads_mc, params32_mc, reinterpret_cast<bf16*>(params16_mc), h->segs_dev[mode],
+                           h->nseg, begin, end, 1.0f / (float)world, lr, beta1, beta2, eps, weight_decay, (float)bc1d, (float)bc2d,
+                           (cudaStream_t)stream);
 }
 
 // --------------------------------------------------------------------------------------- profiling

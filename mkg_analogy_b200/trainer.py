@@ -81,7 +81,7 @@ def init_weights_(engine: Engine, seed=0):
 class MartTrainer:
     def __init__(self, cfg: MKGformerConfig, vocab: VocabLayout, *, pretrain=False, lr=5e-5, weight_decay=0.01,
                  warmup_ratio=0.1, total_steps=1000, alpha=0.43, label_smoothing=0.1, device=None, process_group=None,
-                 grad_buckets=8, overlap_comm=True, dropout=True, seed=0, status_every=200, shard_optimizer=True):
+                 grad_buckets=8, overlap_comm=True, dropout=True, seed=0, status_every=200, shard_optimizer=False, multicast=None):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.cfg, self.vocab, self.pretrain = cfg, vocab, bool(pretrain)
@@ -100,10 +100,25 @@ class MartTrainer:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self.grad_buckets = grad_buckets
-        # N > 1: reduce-scatter -> AdamW on this rank's 1/N of each extent -> all-gather of the fp32 masters:
-        # same bytes on NVLink as the all-reduce it replaces, 1/N of the optimizer's HBM traffic per GPU
+        # N > 1, NCCL route, optional: reduce-scatter -> AdamW on this rank's 1/N of each extent -> all-gather of the fp32 masters
+        # (SURVEY.md §8 f1).  Measured on B200 (profiles/scaling_r2.txt): slower than all-reduce + replicated AdamW at N = 2 and
+        # N = 8 (three dependent stages per extent on the exchange stream), so off by default; the fused multicast kernel below is
+        # the sharded optimizer that pays.
         self.shard_optimizer = bool(shard_optimizer) and self.world > 1
         self.rank = torch.distributed.get_rank(process_group) if self.world > 1 else 0
+        # NVSwitch multicast exchange (default for N >= 3 when the box supports it; B200MART_MULTICAST=1 / 0 or multicast=True /
+        # False force it on / off): gradients, fp32 masters and the bf16 mirror live in symmetric memory; ONE kernel per layer
+        # extent pulls the mean gradient of the rank's shard with multimem.ld_reduce, applies AdamW and stores the result in every
+        # replica with multimem.st.  Measured (profiles/scaling_r2.txt): 8 GPUs 8.86 ms / step against 9.54 ms with NCCL
+        # all-reduce; 2 GPUs 8.52 against 8.33 ms, hence the N >= 3 default.
+        self._mc = None
+        self._mc_prev = None
+        if multicast is None:
+            import os
+            env = os.environ.get("B200MART_MULTICAST")
+            multicast = (self.world >= 3) if env is None else (env != "0")
+        if multicast and self.world > 1 and overlap_comm:
+            self._setup_multicast()
         self._dev_batch = None
         # training-mode dropout of the BERT stream (reference: hidden 0.1, attention 0.1); per-rank seed
         self.dropout = bool(dropout)
@@ -126,6 +141,32 @@ class MartTrainer:
             self._extents = self.engine.layer_extents()
             self.engine.exp_avg = torch.zeros_like(self.engine.params32)
             self.engine.exp_avg_sq = torch.zeros_like(self.engine.params32)
+
+    def _setup_multicast(self):
+        """Re-home grads32 / params32 / params16 in torch symmetric memory and fetch their multicast addresses.  Any failure
+        (no NVSwitch multicast on this box, old driver) leaves the NCCL path in place."""
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            eng, group = self.engine, (self.pg if self.pg is not None else dist.group.WORLD)
+            out = {}
+            for name in ("grads32", "params32", "params16"):
+                old = getattr(eng, name)
+                t = symm_mem.empty(old.numel(), dtype=old.dtype, device=self.device)
+                t.copy_(old)
+                hdl = symm_mem.rendezvous(t, group=group)
+                if not hdl.multicast_ptr:
+                    raise RuntimeError("no multicast address (NVSwitch multicast unavailable)")
+                out[name] = (t, hdl)
+            for name, (t, _) in out.items():
+                setattr(eng, name, t)
+            eng.ws_key = None
+            self._mc = {k: h for k, (_, h) in out.items()}
+            torch.cuda.synchronize(self.device)
+        except Exception as e:      # noqa: BLE001
+            import warnings
+            warnings.warn(f"NVSwitch multicast exchange unavailable ({type(e).__name__}: {e}); using NCCL")
+            self._mc = None
 
     # ------------------------------------------------------------------ pieces
     def _head(self, batch):
@@ -168,6 +209,22 @@ class MartTrainer:
         upd = self._update_stream if (self.world > 1 and update is not None) else comm
 
         def finish(b, e):
+            if self._mc is not None and update is not None and (e - b) % (8 * self.world) == 0:
+                # fused exchange + update of the extent [b, e) over NVSwitch multicast; this rank owns [sb, se)
+                S = (e - b) // self.world
+                sb, se = b + self.rank * S, b + (self.rank + 1) * S
+                hg = self._mc["grads32"]
+                # ONE barrier per extent: every rank's local gradients of this extent are complete - and, because every rank
+                # queued it behind its fused kernel of the PREVIOUS extent, every shard of that extent has been read and its new
+                # parameters delivered: the previous extent's gradient replica can be cleared locally
+                hg.barrier(channel=0)
+                if self._mc_prev is not None:
+                    g[self._mc_prev[0]:self._mc_prev[1]].zero_()
+                eng.adamw_multicast(update[0], update[1], hg.multicast_ptr, self._mc["params32"].multicast_ptr,
+                                    self._mc["params16"].multicast_ptr, self.world, sb, se, weight_decay=self.weight_decay,
+                                    pretrain=self.pretrain)
+                self._mc_prev = (b, e)
+                return
             if self.shard_optimizer and update is not None and (e - b) % (8 * self.world) == 0:
                 # sharded update of the extent [b, e): this rank owns [sb, se)
                 S = (e - b) // self.world
@@ -218,6 +275,10 @@ class MartTrainer:
                 if e0 > b0:
                     for b, e in bucket_bounds(e0 - b0, self._tail_chunks):
                         finish(b0 + b, b0 + e)
+            if self._mc is not None and self._mc_prev is not None:      # closing barrier of the step (see finish)
+                self._mc["grads32"].barrier(channel=0)
+                g[self._mc_prev[0]:self._mc_prev[1]].zero_()
+                self._mc_prev = None
         if upd is not comm:
             main.wait_stream(upd)
         main.wait_stream(comm)

@@ -19,7 +19,7 @@ batch = {k: v.cuda() for k, v in make_finetune_batch(4, 24, TINY.image_size, TIN
 
 grads = {}
 for overlap in (False, True):
-    tr = MartTrainer(TINY, TINY_VOCAB, total_steps=100, overlap_comm=overlap, dropout=False)
+    tr = MartTrainer(TINY, TINY_VOCAB, total_steps=100, overlap_comm=overlap, dropout=False, multicast=False)
     tr.engine.load(params)
     eng = tr.engine
     mb = tr._model_inputs(batch)
@@ -46,8 +46,13 @@ assert e_plain <= 1e-5 * scale and e_over <= 2e-4 * scale, (e_plain, e_over, sca
 # replicas stay identical through optimizer steps, with the sharded optimizer (reduce-scatter -> shard AdamW -> all-gather) and
 # with the replicated one (all-reduce -> full AdamW); both give the same parameters (summation order of the collective aside)
 final = {}
-for shard in (True, False):
-    tr = MartTrainer(TINY, TINY_VOCAB, total_steps=100, lr=1e-3, overlap_comm=True, shard_optimizer=shard, dropout=False)
+modes = {"multicast": dict(multicast=True), True: dict(multicast=False, shard_optimizer=True), False: dict(multicast=False, shard_optimizer=False)}
+for shard, kw in modes.items():
+    tr = MartTrainer(TINY, TINY_VOCAB, total_steps=100, lr=1e-3, overlap_comm=True, dropout=False, **kw)
+    if shard == "multicast" and tr._mc is None:
+        if rank == 0:
+            print("multicast exchange unavailable on this box: skipped")
+        continue
     tr.engine.load(params)
     for step in range(3):
         b = {k: v.cuda() for k, v in make_finetune_batch(4, 24, TINY.image_size, TINY_VOCAB, seed=shard_seed(50, rank, step), min_len=16).items()}
@@ -61,6 +66,11 @@ for shard in (True, False):
     final[shard] = tr.engine.params32.clone()
 d = (final[True] - final[False]).abs()
 assert d.max().item() <= 2 * 3 * 1e-3 + 1e-6 and d.mean().item() <= 2e-5, (d.max().item(), d.mean().item())
+if "multicast" in final:
+    dm = (final["multicast"] - final[False]).abs()
+    assert dm.max().item() <= 2 * 3 * 1e-3 + 1e-6 and dm.mean().item() <= 2e-5, (dm.max().item(), dm.mean().item())
+    if rank == 0:
+        print(f"multicast (multimem.ld_reduce + AdamW + multimem.st) vs replicated NCCL: max |dp| {dm.max().item():.2e}, mean {dm.mean().item():.2e}")
 if rank == 0:
     print(f"ddp_check ok: world {world}, plain err {e_plain:.2e}, overlapped err {e_over:.2e} (scale {scale:.2e}); "
           f"sharded vs replicated optimizer: max |dp| {d.max().item():.2e}, mean {d.mean().item():.2e}")

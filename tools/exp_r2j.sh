@@ -1,0 +1,11 @@
+#!/bin/bash
+# N GPUs (N = $1): the three exchange modes
+N=$1
+mkdir -p gpurun_out
+run() { tag=$1; shift; timeout 600 env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus $N --steps 30 --warmup 5 --no-cpu $EXTRA > gpurun_out/bench_n${N}_$tag.json 2> gpurun_out/bench_n${N}_$tag.err; python -c "
+import json
+d=json.load(open('gpurun_out/bench_n${N}_$tag.json'))
+print('N=$N $tag:', round(d['value'],1), 'ex/s', round(d['ms_per_step'],3), 'ms  e2e', round(d['e2e']['value'],1), 'replica', d['replica_check']['max_abs_param_diff_vs_rank0'], d['config']['gradient_exchange'][:36])" || tail -5 gpurun_out/bench_n${N}_$tag.err; }
+EXTRA="" run mc X=0
+EXTRA="--no-multicast" run nccl_shard X=0
+EXTRA="--no-multicast --no-shard" run nccl_ar X=0

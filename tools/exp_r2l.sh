@@ -1,0 +1,12 @@
+#!/bin/bash
+N=2
+mkdir -p gpurun_out
+run() { tag=$1; shift; timeout 600 env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus $N --steps 30 --warmup 5 --no-cpu $EXTRA > gpurun_out/bench_n${N}_$tag.json 2> gpurun_out/bench_n${N}_$tag.err; python -c "
+import json
+d=json.load(open('gpurun_out/bench_n${N}_$tag.json'))
+print('N=$N $tag:', round(d['value'],1), 'ex/s', round(d['ms_per_step'],3), 'ms  e2e', round(d['e2e']['value'],1), 'replica', d['replica_check']['max_abs_param_diff_vs_rank0'], d['config']['gradient_exchange'][:36])" || tail -5 gpurun_out/bench_n${N}_$tag.err; }
+EXTRA="--no-multicast --no-shard" run ar_tail4 B200MART_TAIL_CHUNKS=4
+EXTRA="--no-multicast --no-shard" run ar_tail8 B200MART_TAIL_CHUNKS=8
+EXTRA="" run mc_tail4 B200MART_TAIL_CHUNKS=4
+EXTRA="--no-multicast --no-shard" run ar_nvls NCCL_ALGO=NVLS
+EXTRA="--no-multicast --no-shard" run ar_ctas32 NCCL_MAX_CTAS=32
