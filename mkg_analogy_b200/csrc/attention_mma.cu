@@ -192,6 +192,55 @@ __device__ __forceinline__ void mma_p_b(float (&c)[8][4], const uint32_t (&pa)[4
         }
     }
 }
+// The same three helpers for a chunk of NT n-tiles (8 NT keys, NT even) instead of 64 keys.  The backward kernels walk the keys
+// in chunks of 16 / 32 (NT = 2 / 4): their per-chunk element-wise code is fully unrolled over the accumulator fragments, and at
+// 64 keys the straight-line body of attn_bwd_fused was ~8,000 SASS instructions (128 KB) that every warp runs once or twice -
+// ncu attributes 25 % (vision) to 50 % (text) of its stall samples to instruction fetch ("no_inst",
+// profiles/attention_r2.txt).  A quarter of the body, looped four times as often, stays in the instruction caches.
+template <int NT>
+__device__ __forceinline__ void mma_a_bt_t(float (&c)[NT][4], const uint32_t (&a)[4][4], const bf16* Bs, int n0, int lane) {
+    const uint32_t base = smem_u32(Bs);
+    const int lr = lane & 7, sel = lane >> 3;
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t b[4];
+            const int row = n0 + np * 16 + (sel >> 1) * 8 + lr;
+            const int col = ks * 16 + (sel & 1) * 8;
+            ldsm_x4(base + (uint32_t)(row * LDS + col) * 2u, b);
+            mma16816(c[2 * np], a[ks], b[0], b[1]);
+            mma16816(c[2 * np + 1], a[ks], b[2], b[3]);
+        }
+    }
+}
+template <int NT>
+__device__ __forceinline__ void mma_p_b_t(float (&c)[8][4], const uint32_t (&pa)[NT / 2][4], const bf16* Bs, int k0, int lane) {
+    const uint32_t base = smem_u32(Bs);
+    const int lr = lane & 7, sel = lane >> 3;
+#pragma unroll
+    for (int ks = 0; ks < NT / 2; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            uint32_t b[4];
+            const int row = k0 + ks * 16 + (sel & 1) * 8 + lr;
+            const int col = np * 16 + (sel >> 1) * 8;
+            ldsm_x4_t(base + (uint32_t)(row * LDS + col) * 2u, b);
+            mma16816(c[2 * np], pa[ks], b[0], b[1]);
+            mma16816(c[2 * np + 1], pa[ks], b[2], b[3]);
+        }
+    }
+}
+template <int NT>
+__device__ __forceinline__ void acc_to_a_t(const float (&c)[NT][4], uint32_t (&a)[NT / 2][4]) {
+#pragma unroll
+    for (int ks = 0; ks < NT / 2; ++ks) {
+        a[ks][0] = pack_bf16x2(c[2 * ks][0], c[2 * ks][1]);
+        a[ks][1] = pack_bf16x2(c[2 * ks][2], c[2 * ks][3]);
+        a[ks][2] = pack_bf16x2(c[2 * ks + 1][0], c[2 * ks + 1][1]);
+        a[ks][3] = pack_bf16x2(c[2 * ks + 1][2], c[2 * ks + 1][3]);
+    }
+}
 // accumulator tiles (16 x 64) -> packed bf16 A fragments (4 k-steps of 16)
 __device__ __forceinline__ void acc_to_a(const float (&c)[8][4], uint32_t (&a)[4][4]) {
 #pragma unroll
@@ -251,11 +300,12 @@ __device__ __forceinline__ void stage_keys(const AttnFwd& a, int b, int h, bf16*
 
 // partial row sums of P_ij * mult_ij * dP_ij over one 16 x 64 chunk (s = raw QK^T accumulators, dp = dO V^T accumulators):
 // the softmax-backward delta that is consistent with the dP values the caller goes on to use
-__device__ __forceinline__ void consistent_delta(const AttnFwd& a, const Adapt& ad, const float (&s)[8][4], const float (&dp)[8][4],
+template <int NT>
+__device__ __forceinline__ void consistent_delta(const AttnFwd& a, const Adapt& ad, const float (&s)[NT][4], const float (&dp)[NT][4],
                                                  const float* madd, const float (&lse)[2], int kc, int r0, int g, int t, int n1, int n,
                                                  int Lq, int b, int h, float (&acc)[2]) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int col = kc + nt * 8 + 2 * t + (e & 1);
@@ -401,7 +451,7 @@ attn_bwd_rows_mma(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx, fl
                 }
                 mma_a_bt(s, qa, Ks, kc, lane);
                 mma_a_bt(dp, doa, Vs, kc, lane);
-                consistent_delta(a, ad, s, dp, madd, lse, kc, r0, g, t, n1, n, a.Lq, b, h, acc);
+                consistent_delta<8>(a, ad, s, dp, madd, lse, kc, r0, g, t, n1, n, a.Lq, b, h, acc);
             }
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
@@ -593,7 +643,7 @@ attn_bwd_keys_mma(const AttnBwd gr, const float* __restrict__ delta) {
 // with ldmatrix.trans as the A operand of dV = P^T dO and dK = (dS f)^T Q, instead of recomputing S^T and dP^T from
 // global memory.  5 matrix products instead of 7, one launch, no delta round trip, Q / dO staged once over the K / V
 // buffers phase A is done with.  (The two-kernel path stays for shapes whose P does not fit: MKGformer-large vision.)
-template <int NW>
+template <int NW, int NTK>
 __global__ void __launch_bounds__(NW * 32, NW == 4 ? 3 : 1)     // text tiles: 3 CTAs per SM hold all B * heads CTAs in one wave
 attn_bwd_fused(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -636,8 +686,10 @@ attn_bwd_fused(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx) {
     const Adapt ad = load_adapt(a, b);
     __syncthreads();
 
-    // ---------------- phase A: query-row blocks
+    // ---------------- phase A: query-row blocks, keys in chunks of KC = 8 NTK
+    constexpr int KC = 8 * NTK;
     float dw0 = 0.f, dw1 = 0.f;
+#pragma unroll 1
     for (int r0 = warp * 16; r0 < Lq16; r0 += NW * 16) {
         uint32_t qa[4][4], doa[4][4];
         load_a_smem(Qs, r0, lane, qa);
@@ -654,40 +706,37 @@ attn_bwd_fused(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx) {
         for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
         // Adaptive scaling: dW0 / dW1 = sum dS * S_raw is a heavily cancelling sum (sum_j dS_ij = 0 in exact arithmetic), so
         // delta must be CONSISTENT with the dP this kernel computes (bf16 dO, bf16 V): delta_i = sum_j P_ij dP_ij from the same
-        // registers, not rowsum(dO * O) with its independently rounded O - otherwise (delta error) x (row mean of S_raw) leaks
-        // into the two scalars.  More than one key chunk: a pre-pass over the chunks; one chunk: from the chunk's own registers.
+        // products, not rowsum(dO * O) with its independently rounded O - otherwise (delta error) x (row mean of S_raw) leaks
+        // into the two scalars.  A pre-pass over the key chunks accumulates it.
         const bool adaptive = ad.split >= 0;
-        if (adaptive && n_pad > 64) {
+        if (adaptive) {
             float acc[2] = {0.f, 0.f};
-            for (int kc = 0; kc < n_pad; kc += 64) {
-                float s[8][4], dp[8][4];
+#pragma unroll 1
+            for (int kc = 0; kc < n_pad; kc += KC) {
+                float s[NTK][4], dp[NTK][4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < NTK; ++i) {
                     s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
                     dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
                 }
-                mma_a_bt(s, qa, Ks, kc, lane);
-                mma_a_bt(dp, doa, Vs, kc, lane);
-                consistent_delta(a, ad, s, dp, madd, lse, kc, r0, g, t, n1, n, Lq, b, h, acc);
+                mma_a_bt_t<NTK>(s, qa, Ks, kc, lane);
+                mma_a_bt_t<NTK>(dp, doa, Vs, kc, lane);
+                consistent_delta<NTK>(a, ad, s, dp, madd, lse, kc, r0, g, t, n1, n, Lq, b, h, acc);
             }
             dl[0] = quad_sum(acc[0]); dl[1] = quad_sum(acc[1]);
         }
-        for (int kc = 0; kc < n_pad; kc += 64) {
-            float s[8][4], dp[8][4];
+#pragma unroll 1
+        for (int kc = 0; kc < n_pad; kc += KC) {
+            float s[NTK][4], dp[NTK][4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < NTK; ++i) {
                 s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
                 dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
             }
-            mma_a_bt(s, qa, Ks, kc, lane);
-            mma_a_bt(dp, doa, Vs, kc, lane);
-            if (adaptive && n_pad <= 64) {
-                float acc[2] = {0.f, 0.f};
-                consistent_delta(a, ad, s, dp, madd, lse, kc, r0, g, t, n1, n, Lq, b, h, acc);
-                dl[0] = quad_sum(acc[0]); dl[1] = quad_sum(acc[1]);
-            }
+            mma_a_bt_t<NTK>(s, qa, Ks, kc, lane);
+            mma_a_bt_t<NTK>(dp, doa, Vs, kc, lane);
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
+            for (int nt = 0; nt < NTK; ++nt) {
                 float pd[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -714,9 +763,9 @@ attn_bwd_fused(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx) {
                     *reinterpret_cast<uint32_t*>(Ds + off) = pack_bf16x2(s[nt][2 * hh], s[nt][2 * hh + 1]);
                 }
             }
-            uint32_t da[4][4];
-            acc_to_a(s, da);
-            mma_p_b(dq, da, Ks, kc, lane);
+            uint32_t da[NTK / 2][4];
+            acc_to_a_t<NTK>(s, da);
+            mma_p_b_t<NTK>(dq, da, Ks, kc, lane);
         }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -735,6 +784,7 @@ attn_bwd_fused(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx) {
     // ---------------- phase B: key blocks
     const int lr = lane & 7, sel = lane >> 3;
     const uint32_t ps_u = smem_u32(Ps), ds_u = smem_u32(Ds), qs_u = smem_u32(Qs), os_u = smem_u32(Os);
+#pragma unroll 1
     for (int j0 = warp * 16; j0 < n; j0 += NW * 16) {
         float dk[8][4], dv[8][4];
 #pragma unroll
@@ -742,6 +792,7 @@ attn_bwd_fused(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx) {
             dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
             dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
         }
+#pragma unroll 1
         for (int r16 = 0; r16 < Lq16; r16 += 16) {
             // A = P^T / (dS f)^T tile (16 keys x 16 query rows): transposed 8x8 blocks of the row-major [row][key] buffers
             uint32_t pa[4], da[4];
@@ -845,12 +896,17 @@ int launch_attention_bwd(const AttnBwd& g, const bf16* ctx, long ldctx, float* d
         const int lq16 = (a.Lq + 15) & ~15;
         const size_t smemf = (size_t)2 * (n_pad + lq16) * LDS * 2 + (size_t)2 * lq16 * (n_pad + 8) * 2 + (size_t)(n_pad + lq16) * 4;
         if (allow && smemf <= 200 * 1024) {
+            static int ntk = -1;       // B200MART_ATTN_KC = keys per chunk of the rows pass: 16 / 32 / 64 (default 32)
+            if (ntk < 0) { const char* e = getenv("B200MART_ATTN_KC"); const int kc = e ? atoi(e) : 32; ntk = kc == 16 ? 2 : (kc == 64 ? 8 : 4); }
+            auto go = [&](auto kernel, int nw) -> int {
+                B2_TRY(set_smem(kernel, smemf));
+                CUDA_TRY(launch_pdl(kernel, dim3(a.nh, a.B), dim3(nw * 32), smemf, s, g, ctx, ldctx));
+                return 0;
+            };
             if (a.Lq <= 64 && a.n1 + a.n2 <= 64) {
-                B2_TRY(set_smem(attn_bwd_fused<4>, smemf));
-                CUDA_TRY(launch_pdl(attn_bwd_fused<4>, dim3(a.nh, a.B), dim3(4 * 32), smemf, s, g, ctx, ldctx));
+                B2_TRY(ntk == 2 ? go(attn_bwd_fused<4, 2>, 4) : (ntk == 8 ? go(attn_bwd_fused<4, 8>, 4) : go(attn_bwd_fused<4, 4>, 4)));
             } else {
-                B2_TRY(set_smem(attn_bwd_fused<8>, smemf));
-                CUDA_TRY(launch_pdl(attn_bwd_fused<8>, dim3(a.nh, a.B), dim3(8 * 32), smemf, s, g, ctx, ldctx));
+                B2_TRY(ntk == 2 ? go(attn_bwd_fused<8, 2>, 8) : (ntk == 8 ? go(attn_bwd_fused<8, 8>, 8) : go(attn_bwd_fused<8, 4>, 8)));
             }
             B2_LAUNCHED();
             return 0;
