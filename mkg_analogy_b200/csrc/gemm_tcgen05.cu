@@ -200,9 +200,9 @@ int gemm_plan_create(const GemmOp& op, GemmPlan** out) {
         // B200MART_GEMM_HALF_SLOTS = CTAs per SM ONE launch may occupy (default 2: a launch with more tiles than SM pairs runs them
         // side by side, the main loop of one under the epilogue of the other; 1 leaves the second slot to other launches).
         static int half = -1, slots = -1;
-        if (half < 0) { const char* e = getenv("B200MART_GEMM_HALF"); half = e ? atoi(e) : 0; }
+        if (half < 0) { const char* e = getenv("B200MART_GEMM_HALF"); half = e ? atoi(e) : 0; if (half == 1) half = 0xffff; }   // 1 = every kind, else bitmask by epilogue kind
         if (slots < 0) { const char* e = getenv("B200MART_GEMM_HALF_SLOTS"); slots = e ? atoi(e) : 2; if (slots < 1) slots = 1; if (slots > 2) slots = 2; }
-        const bool use_half = half && gemm_pick_kernel_pair_half(op.a_mn, op.b_mn, epi) != nullptr;
+        const bool use_half = ((half >> epi) & 1) && gemm_pick_kernel_pair_half(op.a_mn, op.b_mn, epi) != nullptr;
         d.mt = (op.M + 2 * BM - 1) / (2 * BM);
         d.nt = (op.N + PairLayout::BN_TILE - 1) / PairLayout::BN_TILE;
         const long ptiles = (long)d.mt * d.nt * split;

@@ -362,8 +362,9 @@ int run_gemm(b200mart_handle* h, const GemmOp& op, cudaStream_t s) {
 // streams next to the two dependent chains, and a resident persistent CTA is never preempted whatever the stream priority
 int dw_max_ctas() {
     static int cap = -1;
-    // default 40 of 148 SMs (about the weight gradients' share of the backward FLOPs): measured 7.87 -> 7.67 ms per step
-    if (cap < 0) { const char* e = getenv("B200MART_DW_MAXCTAS"); cap = e ? atoi(e) : 40; if (cap < 0) cap = 0; }
+    // round 1: 40 of 148 SMs (7.87 -> 7.67 ms per step against an unbounded grid); round 2, with the lighter LayerNorm / column-sum
+    // kernels next to them: 32 / 40 / 48 / 56 / 64 CTAs = 7.10 / 7.04 / 7.03 / 7.00 / 7.00 ms (gpurun_out/ab_r2o.txt) -> 56
+    if (cap < 0) { const char* e = getenv("B200MART_DW_MAXCTAS"); cap = e ? atoi(e) : 56; if (cap < 0) cap = 0; }
     return cap;
 }
 
