@@ -298,6 +298,23 @@ __device__ __forceinline__ void stage_keys(const AttnFwd& a, int b, int h, bf16*
     }
 }
 
+// the same with cp.async (every request of the CTA in flight at once); finish with cp_async_wait_all() + __syncthreads()
+__device__ __forceinline__ void stage_keys_async(const AttnFwd& a, int b, int h, bf16* Ks, bf16* Vs, float* madd, int n_pad, int tid, int nthreads) {
+    const int n1 = a.n1, n2 = a.n2, n = n1 + n2;
+    if (n1 > 0) {
+        stage_bf16_async(Ks, a.k1 + (long)b * n1 * a.ld1 + h * D, a.ld1, n1, n1, tid, nthreads);
+        stage_bf16_async(Vs, a.v1 + (long)b * n1 * a.ld1 + h * D, a.ld1, n1, n1, tid, nthreads);
+    }
+    stage_bf16_async(Ks + n1 * LDS, a.k2 + (long)b * n2 * a.ld2 + h * D, a.ld2, n2, n_pad - n1, tid, nthreads);
+    stage_bf16_async(Vs + n1 * LDS, a.v2 + (long)b * n2 * a.ld2 + h * D, a.ld2, n2, n_pad - n1, tid, nthreads);
+    for (int j = tid; j < n_pad; j += nthreads) {
+        float m = 0.f;
+        if (j >= n) m = NEG_BIG;
+        else if (a.key_mask && j >= n1) m = (1.0f - (float)a.key_mask[(long)b * n2 + (j - n1)]) * -10000.0f;
+        madd[j] = m;
+    }
+}
+
 // partial row sums of P_ij * mult_ij * dP_ij over one 16 x 64 chunk (s = raw QK^T accumulators, dp = dO V^T accumulators):
 // the softmax-backward delta that is consistent with the dP values the caller goes on to use
 template <int NT>
@@ -319,7 +336,10 @@ __device__ __forceinline__ void consistent_delta(const AttnFwd& a, const Adapt& 
 }
 
 // ------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(WARPS * 32)
+// NW warps of 16 query rows each: 4 for the text stream (L <= 64: one round), 8 for the vision stream (99 rows: one round
+// instead of two over the same staged K / V)
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 3)
 attn_fwd_mma(const AttnFwd a, float* __restrict__ out32) {
     extern __shared__ __align__(16) uint8_t smem[];
     pdl_wait();
@@ -330,12 +350,13 @@ attn_fwd_mma(const AttnFwd a, float* __restrict__ out32) {
     bf16* Vs = Ks + (size_t)n_pad * LDS;
     float* madd = reinterpret_cast<float*>(Vs + (size_t)n_pad * LDS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-    stage_keys(a, b, h, Ks, Vs, madd, n_pad, tid);
+    stage_keys_async(a, b, h, Ks, Vs, madd, n_pad, tid, NW * 32);
     const Adapt ad = load_adapt(a, b);
+    const bf16* qbase = a.q + (long)b * a.Lq * a.ldq + h * D;
+    cp_async_wait_all();
     __syncthreads();
 
-    const bf16* qbase = a.q + (long)b * a.Lq * a.ldq + h * D;
-    for (int r0 = warp * 16; r0 < a.Lq; r0 += WARPS * 16) {
+    for (int r0 = warp * 16; r0 < a.Lq; r0 += NW * 16) {
         uint32_t qa[4][4];
         load_a_bf16(qbase, a.ldq, r0, a.Lq, lane, qa);
         float o[8][4];
@@ -877,8 +898,13 @@ int launch_attention_fwd(const AttnFwd& a, float* out32, cudaStream_t s) {
     B2_CHECK(a.out, "attention: output missing");
     const int n_pad = (a.n1 + a.n2 + 63) & ~63;
     const size_t smem = (size_t)2 * n_pad * LDS * 2 + (size_t)n_pad * 4;
-    B2_TRY(set_smem(attn_fwd_mma, smem));
-    CUDA_TRY(launch_pdl(attn_fwd_mma, dim3(a.nh, a.B), dim3(WARPS * 32), smem, s, a, out32));
+    if (a.Lq > 64) {
+        B2_TRY(set_smem(attn_fwd_mma<8>, smem));
+        CUDA_TRY(launch_pdl(attn_fwd_mma<8>, dim3(a.nh, a.B), dim3(8 * 32), smem, s, a, out32));
+    } else {
+        B2_TRY(set_smem(attn_fwd_mma<4>, smem));
+        CUDA_TRY(launch_pdl(attn_fwd_mma<4>, dim3(a.nh, a.B), dim3(4 * 32), smem, s, a, out32));
+    }
     B2_LAUNCHED();
     return 0;
 }
