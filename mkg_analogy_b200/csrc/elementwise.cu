@@ -575,10 +575,13 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
     // one block per 4096-element chunk; the owning segment is found by binary search on the chunk start
     // (segments are aligned to 8 elements and chunks never straddle an unaligned boundary element-wise: each
     // thread re-checks its own element range).
-    const long base = begin + (long)blockIdx.x * 4096;     // processes the flat range [begin, n)
+  // grid-stride over 4096-element chunks: with a bounded grid (B200MART_ADAMW_CTAS) at most one of these 30-register blocks
+  // sits on an SM, beside a GEMM CTA (53,760 of 65,536 registers) instead of in front of it
+  for (long chunk = blockIdx.x; begin + chunk * 4096 < n; chunk += gridDim.x) {
+    const long base = begin + chunk * 4096;     // processes the flat range [begin, n)
     for (int it = 0; it < 4; ++it) {
         const long i = base + ((long)it * blockDim.x + threadIdx.x) * 4;
-        if (i >= n) return;
+        if (i >= n) break;
         int lo = 0, hi = nseg - 1;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -605,6 +608,7 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
         if (zero_grads) st4(g + i, make_float4(0.f, 0.f, 0.f, 0.f));   // the next step accumulates into a clean buffer
         if (p16) st4_bf16(p16 + i, pv);
     }
+  }
 }
 
 // AdamW over this rank's shard of a flat range with the data-parallel exchange fused in, over NVSwitch multicast:
@@ -908,7 +912,10 @@ int launch_adamw_mc(const float* p, float* m, float* v, float* g_mc, float* p_mc
 int launch_adamw(float* p, float* g, float* m, float* v, bf16* p16, const AdamSeg* segs_dev, int nseg, long begin, long end,
                  int zero_grads, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, cudaStream_t s) {
     B2_CHECK(begin % 8 == 0 && end % 8 == 0 && begin < end, "adamw: range [%ld, %ld) must be non-empty and 8-aligned", begin, end);
-    const long blocks = (end - begin + 4095) / 4096;
+    long blocks = (end - begin + 4095) / 4096;
+    static int cap = -1;       // B200MART_ADAMW_CTAS: bound of the grid (0 = one block per 4096 elements)
+    if (cap < 0) { const char* e = getenv("B200MART_ADAMW_CTAS"); cap = e ? atoi(e) : 0; if (cap < 0) cap = 0; }
+    if (cap > 0 && blocks > cap) blocks = cap;
     adamw_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, g, m, v, p16, segs_dev, nseg, begin, end, zero_grads, lr, b1, b2, eps, wd,
                                                   bc1, bc2);
     B2_LAUNCHED();
