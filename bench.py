@@ -418,11 +418,7 @@ def run_family(args):
     host = [{k: v.pin_memory() for k, v in mk(i).items()} for i in range(nb)]
     devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
 
-    def ls_ce(x, y, eps=0.1):      # LabelSmoothSoftmaxCEV1 (lit_models/utils.py:42-66): q[label] = 1 - eps, others eps / C
-        lp = F.log_softmax(x.float(), dim=-1)
-        C = x.shape[-1]
-        q = torch.full_like(lp, eps / C).scatter_(1, y[:, None], 1.0 - eps)
-        return -(q * lp).sum(-1).mean()
+    from mkg_analogy_b200 import nn as BN      # [MASK]-row score product on the tcgen05 GEMM + the fused LS-CE kernel
 
     def step(b):
         opt.zero_grad(set_to_none=True)
@@ -432,16 +428,16 @@ def run_family(args):
         _, trans = model(**kw, output_logits=False)
         B = trans.shape[0]
         _, mpos = (b["input_ids"] == 103).nonzero(as_tuple=True)
-        zm = trans[torch.arange(B, device=dev), mpos]                       # [MASK] rows only (fused route)
+        # [MASK] rows only (fused route)
         if name == "vilt":                                                  # pre-train branch, transformer.py:72-90
             ent = b["pre_type"] != 2
-            loss = zm.new_zeros(())
+            loss = trans.new_zeros(())
             if ent.any():
-                loss = loss + ls_ce(zm[ent] @ E[voc.entity_id_st:voc.entity_id_ed].t() + bias[voc.entity_id_st:voc.entity_id_ed], b["label"][ent])
+                loss = loss + BN.mask_row_loss(trans[ent], mpos[ent], E, bias, (voc.entity_id_st, voc.entity_id_ed), b["label"][ent])[0]
             if (~ent).any():
-                loss = loss + ls_ce(zm[~ent] @ E[voc.relation_id_st:voc.relation_id_ed].t() + bias[voc.relation_id_st:voc.relation_id_ed], b["label"][~ent])
+                loss = loss + BN.mask_row_loss(trans[~ent], mpos[~ent], E, bias, (voc.relation_id_st, voc.relation_id_ed), b["label"][~ent])[0]
         else:                                                               # fine-tune branch, transformer.py:92-109
-            loss = ls_ce(zm @ E[cols].t() + bias[cols], b["label"])
+            loss = BN.mask_row_loss(trans, mpos, E, bias, cols, b["label"])[0]
             ar = torch.arange(B, device=dev)
             cos = F.cosine_similarity
             sim = torch.relu(cos(trans[ar, b["q_head_idx"]], trans[ar, b["a_head_idx"]], dim=-1)) + 1 - \
@@ -509,8 +505,9 @@ def run_family(args):
                 "data": "synthetic",
                 "config": config_dict(name, world, {
                     "library_part": "every transformer block (attention + MLP, forward and backward) of the encoder stacks: b200mart_stack_*",
-                    "torch_part": "patch convolution, embeddings, mm projections (FLAVA), final LayerNorm, head transform, [MASK]-row score "
-                                  "product and loss, fused torch AdamW, per-parameter NCCL all-reduce",
+                    "library_plumbing": "patch embedding (im2col view + tcgen05 GEMM), mm projections (FLAVA), LayerNorms, head transform, "
+                                        "[MASK]-row score product and LS-CE loss: mkg_analogy_b200/nn.py over the C ABI (no cuBLAS / cuDNN call)",
+                    "torch_part": "embedding gathers, concatenations, casts, GELU of the head, relaxation loss, fused torch AdamW, bucketed NCCL all-reduce",
                     "parallelism": f"dp{world}" + ("" if world == 1 else " (mean all-reduce of every parameter gradient after backward)")}),
                 "clocks": clocks, "gpu_launches": int(launches), "final_loss": lv,
                 "e2e": {"value": Bp * world * K / s.item(), "unit": "examples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

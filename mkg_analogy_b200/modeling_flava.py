@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import nn as B
 from .modeling import MaskedLMOutput
 from .pretrained import PretrainedMixin, init_hf_style
 from .stack import EncoderStack
@@ -64,8 +65,8 @@ class _ImageEmbeddings(nn.Module):
         self.dropout = nn.Dropout(c["hidden_dropout_prob"])
 
     def forward(self, px):
-        head = self.patch_embeddings.projection(px[:, 0]).flatten(2).transpose(1, 2)
-        tail = self.patch_embeddings.projection(px[:, 1]).flatten(2).transpose(1, 2)
+        head = B.patch_embed(px[:, 0], self.patch_embeddings.projection)       # im2col + tcgen05 GEMM (no cuDNN)
+        tail = B.patch_embed(px[:, 1], self.patch_embeddings.projection)
         x = torch.cat([self.cls_token.expand(head.shape[0], -1, -1), head], dim=1) + self.position_embeddings
         tail = tail + self.position_embeddings[:, :tail.shape[1]]
         return self.dropout(torch.cat([x, tail], dim=1))
@@ -87,7 +88,7 @@ class _TextEmbeddings(nn.Module):
         if tt is None:
             tt = torch.zeros_like(ids)
         e = self.word_embeddings(ids) + self.token_type_embeddings(tt) + self.position_embeddings(self.position_ids[:, :L])
-        return self.dropout(self.LayerNorm(e))
+        return self.dropout(B.layer_norm(e, self.LayerNorm))
 
 
 class _Tower(nn.Module):
@@ -122,7 +123,7 @@ class _Transform(nn.Module):
         self.LayerNorm = nn.LayerNorm(hidden, eps=eps)
 
     def forward(self, x):
-        return self.LayerNorm(F.gelu(self.dense(x)))
+        return B.layer_norm(F.gelu(B.linear(x, self.dense.weight, self.dense.bias)), self.LayerNorm)
 
 
 class _Head(nn.Module):
@@ -198,14 +199,15 @@ class FlavaKGC(PretrainedMixin, nn.Module):
         fl = self.flava
         dev = fl.multimodal_model.cls_token.device
         ids = input_ids.to(dev)
-        B, L = ids.shape
+        Bn, L = ids.shape
         img = fl.image_model.encoder(fl.image_model.embeddings(pixel_values.to(dev, torch.float32)))            # pre-final-LN
         txt = fl.text_model.encoder(fl.text_model.embeddings(ids, None if token_type_ids is None else token_type_ids.to(dev)),
                                     attention_mask=None if attention_mask is None else attention_mask.to(dev),
                                     sep_idx=None if sep_idx is None else sep_idx.to(dev), row_lo=1)
-        mm_in = torch.cat([fl.multimodal_model.cls_token.expand(B, -1, -1), fl.image_to_mm_projection(img),
-                           fl.text_to_mm_projection(txt)], dim=1)
-        mm = fl.multimodal_model.layernorm(fl.multimodal_model.encoder(mm_in))
+        ip, tp = fl.image_to_mm_projection, fl.text_to_mm_projection
+        mm_in = torch.cat([fl.multimodal_model.cls_token.expand(Bn, -1, -1), B.linear(img, ip.weight, ip.bias),
+                           B.linear(txt, tp.weight, tp.bias)], dim=1)
+        mm = B.layer_norm(fl.multimodal_model.encoder(mm_in), fl.multimodal_model.layernorm)
         trans = self.cls.transform(mm[:, -L:])
-        logits = F.linear(trans, self.cls.decoder.weight, self.cls.bias) if output_logits else None
+        logits = B.linear(trans, self.cls.decoder.weight, self.cls.bias) if output_logits else None
         return MaskedLMOutput(logits=logits), trans

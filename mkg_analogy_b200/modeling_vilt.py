@@ -24,6 +24,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import nn as B
 from .modeling import MaskedLMOutput
 from .pretrained import PretrainedMixin, init_hf_style
 from .stack import EncoderStack
@@ -47,7 +48,7 @@ class _TextEmbeddings(nn.Module):
         n = min(L, self.position_embeddings.num_embeddings)      # only the first 40 positions get one (:296-299)
         pos = self.position_embeddings(self.position_ids[:, :n])
         e = torch.cat([e[:, :n] + pos, e[:, n:]], dim=1)
-        return self.dropout(self.LayerNorm(e))
+        return self.dropout(B.layer_norm(e, self.LayerNorm))
 
 
 class _PatchEmbeddings(nn.Module):
@@ -70,7 +71,7 @@ class _Embeddings(nn.Module):
         self.dropout = nn.Dropout(cfg["hidden_dropout_prob"])
 
     def image_tokens(self, pixels):
-        x = self.patch_embeddings.projection(pixels).flatten(2).transpose(1, 2)          # (B, g*g, H), row-major patches
+        x = B.patch_embed(pixels, self.patch_embeddings.projection)                      # (B, g*g, H), row-major patches; im2col + tcgen05 GEMM
         x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1) + self.position_embeddings
         return self.dropout(x)
 
@@ -88,7 +89,7 @@ class _Transform(nn.Module):
         self.LayerNorm = nn.LayerNorm(hidden, eps=eps)
 
     def forward(self, x):
-        return self.LayerNorm(F.gelu(self.dense(x)))
+        return B.layer_norm(F.gelu(B.linear(x, self.dense.weight, self.dense.bias)), self.LayerNorm)
 
 
 class _MLMHead(nn.Module):
@@ -184,23 +185,23 @@ class ViltKGC(PretrainedMixin, nn.Module):
         emb = self.vilt.embeddings
         dev = emb.cls_token.device
         input_ids = input_ids.to(dev)
-        B, L = input_ids.shape
+        Bn, L = input_ids.shape
         if attention_mask is None:
-            attention_mask = torch.ones(B, L, dtype=torch.long, device=dev)
+            attention_mask = torch.ones(Bn, L, dtype=torch.long, device=dev)
         text = emb.text_embeddings(input_ids, None if token_type_ids is None else token_type_ids.to(dev))
         px = pixel_values.to(dev, torch.float32)
         image = torch.cat([emb.image_tokens(px[:, 0]), emb.image_tokens(px[:, 1])], dim=1)
         text = text + emb.token_type_embeddings.weight[0]
         image = image + emb.token_type_embeddings.weight[1]
         x = torch.cat([text, image], dim=1)
-        mask = torch.cat([attention_mask.to(dev, torch.long), torch.ones(B, image.shape[1], dtype=torch.long, device=dev)], dim=1)
+        mask = torch.cat([attention_mask.to(dev, torch.long), torch.ones(Bn, image.shape[1], dtype=torch.long, device=dev)], dim=1)
         img_length = image.shape[1]
         sep = None
         if sep_idx is not None:
             sep = sep_idx.to(dev).clone()
             sep[:, 2] += img_length
         y = self.vilt.encoder(x, attention_mask=mask, sep_idx=sep, row_lo=img_length + 1)
-        seq = self.vilt.layernorm(y)[:, :L]
+        seq = B.layer_norm(y[:, :L].contiguous(), self.vilt.layernorm)          # LayerNorm is per row: the text rows only
         trans = self.mlm_score.transform(seq)
-        logits = F.linear(trans, self.mlm_score.decoder.weight, self.mlm_score.bias) if output_logits else None
+        logits = B.linear(trans, self.mlm_score.decoder.weight, self.mlm_score.bias) if output_logits else None
         return MaskedLMOutput(logits=logits), trans
