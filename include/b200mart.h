@@ -252,11 +252,19 @@ int64_t b200mart_gemm_timeline(void* device_buffer, int64_t records);
  * h = x + drop(Wo attn(LN x) + bo); y = h + drop(W2 act(W1 LN h + b1) + b2); head_dim 64; act 1 = erf-GELU, 2 = quick-GELU.
  * Parameters live in flat buffers laid out by the library (names follow the HF modules: layer.<i>.attention.attention.query.weight,
  * layer.<i>.attention.output.dense.*, layer.<i>.intermediate.dense.*, layer.<i>.output.dense.*, layer.<i>.layernorm_before/after.*,
- * layer.<i>.attention.attention.adaptive_weight.{0,1}); buffers/workspace conventions as for the MKGformer handle. */
+ * layer.<i>.attention.attention.adaptive_weight.{0,1}); buffers/workspace conventions as for the MKGformer handle.
+ *
+ * post_ln = 1 selects the post-LayerNorm block instead:
+ *   VisualBertLayer / VisualBertSelfAttention  MarT/models/modeling_visual_bert.py:381-421, :203-286 (adaptive scaling :255-260 on
+ *                                              rows img_length+1 : s' of the [text ; 72 region features] sequence)
+ * h = LN(x + drop(Wo attn(x) + bo)); y = LN(h + drop(W2 act(W1 h + b1) + b2)), names layer.<i>.attention.self.{query,key,value}.*,
+ * layer.<i>.attention.self.adaptive_weight.{0,1}, layer.<i>.attention.output.{dense,LayerNorm}.*, layer.<i>.intermediate.dense.*,
+ * layer.<i>.output.{dense,LayerNorm}.*. */
 typedef struct b200mart_stack_desc {
     int32_t hidden, layers, heads, intermediate;
     int32_t act;
     float eps;
+    int32_t post_ln;           /* 0: the pre-LayerNorm block above; 1: the BERT (post-LayerNorm) block of VisualBERT, see below */
 } b200mart_stack_desc;
 typedef struct b200mart_stack b200mart_stack;
 typedef struct b200mart_stack_io {

@@ -64,7 +64,7 @@ class Head(C.Structure):
 
 
 class StackDesc(C.Structure):
-    _fields_ = [("hidden", i32), ("layers", i32), ("heads", i32), ("intermediate", i32), ("act", i32), ("eps", f32)]
+    _fields_ = [("hidden", i32), ("layers", i32), ("heads", i32), ("intermediate", i32), ("act", i32), ("eps", f32), ("post_ln", i32)]
 
 
 class StackIO(C.Structure):

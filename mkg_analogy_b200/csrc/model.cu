@@ -1125,7 +1125,8 @@ struct b200mart_stack {
     b200mart_handle core;      // plan cache / profiling / stream plumbing of the GEMM runner
     b200mart_stack_desc d;
     struct LayerP { long ln1_w, ln1_b, qkv_w, qkv_b, aw0, aw1, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b; };
-    struct LayerA { bf16 *u16, *qkv16, *ctx16, *u2_16, *pre16, *h16; float *mean1, *rstd1, *lse, *x1, *mean2, *rstd2; };
+    struct LayerA { bf16 *u16, *qkv16, *ctx16, *u2_16, *pre16, *h16; float *mean1, *rstd1, *lse, *x1, *mean2, *rstd2;
+                    float *h1 = nullptr, *x2 = nullptr; };     // post-LN only: LayerNorm(x1) in fp32 (residual of the MLP), pre-LN sum of the MLP
     std::vector<LayerP> lay;
     // workspace carving
     int B = 0, T = 0; void* ws_base = nullptr; size_t ws_bytes = 0;
@@ -1148,6 +1149,7 @@ void stack_carve(b200mart_stack* st, int B, int T, void* base) {
         a.ctx16 = c.take<bf16>(M * H); a.x1 = c.take<float>(M * H);
         a.u2_16 = c.take<bf16>(M * H); a.mean2 = c.take<float>(M); a.rstd2 = c.take<float>(M);
         a.pre16 = c.take<bf16>(M * F); a.h16 = c.take<bf16>(M * F);
+        if (st->d.post_ln) { a.h1 = c.take<float>(M * H); a.x2 = c.take<float>(M * H); }
     }
     st->s32a = c.take<float>(M * H); st->s32b = c.take<float>(M * H); st->dX = c.take<float>(M * H);
     st->dX16 = c.take<bf16>(M * H); st->s16a = c.take<bf16>(M * H); st->sF16 = c.take<bf16>(M * F);
@@ -1196,24 +1198,26 @@ extern "C" int32_t b200mart_stack_create(const b200mart_stack_desc* desc, b200ma
     for (int i = 0; i < d.layers; ++i) {
         b200mart_stack::LayerP p;
         auto nm = [&](const char* s) { snprintf(buf, sizeof(buf), "layer.%d.%s", i, s); return std::string(buf); };
-        p.qkv_w = add_param(h, nm("attention.attention.query.weight"), {H, H});
-        add_param(h, nm("attention.attention.key.weight"), {H, H});
-        add_param(h, nm("attention.attention.value.weight"), {H, H});
-        p.qkv_b = add_param(h, nm("attention.attention.query.bias"), {H});
-        add_param(h, nm("attention.attention.key.bias"), {H});
-        add_param(h, nm("attention.attention.value.bias"), {H});
-        p.aw0 = add_param(h, nm("attention.attention.adaptive_weight.0"), {1});
-        p.aw1 = add_param(h, nm("attention.attention.adaptive_weight.1"), {1});
+        // pre-LN: ViT-style names (FLAVA / ViLT); post-LN: BERT-style names (VisualBERT)
+        const std::string sa = d.post_ln ? "attention.self." : "attention.attention.";
+        p.qkv_w = add_param(h, nm((sa + "query.weight").c_str()), {H, H});
+        add_param(h, nm((sa + "key.weight").c_str()), {H, H});
+        add_param(h, nm((sa + "value.weight").c_str()), {H, H});
+        p.qkv_b = add_param(h, nm((sa + "query.bias").c_str()), {H});
+        add_param(h, nm((sa + "key.bias").c_str()), {H});
+        add_param(h, nm((sa + "value.bias").c_str()), {H});
+        p.aw0 = add_param(h, nm((sa + "adaptive_weight.0").c_str()), {1});
+        p.aw1 = add_param(h, nm((sa + "adaptive_weight.1").c_str()), {1});
         p.o_w = add_param(h, nm("attention.output.dense.weight"), {H, H});
         p.o_b = add_param(h, nm("attention.output.dense.bias"), {H});
         p.fc1_w = add_param(h, nm("intermediate.dense.weight"), {F, H});
         p.fc1_b = add_param(h, nm("intermediate.dense.bias"), {F});
         p.fc2_w = add_param(h, nm("output.dense.weight"), {H, F});
         p.fc2_b = add_param(h, nm("output.dense.bias"), {H});
-        p.ln1_w = add_param(h, nm("layernorm_before.weight"), {H});
-        p.ln1_b = add_param(h, nm("layernorm_before.bias"), {H});
-        p.ln2_w = add_param(h, nm("layernorm_after.weight"), {H});
-        p.ln2_b = add_param(h, nm("layernorm_after.bias"), {H});
+        p.ln1_w = add_param(h, nm(d.post_ln ? "attention.output.LayerNorm.weight" : "layernorm_before.weight"), {H});
+        p.ln1_b = add_param(h, nm(d.post_ln ? "attention.output.LayerNorm.bias" : "layernorm_before.bias"), {H});
+        p.ln2_w = add_param(h, nm(d.post_ln ? "output.LayerNorm.weight" : "layernorm_after.weight"), {H});
+        p.ln2_b = add_param(h, nm(d.post_ln ? "output.LayerNorm.bias" : "layernorm_after.bias"), {H});
         st->lay.push_back(p);
     }
     *out = st;
@@ -1244,6 +1248,30 @@ extern "C" int32_t b200mart_stack_forward(b200mart_stack* st, const b200mart_buf
     cudaStream_t s = (cudaStream_t)stream;
     Run r{&st->core, bufs, s};
     CUDA_TRY(cudaMemcpyAsync(st->X[0], io->x, sizeof(float) * M * H, cudaMemcpyDeviceToDevice, s));
+    if (d.post_ln) {
+        // BertLayer order (VisualBertLayer, MarT/models/modeling_visual_bert.py:381-421): x1 = x + drop(Wo attn(x) + bo); h1 = LN(x1);
+        // x2 = h1 + drop(W2 act(W1 h1 + b1) + b2); y = LN(x2)
+        B2_TRY(launch_cast_bf16(io->x, st->act[0].u16, (long)M * H, s));
+        for (int i = 0; i < d.layers; ++i) {
+            const b200mart_stack::LayerP& p = st->lay[i];
+            b200mart_stack::LayerA& a = st->act[i];
+            B2_TRY(r.linear(M, 3 * H, H, a.u16, p.qkv_w, p.qkv_b, 0, nullptr, nullptr, nullptr, a.qkv16));
+            AttnFwd at{};
+            stack_attn(st, io, r, i, at);
+            at.out = a.ctx16; at.ldo = H;
+            B2_TRY(launch_attention_fwd(at, nullptr, s));
+            r.drop_next = make_drop(io->p_hidden, io->seed, 2 + 3 * i);
+            B2_TRY(r.linear(M, H, H, a.ctx16, p.o_w, p.o_b, 0, nullptr, st->X[i], a.x1, nullptr));
+            B2_TRY(launch_layernorm_fwd(a.x1, r.p32(p.ln1_w), r.p32(p.ln1_b), d.eps, a.h1, a.u2_16, a.mean1, a.rstd1, M, H, s));
+            B2_TRY(r.linear(M, F, H, a.u2_16, p.fc1_w, p.fc1_b, d.act, a.pre16, nullptr, nullptr, a.h16));
+            r.drop_next = make_drop(io->p_hidden, io->seed, 3 + 3 * i);
+            B2_TRY(r.linear(M, H, F, a.h16, p.fc2_w, p.fc2_b, 0, nullptr, a.h1, a.x2, nullptr));
+            B2_TRY(launch_layernorm_fwd(a.x2, r.p32(p.ln2_w), r.p32(p.ln2_b), d.eps, st->X[i + 1], i + 1 < d.layers ? st->act[i + 1].u16 : st->s16a,
+                                        a.mean2, a.rstd2, M, H, s));
+        }
+        CUDA_TRY(cudaMemcpyAsync(io->y, st->X[d.layers], sizeof(float) * M * H, cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
     for (int i = 0; i < d.layers; ++i) {
         const b200mart_stack::LayerP& p = st->lay[i];
         b200mart_stack::LayerA& a = st->act[i];
@@ -1273,6 +1301,35 @@ extern "C" int32_t b200mart_stack_backward(b200mart_stack* st, const b200mart_bu
     cudaStream_t s = (cudaStream_t)stream;
     Run r{&st->core, bufs, s};
     const DropCfg nodrop{0u, 0u, 1.f};
+    if (d.post_ln) {
+        CUDA_TRY(cudaMemcpyAsync(st->dX, dy, sizeof(float) * M * H, cudaMemcpyDeviceToDevice, s));
+        for (int i = D - 1; i >= 0; --i) {
+            const b200mart_stack::LayerP& p = st->lay[i];
+            b200mart_stack::LayerA& a = st->act[i];
+            // output LayerNorm: d x2 (fp32: the residual branch into h1) + its masked bf16 copy (the fc2 branch) + fc2 bias gradient
+            B2_TRY(launch_layernorm_bwd(st->dX, a.x2, a.mean2, a.rstd2, r.p32(p.ln2_w), nullptr, nullptr, 0, st->s32a, st->dX16,
+                                        r.g32(p.ln2_w), r.g32(p.ln2_b), r.g32(p.fc2_b), M, H, s, nodrop, make_drop(io->p_hidden, io->seed, 3 + 3 * i)));
+            B2_TRY(r.grad_weight(M, H, F, st->dX16, H, a.h16, F, p.fc2_w, -1));
+            B2_TRY(r.grad_input(M, H, F, st->dX16, p.fc2_w, a.pre16, 3, nullptr, nullptr, st->sF16, p.fc1_b));
+            B2_TRY(r.grad_weight(M, F, H, st->sF16, F, a.u2_16, H, p.fc1_w, -1));
+            B2_TRY(r.grad_input(M, F, H, st->sF16, p.fc1_w, nullptr, 0, st->s32a, st->s32b, nullptr));        // d h1 (incl. residual)
+            // attention-output LayerNorm: d x1 (fp32: the residual branch into x) + masked bf16 copy (the Wo branch) + bo gradient
+            B2_TRY(launch_layernorm_bwd(st->s32b, a.x1, a.mean1, a.rstd1, r.p32(p.ln1_w), nullptr, nullptr, 0, st->s32a, st->s16a,
+                                        r.g32(p.ln1_w), r.g32(p.ln1_b), r.g32(p.o_b), M, H, s, nodrop, make_drop(io->p_hidden, io->seed, 2 + 3 * i)));
+            B2_TRY(r.grad_weight(M, H, H, st->s16a, H, a.ctx16, H, p.o_w, -1));
+            B2_TRY(r.grad_input(M, H, H, st->s16a, p.o_w, nullptr, 0, nullptr, st->s32b, nullptr));            // d ctx
+            AttnBwd ab{};
+            stack_attn(st, io, r, i, ab.f);
+            if (io->split) { ab.dw0 = r.g32(p.aw0); ab.dw1 = r.g32(p.aw1); }
+            ab.dout = st->s32b; ab.lddo = H;
+            ab.dq = st->sdqkv16; ab.dk2 = st->sdqkv16 + H; ab.dv2 = st->sdqkv16 + 2 * H; ab.ldd = 3 * H;
+            B2_TRY(launch_attention_bwd(ab, a.ctx16, H, st->delta, s));
+            B2_TRY(r.grad_weight(M, 3 * H, H, st->sdqkv16, 3 * H, a.u16, H, p.qkv_w, p.qkv_b));
+            B2_TRY(r.grad_input(M, 3 * H, H, st->sdqkv16, p.qkv_w, nullptr, 0, st->s32a, st->dX, nullptr));     // d x (incl. residual)
+        }
+        if (dx) CUDA_TRY(cudaMemcpyAsync(dx, st->dX, sizeof(float) * M * H, cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
     // gradient wrt the stack output: fp32 copy (residual path) + masked bf16 copy / bias gradient of the top fc2
     CUDA_TRY(cudaMemcpyAsync(st->dX, dy, sizeof(float) * M * H, cudaMemcpyDeviceToDevice, s));
     B2_TRY(launch_mask_cast_colsum(dy, st->dX16, r.g32(st->lay[D - 1].fc2_b), M, H, make_drop(io->p_hidden, io->seed, 3 + 3 * (D - 1)), s));

@@ -1,10 +1,11 @@
-"""Pre-LayerNorm encoder stack on the B200 library: the block FLAVA and ViLT are built from.
+"""Encoder stack on the B200 library: the pre-LayerNorm block FLAVA and ViLT are built from, and (post_ln=True) the BERT block of VisualBERT.
 
 `EncoderStack` mirrors the HF encoders the reference vendors — `FlavaEncoder` (MarT/models/modeling_flava.py:668-722: image,
 text and multimodal encoders are three instances) and `ViltEncoder` (MarT/models/modeling_vilt.py:531-583) — same
 `state_dict()` names (`layer.<i>.attention.attention.query.weight`, ...), same call shape (hidden states in, hidden states
 out), with the reference's adaptive analogy scaling (`sep_idx`, FLAVA rows 1:s / ViLT rows img_length+1:s) and additive
-padding mask inside the fused attention kernel.  Parameters are `nn.Parameter` views of a flat fp32 buffer; the backward is
+padding mask inside the fused attention kernel.  `post_ln=True` gives `VisualBertEncoder` (MarT/models/modeling_visual_bert.py:424-488:
+`layer.<i>.attention.self.query.weight`, `...attention.output.LayerNorm.weight`, ...; scaling on rows img_length+1:s', :255-260).  Parameters are `nn.Parameter` views of a flat fp32 buffer; the backward is
 `b200mart_stack_backward` (hand-derived), hooked into torch autograd so that embeddings / heads written in PyTorch around it
 train normally.  No CPU fallback: computing needs a CUDA device.
 """
@@ -33,11 +34,12 @@ class _StackFn(torch.autograd.Function):
 
 class EncoderStack(nn.Module):
     def __init__(self, hidden, layers, heads, intermediate, eps=1e-12, act="gelu", hidden_dropout=0.0, attn_dropout=0.0,
-                 device=None, initializer_range=0.02):
+                 device=None, initializer_range=0.02, post_ln=False):
         super().__init__()
         self.l = _lib.lib()
         d = _lib.StackDesc()
         d.hidden, d.layers, d.heads, d.intermediate = hidden, layers, heads, intermediate
+        d.post_ln = 1 if post_ln else 0
         d.act = {"gelu": 1, "quick_gelu": 2}[act]
         d.eps = eps
         self.h = _lib.vp()
@@ -57,7 +59,7 @@ class EncoderStack(nn.Module):
         with torch.no_grad():
             for name, off, shape in self.infos:
                 v = self._view(self.params32, off, shape)
-                if name.endswith("layernorm_before.weight") or name.endswith("layernorm_after.weight"):
+                if name.lower().endswith(("layernorm_before.weight", "layernorm_after.weight", "layernorm.weight")):
                     v.fill_(1.0)
                 elif name.endswith("adaptive_weight.0"):
                     v.uniform_(0.0, 0.5)
