@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """MARS analogy-examples/sec of the MarT training step (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config base|large|flava|vilt]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config base|large|flava|vilt|visualbert]
 
 Default (--config base, BASELINE.json configs[1], the configuration the metric is quoted on): one "step" = one optimizer step on
 one 32-example synthetic MARS-shaped batch per GPU (224x224 image pair, 64 text tokens, 2,063-entity score head over the
@@ -48,18 +48,21 @@ WORKLOADS = {
                   workload="FLAVA-base MarT fine-tune step (image 12 + text 12 + multimodal 6 blocks), synthetic batch"),
     "vilt": dict(metric="MarKG pre-train examples/sec (ViLT-base, 384px/128tok)", B=32, L=128, gf=3 * 79.0, params_M=None,
                  workload="ViLT-base MarT pre-train step on synthetic MarKG triples (12 blocks over 128 + 290 tokens)"),
+    # not a BASELINE.json config: the reference's scripts/run_finetune_visualbert.sh shape (batch 64, max_seq_length 128, 2 x 36 region features)
+    "visualbert": dict(metric="MARS analogy-examples/sec (VisualBERT-base, bs=64/GPU, 72 regions/128tok)", B=64, L=128, gf=3 * 36.0, params_M=None,
+                       workload="VisualBERT-base MarT fine-tune step (12 post-LN blocks over 128 text tokens + 72 region features), synthetic batch"),
 }
 
 
 def config_dict(name, n_gpus, extra=None):
     w = WORKLOADS[name]
     d = {"workload": w["workload"], "name": name, "batch_per_gpu": w["B"], "global_batch": w["B"] * n_gpus, "seq_len": w["L"],
-         "image": "2x3x384x384" if name == "vilt" else "2x3x224x224",
+         "image": "2x3x384x384" if name == "vilt" else "72 region features x 2048 (Faster-RCNN stand-in)" if name == "visualbert" else "2x3x224x224",
          "score_head": "entity (11292) + relation (192) column groups of a 42007-token vocab" if name == "vilt"
          else "2063 analogy entities of a 42007-token vocab",
          "parallelism": f"dp{n_gpus}",
          "optimizer": "AdamW per layer extent, pipelined behind the backward of the layers below",
-         "dropout": "hidden 0.1 / attention 0.1 (BERT stream, as the reference trains)" if name in ("base", "large") else "off (HF defaults of the family)",
+         "dropout": "hidden 0.1 / attention 0.1 (BERT stream, as the reference trains)" if name in ("base", "large", "visualbert") else "off (HF defaults of the family)",
          "l2": "per-step working set (bf16 weights + >1 GB activations) exceeds the 126 MB L2; 4 rotating batches"}
     if w["params_M"]:
         d["params_M"] = w["params_M"]
@@ -390,7 +393,7 @@ def run_family(args):
     import torch
     import torch.distributed as dist
     import torch.nn.functional as F
-    from mkg_analogy_b200.data import MARS_VOCAB, make_finetune_batch, make_pretrain_batch
+    from mkg_analogy_b200.data import MARS_VOCAB, make_finetune_batch, make_pretrain_batch, make_region_features
 
     world, rank, local = init_dist()
     dev = torch.device("cuda", local)
@@ -403,6 +406,9 @@ def run_family(args):
     if name == "flava":
         from mkg_analogy_b200.modeling_flava import FlavaKGC
         model, S = FlavaKGC(device=dev), 224
+    elif name == "visualbert":
+        from mkg_analogy_b200.modeling_visual_bert import VisualBertKGC
+        model, S = VisualBertKGC(device=dev), 32
     else:
         from mkg_analogy_b200.modeling_vilt import ViltKGC
         model, S = ViltKGC(device=dev), 384
@@ -415,14 +421,18 @@ def run_family(args):
     nb = 4
     mk = (lambda i: make_pretrain_batch(Bp, L, S, voc, seed=4321 + rank * 100 + i, min_len=64)) if name == "vilt" else \
          (lambda i: make_finetune_batch(Bp, L, S, voc, seed=1234 + rank * 100 + i))
-    host = [{k: v.pin_memory() for k, v in mk(i).items()} for i in range(nb)]
+    batches = [mk(i) for i in range(nb)]
+    if name == "visualbert":
+        for i, b in enumerate(batches):
+            b["pixel_values"], b["visual_attention_mask"] = make_region_features(Bp, seed=99 + rank * 100 + i)
+    host = [{k: v.pin_memory() for k, v in b.items()} for b in batches]
     devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
 
     from mkg_analogy_b200 import nn as BN      # [MASK]-row score product on the tcgen05 GEMM + the fused LS-CE kernel
 
     def step(b):
         opt.zero_grad(set_to_none=True)
-        kw = {k: b[k] for k in ("input_ids", "attention_mask", "token_type_ids", "pixel_values") if k in b}
+        kw = {k: b[k] for k in ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "visual_attention_mask") if k in b}
         if "sep_idx" in b:
             kw["sep_idx"] = b["sep_idx"]
         _, trans = model(**kw, output_logits=False)
@@ -440,8 +450,9 @@ def run_family(args):
             loss = BN.mask_row_loss(trans, mpos, E, bias, cols, b["label"])[0]
             ar = torch.arange(B, device=dev)
             cos = F.cosine_similarity
-            sim = torch.relu(cos(trans[ar, b["q_head_idx"]], trans[ar, b["a_head_idx"]], dim=-1)) + 1 - \
-                cos(trans[ar, b["rel_idx"][:, 0]], trans[ar, b["rel_idx"][:, 1]], dim=-1)
+            sh = b["pixel_values"].shape[1] if name == "visualbert" else 0     # transformer.py:98-102 shifts the indices for VisualBertKGC
+            sim = torch.relu(cos(trans[ar, b["q_head_idx"] + sh], trans[ar, b["a_head_idx"] + sh], dim=-1)) + 1 - \
+                cos(trans[ar, b["rel_idx"][:, 0] + sh], trans[ar, b["rel_idx"][:, 1] + sh], dim=-1)
             loss = loss + 0.43 * sim.mean()
         loss.backward()
         if world > 1:      # DDP semantics: mean of the per-rank gradients, a few large buckets

@@ -200,6 +200,15 @@ int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* params16, floa
                        float* exp_avg_sq, int32_t step, float lr, float beta1, float beta2, float eps,
                        float weight_decay, int32_t pretrain, int64_t begin, int64_t end, int32_t zero_grads, void* stream);
 
+/* Per-step scalars in DEVICE memory, for CUDA-graph replay: a captured graph freezes kernel arguments, so what
+ * changes from step to step must be read from memory.  `device_block` = 16 bytes {uint32 salt, float lr, float 1 - beta1^t,
+ * float 1 - beta2^t}, written by the caller (stream-ordered) before each step.  While a block is set, every dropout mask of
+ * b200mart_forward / b200mart_backward is drawn from site_seed ^ salt (site_seed = the one of the forward that was captured) and
+ * b200mart_adamw takes lr and the bias corrections from the block instead of its by-value arguments; the same code path runs eagerly
+ * and under capture.  NULL restores by-value behaviour.  The reference has no counterpart (PyTorch eager re-issues every launch;
+ * MarT/lit_models/base.py:86-91 builds a stock torch.optim.AdamW). */
+int32_t b200mart_set_step_block(b200mart_handle* h, void* device_block);
+
 /* The optimizer step with the data-parallel exchange fused in, over NVSwitch multicast (one kernel = reduce-scatter + AdamW +
  * all-gather): for this rank's shard [begin, end) the mean gradient is pulled with multimem.ld_reduce from grads_mc (multicast
  * address of the symmetric gradient buffers, every rank's local gradients complete), AdamW runs on the rank's own masters /

@@ -51,13 +51,17 @@ struct DropCfg {
     uint32_t site_seed;
     uint32_t thresh;   // 0 = dropout off
     float scale;
+    // optional per-step salt in DEVICE memory, XORed into site_seed by the kernels: lets a captured CUDA graph (whose kernel
+    // arguments are frozen) draw fresh masks at every replay (b200mart_set_step_block)
+    const uint32_t* salt = nullptr;
 };
 __host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
 }
-inline DropCfg make_drop(float p, uint32_t seed, int site) {
+inline DropCfg make_drop(float p, uint32_t seed, int site, const uint32_t* salt = nullptr) {
     DropCfg d;
+    d.salt = (p > 0.f) ? salt : nullptr;
     d.site_seed = hash32(seed + 0x9E3779B9U * (uint32_t)(site + 1));
     d.thresh = (p > 0.f) ? (uint32_t)((double)p * 4294967296.0) : 0u;
     d.scale = (p > 0.f) ? 1.0f / (1.0f - p) : 1.0f;
@@ -91,8 +95,11 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 // multiplier of element `idx` at a dropout site: 0 (dropped) or 1 / (1 - p)
+__device__ __forceinline__ uint32_t drop_seed(const DropCfg& d) {      // site seed of this launch (salted when a step block is set)
+    return d.salt ? (d.site_seed ^ __ldg(d.salt)) : d.site_seed;
+}
 __device__ __forceinline__ float drop_mult(const DropCfg& d, uint32_t idx) {
-    return (hash32(idx ^ d.site_seed) >= d.thresh) ? d.scale : 0.f;
+    return (hash32(idx ^ drop_seed(d)) >= d.thresh) ? d.scale : 0.f;
 }
 
 

@@ -571,7 +571,10 @@ __global__ void scatter_add_kernel(const float* __restrict__ src, const int64_t*
 __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, bf16* __restrict__ p16, const AdamSeg* __restrict__ segs, int nseg,
                              long begin, long n, int zero_grads, float lr, float b1, float b2, float eps, float wd, float bc1,
-                             float bc2) {
+                             float bc2, const float* __restrict__ dyn) {
+    // dyn: device block {salt, lr, 1 - beta1^t, 1 - beta2^t} of the current step (b200mart_set_step_block): the per-step scalars of a
+    // captured CUDA graph, whose kernel arguments are frozen
+    if (dyn) { lr = __ldg(dyn + 1); bc1 = __ldg(dyn + 2); bc2 = __ldg(dyn + 3); }
     // one block per 4096-element chunk; the owning segment is found by binary search on the chunk start
     // (segments are aligned to 8 elements and chunks never straddle an unaligned boundary element-wise: each
     // thread re-checks its own element range).
@@ -910,14 +913,14 @@ int launch_adamw_mc(const float* p, float* m, float* v, float* g_mc, float* p_mc
 }
 
 int launch_adamw(float* p, float* g, float* m, float* v, bf16* p16, const AdamSeg* segs_dev, int nseg, long begin, long end,
-                 int zero_grads, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, cudaStream_t s) {
+                 int zero_grads, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, cudaStream_t s, const float* dyn) {
     B2_CHECK(begin % 8 == 0 && end % 8 == 0 && begin < end, "adamw: range [%ld, %ld) must be non-empty and 8-aligned", begin, end);
     long blocks = (end - begin + 4095) / 4096;
     static int cap = -1;       // B200MART_ADAMW_CTAS: bound of the grid (0 = one block per 4096 elements)
     if (cap < 0) { const char* e = getenv("B200MART_ADAMW_CTAS"); cap = e ? atoi(e) : 0; if (cap < 0) cap = 0; }
     if (cap > 0 && blocks > cap) blocks = cap;
     adamw_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, g, m, v, p16, segs_dev, nseg, begin, end, zero_grads, lr, b1, b2, eps, wd,
-                                                  bc1, bc2);
+                                                  bc1, bc2, dyn);
     B2_LAUNCHED();
     return 0;
 }

@@ -49,7 +49,8 @@ int launch_scatter_add_f32(const float* src, const int64_t* idx, float* dst, int
 struct AdamSeg { long begin, end; int decay; int skip; };
 // over the flat range [begin, end); zero_grads: clear g after use
 int launch_adamw(float* p, float* g, float* m, float* v, bf16* p16, const AdamSeg* segs_dev, int nseg, long begin, long end,
-                 int zero_grads, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, cudaStream_t s);
+                 int zero_grads, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, cudaStream_t s,
+                 const float* dyn = nullptr);   // dyn: device {salt, lr, bc1, bc2} overriding the by-value scalars (graph replay)
 
 // the same on this rank's shard with the exchange fused in (multimem.ld_reduce of the gradients, multimem.st of the result)
 int launch_adamw_mc(const float* p, float* m, float* v, float* g_mc, float* p_mc, bf16* p16_mc, const AdamSeg* segs_dev,

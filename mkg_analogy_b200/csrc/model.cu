@@ -98,6 +98,7 @@ struct b200mart_handle {
     bool training = false;
     float p_hidden = 0.f, p_attn = 0.f;
     uint32_t seed0 = 0, cur_seed = 0;
+    uint32_t* step_block = nullptr;            // device block {salt, lr, 1 - beta1^t, 1 - beta2^t} (b200mart_set_step_block) or null
     unsigned long long fwd_count = 0;
     float cur_ph = 0.f, cur_pa = 0.f;          // probabilities in effect for the forward whose activations are saved
     // two-chain execution: the vision and text streams of the model are independent below the fusion depth
@@ -681,6 +682,7 @@ extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* 
     h->cur_seed = hash32(h->seed0 ^ hash32((uint32_t)h->fwd_count) ^ (uint32_t)(h->fwd_count >> 32));
     const float ph = h->cur_ph, pa = h->cur_pa;
     const uint32_t seed = h->cur_seed;
+    const uint32_t* salt = h->step_block;
 
     // ---- vision embeddings: im2col -> patch GEMM -> (+cls, +pos) -> pre-LN     (modeling_unimo.py:119-132, :711)
     B2_TRY(launch_im2col(batch->pixel_values, w.patches16, B, d.image_size, d.patch, h->patch_ld, sv));
@@ -701,7 +703,7 @@ extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* 
     // ---- text embeddings (:152-186)
     B2_TRY(launch_text_embed_ln(batch->input_ids, batch->token_type_ids, rt.p32(l.word), rt.p32(l.tpos), rt.p32(l.ttype),
                                 rt.p32(l.eln_w), rt.p32(l.eln_b), d.text_eps, w.tpre, w.T32[0], w.T16[0], w.emean, w.erstd, B, L,
-                                H, d.vocab, d.type_vocab, w.status, make_drop(ph, seed, 0), stx));
+                                H, d.vocab, d.type_vocab, w.status, make_drop(ph, seed, 0, salt), stx));
 
     for (int i = 0; i < D; ++i) {
         const bool fused = i >= d.fuse_from;
@@ -740,19 +742,19 @@ extern "C" int32_t b200mart_forward(b200mart_handle* h, const b200mart_buffers* 
             at.key_mask = batch->attention_mask;
             if (batch->sep_idx) { at.sep_idx = batch->sep_idx + 2; at.sep_stride = 6; at.w0 = rt.p32(p.aw0); at.w1 = rt.p32(p.aw1); }
             at.out = a.ctx16; at.ldo = H; at.lse = a.lse;
-            at.drop = make_drop(pa, seed, 1 + 3 * i);
+            at.drop = make_drop(pa, seed, 1 + 3 * i, salt);
             { ProfScope ps(h, stx, CAT_ATTN); B2_TRY(launch_attention_fwd(at, fused ? a.ctx32 : nullptr, stx)); }
             if (fused) ch.wait(stx, ev_vout[i]);       // needs the vision output of this layer index
             if (fused)   // BertFusion on the context with the vision output of THIS layer index (:373, :627)
                 { ProfScope ps(h, stx, CAT_FUSION); B2_TRY(launch_fusion_fwd(a.ctx32, w.V32[i + 1], a.g16, a.flse, B, L, Nv, H, stx)); }
-            rt.drop_next = make_drop(ph, seed, 2 + 3 * i);
+            rt.drop_next = make_drop(ph, seed, 2 + 3 * i, salt);
             B2_TRY(rt.linear(Mt, H, H, a.ctx16, p.ao_w, p.ao_b, 0, nullptr, w.T32[i], a.apre, nullptr));
             B2_TRY(launch_layernorm_fwd(a.apre, rt.p32(p.aln_w), rt.p32(p.aln_b), d.text_eps, a.a32, a.a16, a.amean, a.arstd, Mt, H, stx));
             if (fused)
                 B2_TRY(rt.linear(Mt, F, H, a.a16, p.i_w, p.i_b, 1, a.ipre16, nullptr, nullptr, a.i16, a.g16, p.f_w, p.f_b));
             else
                 B2_TRY(rt.linear(Mt, F, H, a.a16, p.i_w, p.i_b, 1, a.ipre16, nullptr, nullptr, a.i16));
-            rt.drop_next = make_drop(ph, seed, 3 + 3 * i);
+            rt.drop_next = make_drop(ph, seed, 3 + 3 * i, salt);
             B2_TRY(rt.linear(Mt, H, F, a.i16, p.o_w, p.o_b, 0, nullptr, a.a32, a.opre, nullptr));
             B2_TRY(launch_layernorm_fwd(a.opre, rt.p32(p.oln_w), rt.p32(p.oln_b), d.text_eps, w.T32[i + 1], w.T16[i + 1], a.omean, a.orstd, Mt, H, stx));
         }
@@ -928,6 +930,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
     std::vector<cudaEvent_t> ev_tw_done(D + 2, nullptr), ev_vw_done(D + 2, nullptr);
     const float ph = h->cur_ph, pa = h->cur_pa;      // dropout of the forward whose activations are in the workspace
     const uint32_t seed = h->cur_seed;
+    const uint32_t* salt = h->step_block;
     const DropCfg nodrop{0u, 0u, 1.f};
     for (int i = D - 1; i >= 0; --i) {
         const bool fused = i >= d.fuse_from;
@@ -940,7 +943,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             ch.wait(stx, ev_tw_done[i + 2]);          // the side stream is done with this parity's buffers
             // output LayerNorm
             B2_TRY(launch_layernorm_bwd(w.dT, a.opre, a.omean, a.orstd, rt.p32(p.oln_w), nullptr, nullptr, 0, w.t32a, t16a,
-                                        rt.g32(p.oln_w), rt.g32(p.oln_b), rt.g32(p.o_b), Mt, H, stx, nodrop, make_drop(ph, seed, 3 + 3 * i)));
+                                        rt.g32(p.oln_w), rt.g32(p.oln_b), rt.g32(p.o_b), Mt, H, stx, nodrop, make_drop(ph, seed, 3 + 3 * i, salt)));
             ch.wait(stw, ch.mark(stx));
             B2_TRY(rtw.grad_weight(Mt, H, F, t16a, H, a.i16, F, p.o_w, -1));
             // d(pre-GELU) = (dY Wout) * gelu'(pre); its column sums are the intermediate (and fusion_dense) bias gradients
@@ -952,7 +955,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             if (fused) B2_TRY(rt.grad_input(Mt, F, H, tF16, p.f_w, nullptr, 0, nullptr, w.t32c, nullptr));  // d fusion output
             // attention-output LayerNorm
             B2_TRY(launch_layernorm_bwd(w.t32b, a.apre, a.amean, a.arstd, rt.p32(p.aln_w), nullptr, nullptr, 0, w.t32a, t16b,
-                                        rt.g32(p.aln_w), rt.g32(p.aln_b), rt.g32(p.ao_b), Mt, H, stx, nodrop, make_drop(ph, seed, 2 + 3 * i)));
+                                        rt.g32(p.aln_w), rt.g32(p.aln_b), rt.g32(p.ao_b), Mt, H, stx, nodrop, make_drop(ph, seed, 2 + 3 * i, salt)));
             ch.wait(stw, ch.mark(stx));
             B2_TRY(rtw.grad_weight(Mt, H, H, t16b, H, a.ctx16, H, p.ao_w, -1));
             B2_TRY(rt.grad_input(Mt, H, H, t16b, p.ao_w, nullptr, 0, nullptr, w.t32b, nullptr));      // d ctx
@@ -973,7 +976,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
             at.key_mask = batch->attention_mask;
             if (batch->sep_idx) { at.sep_idx = batch->sep_idx + 2; at.sep_stride = 6; at.w0 = rt.p32(p.aw0); at.w1 = rt.p32(p.aw1); ab.dw0 = rt.g32(p.aw0); ab.dw1 = rt.g32(p.aw1); }
             at.lse = a.lse;
-            at.drop = make_drop(pa, seed, 1 + 3 * i);
+            at.drop = make_drop(pa, seed, 1 + 3 * i, salt);
             ab.dout = w.t32b; ab.lddo = H;
             ab.dq = tdqkv16; ab.dk2 = tdqkv16 + H; ab.dv2 = tdqkv16 + 2 * H; ab.ldd = 3 * H;
             if (i + 1 < D && i + 1 >= d.fuse_from) { ab.dk2_add = w.dk1; ab.dv2_add = w.dv1; ab.ldadd = H; }   // from vision layer i+1
@@ -1036,7 +1039,7 @@ extern "C" int32_t b200mart_backward(b200mart_handle* h, const b200mart_buffers*
     }
     // ---- embeddings
     B2_TRY(launch_layernorm_bwd(w.dT, w.tpre, w.emean, w.erstd, rt.p32(l.eln_w), nullptr, nullptr, 0, w.t32a, nullptr,
-                                rt.g32(l.eln_w), rt.g32(l.eln_b), nullptr, Mt, H, stx, make_drop(ph, seed, 0), nodrop));
+                                rt.g32(l.eln_w), rt.g32(l.eln_b), nullptr, Mt, H, stx, make_drop(ph, seed, 0, salt), nodrop));
     B2_TRY(launch_text_embed_bwd(w.t32a, batch->input_ids, batch->token_type_ids, rt.g32(l.word), rt.g32(l.tpos), rt.g32(l.ttype), B, L, H, d.vocab, d.type_vocab, stx));
     if (any_fusion) {
         B2_TRY(launch_layernorm_bwd(w.dV[1], w.vx0, w.vmean0, w.vrstd0, rv.p32(l.preln_w), nullptr, nullptr, 0, w.v32a, nullptr,
@@ -1064,7 +1067,15 @@ extern "C" int32_t b200mart_adamw(b200mart_handle* h, float* params32, void* par
     const double bc1d = 1.0 - pow((double)beta1, (double)step), bc2d = 1.0 - pow((double)beta2, (double)step);
     const float bc1 = (float)bc1d, bc2 = (float)bc2d;
     return launch_adamw(params32, grads32, exp_avg, exp_avg_sq, reinterpret_cast<bf16*>(params16), h->segs_dev[mode],
-                        h->nseg, begin, end, zero_grads, lr, beta1, beta2, eps, weight_decay, bc1, bc2, (cudaStream_t)stream);
+                        h->nseg, begin, end, zero_grads, lr, beta1, beta2, eps, weight_decay, bc1, bc2, (cudaStream_t)stream,
+                        reinterpret_cast<const float*>(h->step_block));
+}
+
+extern "C" int32_t b200mart_set_step_block(b200mart_handle* h, void* device_block) {
+    B2_CHECK(h, "set_step_block: null handle");
+    B2_CHECK(((uintptr_t)device_block & 15) == 0, "set_step_block: the block must be 16-byte aligned");
+    h->step_block = reinterpret_cast<uint32_t*>(device_block);
+    return 0;
 }
 
 extern "C" int32_t b200mart_adamw_multicast(b200mart_handle* h, const float* params32, float* exp_avg, float* exp_avg_sq,

@@ -73,6 +73,21 @@ def _composition(total, parts, g):
     return [edges[i + 1] - edges[i] for i in range(parts)]
 
 
+def make_region_features(B, regions_per_entity=36, dim=2048, seed=77, single_every=3):
+    """Synthetic stand-in for the Faster-RCNN region features VisualBERT / ViLBERT consume (the collator stacks two entities of
+    36 x 2048 features each, MarT/data/data_module.py:129-157): non-negative (post-ReLU) features; every `single_every`-th sample has
+    only ONE entity — its second block is zeros with visual_attention_mask 0, as the collator builds it (:144-152).
+    Returns (pixel_values (B, 72, dim) fp32, visual_attention_mask (B, 72) fp32)."""
+    g = torch.Generator().manual_seed(seed)
+    f = torch.relu(torch.randn(B, 2 * regions_per_entity, dim, generator=g))
+    m = torch.ones(B, 2 * regions_per_entity)
+    for b in range(B):
+        if single_every and b % single_every == single_every - 1:
+            f[b, regions_per_entity:] = 0
+            m[b, regions_per_entity:] = 0
+    return f, m
+
+
 def make_finetune_batch(B, L, image_size=224, vocab: VocabLayout = MARS_VOCAB, seed=1234, pad=True, min_len=24):
     """One fine-tune batch.  Prompt structure per sample (positions):
     [CLS] e_h ... [SEP]0 ... [R] ... [SEP]1 e_t ... [SEP]2 e_q ... [SEP]3 ... [R] ... [SEP]4 ... [MASK] ... [SEP]5 [PAD]*

@@ -281,6 +281,14 @@ class Engine:
     def set_dropout(self, p_hidden, p_attn, seed=0):
         _lib.check(self.l.b200mart_set_dropout(self.h, float(p_hidden), float(p_attn), int(seed) & 0xFFFFFFFF))
 
+    def set_step_block(self, block):
+        """Per-step scalars in device memory (b200mart_set_step_block): a 16-byte CUDA tensor {uint32 salt, float lr, float 1 - beta1^t,
+        float 1 - beta2^t} the kernels read dropout salt / AdamW scalars from, or None to restore by-value arguments."""
+        if block is not None:
+            assert block.is_cuda and block.numel() * block.element_size() == 16 and block.is_contiguous()
+        self._step_block = block                      # keeps the storage alive
+        _lib.check(self.l.b200mart_set_step_block(self.h, _lib.ptr(block)))
+
     def train(self, mode=True):
         """nn.Module.train()/eval(): dropout on/off for the following forward calls."""
         self.set_option("training", 1 if mode else 0)

@@ -120,6 +120,8 @@ class MartTrainer:
         if multicast and self.world > 1 and overlap_comm:
             self._setup_multicast()
         self._dev_batch = None
+        self._graphs = None          # CUDA-graph replay of the step (enable_graphs)
+        self._step_dev = None
         # training-mode dropout of the BERT stream (reference: hidden 0.1, attention 0.1); per-rank seed
         self.dropout = bool(dropout)
         rank = torch.distributed.get_rank(process_group) if self.world > 1 else 0
@@ -293,8 +295,9 @@ class MartTrainer:
             raise IndexError(f"b200mart status flags {flags:#x}: " + "; ".join(names))
 
     # ------------------------------------------------------------------ public API
-    def train_step(self, batch):
-        """One optimizer step on a device-resident batch. Returns the loss as a device tensor (1,)."""
+    def _step_body(self, batch, step, lr):
+        """forward -> [MASK]-row head + loss -> backward with the per-layer exchange / AdamW tail.  Everything here is stream work with
+        device-resident arguments (capturable into a CUDA graph once the shapes are warm)."""
         eng = self.engine
         mb = self._model_inputs(batch)
         eng.train(True)
@@ -302,18 +305,111 @@ class MartTrainer:
             eng.zero_grad()
         eng.forward(mb, want_z=False)
         loss, _, _ = eng.head_loss(mb, self._head(batch), compute_grad=True)
-        lr = linear_warmup_lr(self.steps_done, self.total_steps, self.lr, self.warmup_ratio)
-        self.steps_done += 1
         if self.overlap_comm:
-            self._backward_overlapped(mb, update=(self.steps_done, lr))
+            self._backward_overlapped(mb, update=(step, lr))
             self._grads_clean = True             # AdamW cleared every gradient range it consumed
         else:
             eng.backward(mb)
             self.allreduce_grads()
-            eng.adamw(self.steps_done, lr, weight_decay=self.weight_decay, pretrain=self.pretrain)
+            eng.adamw(step, lr, weight_decay=self.weight_decay, pretrain=self.pretrain)
+        return loss
+
+    def _next_step(self):
+        """Advance the optimizer step counter; returns (step, lr) and, in step-block mode, publishes {salt, lr, 1 - beta1^t,
+        1 - beta2^t} to the device block the kernels read (stream-ordered before the step)."""
+        lr = linear_warmup_lr(self.steps_done, self.total_steps, self.lr, self.warmup_ratio)
+        self.steps_done += 1
+        t = self.steps_done
+        if self._step_dev is not None:
+            k = t % len(self._step_host)
+            if self._step_ev[k] is not None:
+                self._step_ev[k].synchronize()            # the copy that last read this pinned slot has run (never blocks in practice)
+            h = self._step_host[k]
+            x = (self._salt0 + 0x9E3779B9 * t) & 0xFFFFFFFF     # 32-bit mix of (seed, step): the salt of this step's dropout masks
+            x ^= x >> 16
+            x = (x * 0x7FEB352D) & 0xFFFFFFFF
+            x ^= x >> 15
+            x = (x * 0x846CA68B) & 0xFFFFFFFF
+            x ^= x >> 16
+            self.last_salt = x
+            h[0] = x - (1 << 32) if x >= (1 << 31) else x
+            hf = h.view(torch.float32)
+            hf[1], hf[2], hf[3] = lr, 1.0 - 0.9 ** t, 1.0 - 0.999 ** t
+            self._step_dev.copy_(h, non_blocking=True)
+            self._step_ev[k] = torch.cuda.Event()
+            self._step_ev[k].record()
+        return t, lr
+
+    def train_step(self, batch):
+        """One optimizer step on a device-resident batch. Returns the loss as a device tensor (1,)."""
+        if self._graphs is not None:
+            return self._train_step_graphed(batch)
+        step, lr = self._next_step()
+        loss = self._step_body(batch, step, lr)
         if self.status_every and self.steps_done % self.status_every == 0:
             self.check_status()
         return loss
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the step (SURVEY.md §8 d2b)
+    def enable_graphs(self, buckets=(32, 64, 96, 128), warmup=2):
+        """Replay the training step as ONE CUDA graph per (batch size, sequence-length bucket): the ~520 launches of a step, the forks /
+        joins of the library's five streams and the pipelined AdamW tail are captured once (after `warmup` eager steps of that shape
+        have created the GEMM plans and the workspace) and re-issued with a single cudaGraphLaunch.  What changes per step lives in
+        memory: the batch is copied into the graph's static input buffers (text rows zero-padded up to the bucket: padded keys are
+        masked by the additive -1e4, padded rows feed nothing, so the real rows' results are those of the unpadded call), and the
+        dropout salt / learning rate / AdamW bias corrections are read from the device step block (b200mart_set_step_block).
+        One process per GPU without a gradient exchange only (world size 1); returns self."""
+        if self.world != 1:
+            raise NotImplementedError("graph replay covers the single-GPU step (the exchange paths run eagerly)")
+        self._graphs = {"buckets": tuple(sorted(int(b) for b in buckets)), "warmup": int(warmup), "entries": {}}
+        self._enable_step_block()
+        return self
+
+    def _enable_step_block(self):
+        if self._step_dev is None:
+            self._step_host = [torch.zeros(4, dtype=torch.int32).pin_memory() for _ in range(8)]
+            self._step_ev = [None] * 8
+            self._step_dev = torch.zeros(4, dtype=torch.int32, device=self.device)
+            self._salt0 = (0x51ED27 * (self.rank + 1) + 977 * int(torch.initial_seed())) & 0xFFFFFFFF
+            self.last_salt = 0
+            self.engine.set_step_block(self._step_dev)
+
+    def _train_step_graphed(self, batch):
+        g = self._graphs
+        B, L = batch["input_ids"].shape
+        Lb = next((b for b in g["buckets"] if b >= L), None)
+        if Lb is None:
+            raise ValueError(f"sequence length {L} exceeds the largest graph bucket {g['buckets'][-1]}")
+        keys = tuple(sorted(k for k in batch if k in BATCH_KEYS and k != "pixel_idx"))
+        ent = g["entries"].get((B, Lb, keys))
+        if ent is None:
+            static = {}
+            for k in keys:
+                v = batch[k]
+                shape = (B, Lb) if k in ("input_ids", "attention_mask", "token_type_ids") else tuple(v.shape)
+                static[k] = torch.zeros(shape, dtype=v.dtype, device=self.device)
+            ent = g["entries"][(B, Lb, keys)] = {"static": static, "n": 0, "graph": None, "loss": None}
+        for k, dst in ent["static"].items():
+            src = batch[k]
+            if dst.shape != src.shape:                  # text rows: pad up to the bucket ([PAD] = 0, attention_mask 0)
+                dst[:, :L].copy_(src)
+                dst[:, L:].zero_()
+            elif dst.data_ptr() != src.data_ptr():
+                dst.copy_(src)
+        step, lr = self._next_step()
+        if ent["n"] < g["warmup"]:
+            ent["loss"] = self._step_body(ent["static"], step, lr)
+        else:
+            if ent["graph"] is None:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    ent["loss"] = self._step_body(ent["static"], step, lr)
+                ent["graph"] = graph
+            ent["graph"].replay()
+        ent["n"] += 1
+        if self.status_every and self.steps_done % self.status_every == 0:
+            self.check_status()
+        return ent["loss"]
 
     def attach_image_table(self, table):
         """Serve `pixel_values` from a device-resident `EntityImageTable`: host batches then carry `pixel_idx`

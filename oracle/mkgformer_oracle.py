@@ -349,11 +349,46 @@ def preln_stack(P, x, heads, eps=1e-12, act="gelu", attention_mask=None, sep_spl
     return x
 
 
-def hash_dropout(seed, p_hidden, p_attn):
+def postln_stack(P, x, heads, eps=1e-12, attention_mask=None, sep_split=None, row_lo=1, drop=None, prefix=""):
+    """VisualBertEncoder (modeling_visual_bert.py:424-488 over VisualBertLayer :381-421, VisualBertSelfAttention :203-286,
+    VisualBertSelfOutput :289-300, VisualBertOutput :367-378): post-LayerNorm BERT blocks with the adaptive scaling of :255-260
+    (rows img_length+1 : s' -> row_lo = img_length + 1).  P: {"layer.i....": tensor} with the HF names; attention_mask (B, T) 1 = keep;
+    drop: explicit-mask dropout callback, sites as in preln_stack."""
+    B, T, H = x.shape
+    d = H // heads
+    n_layers = 1 + max(int(k[len(prefix):].split(".")[1]) for k in P if k.startswith(prefix + "layer."))
+    ext = None if attention_mask is None else (1.0 - attention_mask[:, None, None, :].to(x.dtype)) * -10000.0
+    for i in range(n_layers):
+        p = f"{prefix}layer.{i}."
+        q = _heads(F.linear(x, P[p + "attention.self.query.weight"], P[p + "attention.self.query.bias"]), heads)
+        k = _heads(F.linear(x, P[p + "attention.self.key.weight"], P[p + "attention.self.key.bias"]), heads)
+        v = _heads(F.linear(x, P[p + "attention.self.value.weight"], P[p + "attention.self.value.bias"]), heads)
+        sc = (q @ k.transpose(-1, -2)) / math.sqrt(d)
+        if sep_split is not None:
+            sc = adaptive_scale_rows(sc, sep_split, P[p + "attention.self.adaptive_weight.0"], P[p + "attention.self.adaptive_weight.1"], row_lo)
+        if ext is not None:
+            sc = sc + ext
+        pr = torch.softmax(sc, dim=-1)
+        if drop is not None:
+            pr = drop(1 + 3 * i, pr)
+        ctx = (pr @ v).permute(0, 2, 1, 3).reshape(B, T, H)
+        ao = F.linear(ctx, P[p + "attention.output.dense.weight"], P[p + "attention.output.dense.bias"])
+        if drop is not None:
+            ao = drop(2 + 3 * i, ao)
+        h = layer_norm(x + ao, P[p + "attention.output.LayerNorm.weight"], P[p + "attention.output.LayerNorm.bias"], eps)
+        f = F.gelu(F.linear(h, P[p + "intermediate.dense.weight"], P[p + "intermediate.dense.bias"]))
+        fo = F.linear(f, P[p + "output.dense.weight"], P[p + "output.dense.bias"])
+        if drop is not None:
+            fo = drop(3 + 3 * i, fo)
+        x = layer_norm(h + fo, P[p + "output.LayerNorm.weight"], P[p + "output.LayerNorm.bias"], eps)
+    return x
+
+
+def hash_dropout(seed, p_hidden, p_attn, salt=0):
     """drop(site, tensor) callback reproducing the CUDA path's stateless dropout masks (csrc/common.cuh: keep element e of
     site s iff hash32(e ^ hash32(seed + 0x9E3779B9 (s + 1))) >= p 2^32; kept values scaled by 1/(1-p) in fp32), so the
     training-mode graph can be checked against the oracle mask for mask.  Sites: 0 embeddings, 1+3i attention probabilities
-    (p_attn), 2+3i / 3+3i sub-layer outputs."""
+    (p_attn), 2+3i / 3+3i sub-layer outputs.  salt: the per-step word of b200mart_set_step_block (XORed into every site seed)."""
     import numpy as np
     M = 0xFFFFFFFF
 
@@ -370,7 +405,7 @@ def hash_dropout(seed, p_hidden, p_attn):
             return t
         thresh = int(np.float64(p) * 4294967296.0)
         scale = float(np.float32(1.0) / (np.float32(1.0) - p))
-        site_seed = int(h32(torch.tensor((seed + 0x9E3779B9 * (site + 1)) & M, dtype=torch.int64)))
+        site_seed = int(h32(torch.tensor((seed + 0x9E3779B9 * (site + 1)) & M, dtype=torch.int64))) ^ (salt & M)
         idx = torch.arange(t.numel(), dtype=torch.int64, device=t.device)
         keep = h32(idx ^ site_seed) >= thresh
         return t * (keep.to(t.dtype) * scale).view(t.shape)

@@ -72,6 +72,23 @@ def load_vilt():
     return load_module("ref_vilt", "models/modeling_vilt.py")
 
 
+def load_visual_bert():
+    """modeling_visual_bert.py under transformers 5.x: its classes call the 4.x `init_weights()` from `__init__` (5.x expects
+    `post_init()` to have run first), so the module's base class gets the 4.x behaviour back (apply `_init_weights`; the callers tie the
+    decoder themselves); configs additionally need `is_decoder` / `torchscript` attributes (see `visual_bert_config`)."""
+    m = load_module("ref_visual_bert", "models/modeling_visual_bert.py")
+    m.VisualBertPreTrainedModel.init_weights = lambda self: self.apply(self._init_weights)
+    return m
+
+
+def visual_bert_config(**kw):
+    from transformers import VisualBertConfig
+    cfg = VisualBertConfig(**kw)
+    cfg.is_decoder = False            # read at modeling_visual_bert.py:1640; no longer a config attribute in 5.x
+    cfg.torchscript = False
+    return cfg
+
+
 def build_reference_model(cfg, params=None):
     """Instantiate the reference `UnimoForMaskedLM` for `cfg` (MarT/main.py:76-86 construction, then
     resize_token_embeddings as lit_models/transformer.py:33,43 does) and optionally load `params`."""

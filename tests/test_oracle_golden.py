@@ -254,3 +254,57 @@ def test_base_eval_split_oracle_ranks_first_batch(base_fixture):
     r = O.ranks_of_gold(x, b["label"])
     assert torch.equal(r, s["ranks"][: s["bs"]].to(torch.int64))
     assert s["gold_margin"].min().item() > 0.25 and bool((s["ranks"] == 1).all())     # the split is decidable by construction
+
+
+def test_postln_stack_oracle_vs_reference_visual_bert_encoder():
+    """oracle.postln_stack against outputs / gradients of the reference VisualBertEncoder (modeling_visual_bert.py:424-488, adaptive
+    scaling :255-260 with img_length = 16) stored by oracle/make_golden_visual_bert.py::stack_case."""
+    c = torch.load(os.path.join(GOLD, "postln_stack.pt"), weights_only=False)
+    P = {k: v.clone().requires_grad_(True) for k, v in c["params"].items()}
+    x = c["x"].clone().requires_grad_(True)
+    y = O.postln_stack(P, x, 2, attention_mask=c["mask"], sep_split=c["sep"][:, 2], row_lo=c["row_lo"])
+    y.backward(c["gy"])
+    assert torch.allclose(y, c["y"], atol=1e-5, rtol=1e-5)
+    assert torch.allclose(x.grad, c["dx"], atol=1e-5, rtol=1e-4)
+    for n, gr in c["grads"].items():
+        assert torch.allclose(P[n].grad, gr, atol=1e-5, rtol=1e-4), n
+    for n, ref_norm in c["grad_norm"].items():
+        assert abs(P[n].grad.norm().item() - ref_norm) <= 2e-4 * ref_norm + 1e-7, n
+
+
+def test_visual_bert_dropin_plumbing_vs_reference_golden():
+    """VisualBertKGC's plumbing (text + visual embeddings with ONE LayerNorm over [text ; regions], visual token type 1 / visual position
+    0, [attention_mask ; visual_attention_mask], sep_idx + img_length on a copy, head over all L + n_regions rows, tied decoder) with the
+    ORACLE post-LN stack injected as the encoder (test infrastructure only) == reference VisualBertForMaskedLM."""
+    from mkg_analogy_b200.modeling_visual_bert import VisualBertKGC
+    c = torch.load(os.path.join(GOLD, "visual_bert_tiny.pt"), weights_only=False)
+    m = VisualBertKGC(device="cpu", **c["cfg"])
+    missing, unexpected = m.load_state_dict(c["params"], strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    m.tie_weights()
+
+    class OracleEncoder(torch.nn.Module):
+        def __init__(self, st):
+            super().__init__()
+            self.st = st
+
+        def forward(self, x, attention_mask=None, sep_idx=None, row_lo=1):
+            return O.postln_stack(dict(self.st.named_parameters()), x, c["cfg"]["num_attention_heads"], attention_mask=attention_mask,
+                                  sep_split=None if sep_idx is None else sep_idx[:, 2], row_lo=row_lo)
+    m.visual_bert.encoder = OracleEncoder(m.visual_bert.encoder)
+    m.eval()
+    sep = c["sep_idx"].clone()
+    out = m(input_ids=c["input_ids"], attention_mask=c["attention_mask"], token_type_ids=c["token_type_ids"], pixel_values=c["pixel_values"],
+            visual_attention_mask=c["visual_attention_mask"], sep_idx=sep)
+    assert torch.equal(sep, c["sep_idx"])                 # unlike the reference (:876), the caller's sep_idx is not mutated
+    assert out[0].logits.shape == c["logits"].shape       # (B, L + n_regions, V)
+    assert torch.allclose(out[0].logits, c["logits"], atol=2e-5, rtol=1e-4)
+    assert torch.allclose(out[1], c["trans"], atol=2e-5, rtol=1e-4)
+    ((out[0].logits * c["gl"]).sum() + (out[1] * c["gt"]).sum()).backward()
+    prm = dict(m.named_parameters())
+    for n, gr in c["grads"].items():
+        key = n.replace("visual_bert.encoder.", "visual_bert.encoder.st.")
+        assert torch.allclose(prm[key].grad, gr, atol=2e-5, rtol=2e-4), n
+    assert m.get_output_embeddings().weight is m.get_input_embeddings().weight
+    emb = m.resize_token_embeddings(420)
+    assert emb.weight.shape[0] == 420 and m.get_output_embeddings().weight is emb.weight and m.cls.predictions.bias.shape[0] == 420
