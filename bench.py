@@ -255,6 +255,13 @@ def run_mkgformer(args):
 
     sampler = ClockSampler(local) if rank == 0 else None
     # ---------------- device-resident timing
+    graphed = not args.no_graph and world == 1 and not args.no_overlap
+    per_step_launches = None
+    if graphed:      # two eager steps per shape (plans, workspace), then ONE captured graph per step
+        trainer.enable_graphs(buckets=(L,), warmup=2)
+        lc = trainer.engine.launch_count()
+        trainer.train_step(devb[0])
+        per_step_launches = trainer.engine.launch_count() - lc       # kernels one replay re-issues (the counter ticks at capture only)
     for i in range(W):
         trainer.train_step(devb[i % nb])
     barrier()
@@ -268,6 +275,8 @@ def run_mkgformer(args):
     barrier()
     t1 = time.perf_counter()
     launches = trainer.engine.launch_count() - l0
+    if graphed:
+        launches = per_step_launches * K
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -325,6 +334,7 @@ def run_mkgformer(args):
     # ---------------- per-kernel-family device time (separate profiled pass, same steps, chains serialised)
     roof = None
     np_steps = 3
+    trainer._graphs = None                         # the profiled pass issues its launches eagerly
     trainer.engine.set_option("streams", 0)        # serial launches: clean per-kernel durations
     trainer.engine.profile_begin()
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -371,7 +381,9 @@ def run_mkgformer(args):
         line = {"metric": w["metric"], "value": Bp * world * K / (ms_total * 1e-3), "unit": "examples/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": config_dict(name, world, {"parallelism": f"dp{world}", "gradient_exchange": exchange}),
+                "config": config_dict(name, world, {"parallelism": f"dp{world}", "gradient_exchange": exchange,
+                                                    "launch": "one CUDA graph per step (captured after 2 eager steps; per-step scalars in a device block)"
+                                                    if graphed else "eager: every kernel launched from the host each step"}),
                 "clocks": clocks, "gpu_launches": int(launches), "final_loss": loss_val,
                 "e2e": {"value": e2e_rate, "unit": "examples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "api": "MartTrainer.train_step_host_async (pinned host batch in: ids / masks / labels + (B, 2) rows of the "
@@ -539,6 +551,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="base", choices=list(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true", help="N = 1: launch every kernel from the host each step instead of replaying the "
+                                                            "step as one CUDA graph (MartTrainer.enable_graphs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / gpu_eager_baseline legs (profiling runs)")
     ap.add_argument("--no-overlap", action="store_true", help="run the gradient exchange / AdamW after backward instead of pipelined per layer")
     ap.add_argument("--shard", action="store_true", help="N > 1, NCCL route: reduce-scatter + sharded AdamW + all-gather instead of all-reduce + replicated AdamW")

@@ -215,11 +215,12 @@ int32_t b200mart_set_step_block(b200mart_handle* h, void* device_block);
  * moments, and the new fp32 parameters and their bf16 mirror are stored through multimem.st to params32_mc / params16_mc
  * (multicast addresses of the symmetric parameter buffers): every replica receives the same bits.  The caller runs a cross-rank
  * barrier before the call (every rank's local gradients of the range are complete) and one after it (every shard has been read:
- * each rank may now clear its own gradient replica; every new parameter has been delivered). */
+ * each rank may now clear its own gradient replica; every new parameter has been delivered).  max_ctas bounds the grid (0 =
+ * the default of 32 CTAs, which leaves the SMs to the backward pass the call overlaps; extents exchanged after backward take more). */
 int32_t b200mart_adamw_multicast(b200mart_handle* h, const float* params32, float* exp_avg, float* exp_avg_sq,
                                  float* grads_mc, float* params32_mc, void* params16_mc, int32_t step, float lr,
                                  float beta1, float beta2, float eps, float weight_decay, int32_t pretrain, int64_t begin,
-                                 int64_t end, int32_t world, void* stream);
+                                 int64_t end, int32_t world, int32_t max_ctas, void* stream);
 
 /* Device-side status flags of the last calls on this workspace (synchronises the stream):
  * bit0 token id out of range, bit1 token type out of range, bit2 a row without exactly one [MASK], bit3 a label or a

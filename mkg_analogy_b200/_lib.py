@@ -120,7 +120,7 @@ SYMBOLS = {
     "b200mart_read_hidden": (i32, [vp, C.POINTER(Buffers), i32, i32, vp, vp]),
     "b200mart_multimem_add": (i32, [vp, vp, i64, f32, vp]),
     "b200mart_set_step_block": (i32, [vp, vp]),
-    "b200mart_adamw_multicast": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, i32, i64, i64, i32, vp]),
+    "b200mart_adamw_multicast": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, i32, i64, i64, i32, i32, vp]),
     "b200mart_stack_create": (i32, [C.POINTER(StackDesc), C.POINTER(vp)]),
     "b200mart_stack_destroy": (None, [vp]),
     "b200mart_stack_param_count": (i32, [vp]),

@@ -900,11 +900,12 @@ int launch_scatter_add_f32(const float* src, const int64_t* idx, float* dst, int
 }
 int launch_adamw_mc(const float* p, float* m, float* v, float* g_mc, float* p_mc, bf16* p16_mc, const AdamSeg* segs_dev,
                     int nseg, long begin, long end, float inv_world, float lr, float b1, float b2, float eps, float wd, float bc1,
-                    float bc2, cudaStream_t s) {
+                    float bc2, cudaStream_t s, int max_ctas) {
     B2_CHECK(begin % 8 == 0 && end % 8 == 0 && begin < end, "adamw_mc: range [%ld, %ld) must be non-empty and 8-aligned", begin, end);
     long blocks = (end - begin + 4L * MCT * MCQ - 1) / (4L * MCT * MCQ);
-    static int cap = -1;       // B200MART_MC_CTAS: bound of the grid (0 = one block per 32768 elements)
-    if (cap < 0) { const char* e = getenv("B200MART_MC_CTAS"); cap = e ? atoi(e) : 32; if (cap < 0) cap = 0; }
+    static int env_cap = -1;   // B200MART_MC_CTAS: bound of the grid (0 = one block per 32768 elements)
+    if (env_cap < 0) { const char* e = getenv("B200MART_MC_CTAS"); env_cap = e ? atoi(e) : 32; if (env_cap < 0) env_cap = 0; }
+    const int cap = max_ctas > 0 ? max_ctas : env_cap;     // the caller widens the grid for extents it exchanges after backward
     if (cap > 0 && blocks > cap) blocks = cap;
     adamw_mc_kernel<<<(unsigned)blocks, MCT, 0, s>>>(p, m, v, g_mc, p_mc, p16_mc, segs_dev, nseg, begin, end, inv_world, lr, b1, b2,
                                                     eps, wd, bc1, bc2);

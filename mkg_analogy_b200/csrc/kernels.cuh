@@ -55,7 +55,7 @@ int launch_adamw(float* p, float* g, float* m, float* v, bf16* p16, const AdamSe
 // the same on this rank's shard with the exchange fused in (multimem.ld_reduce of the gradients, multimem.st of the result)
 int launch_adamw_mc(const float* p, float* m, float* v, float* g_mc, float* p_mc, bf16* p16_mc, const AdamSeg* segs_dev,
                     int nseg, long begin, long end, float inv_world, float lr, float b1, float b2, float eps, float wd, float bc1,
-                    float bc2, cudaStream_t s);
+                    float bc2, cudaStream_t s, int max_ctas = 0);
 
 // entity-image table gather (collator replacement, MarT/data/data_module.py:127-160): out[i] = table[idx[i]], zeros for idx < 0
 int launch_gather_images(const void* table, int table_is_bf16, const int64_t* idx, float* out, int n_images, long image_elems,

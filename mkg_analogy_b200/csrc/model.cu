@@ -1081,7 +1081,7 @@ extern "C" int32_t b200mart_set_step_block(b200mart_handle* h, void* device_bloc
 extern "C" int32_t b200mart_adamw_multicast(b200mart_handle* h, const float* params32, float* exp_avg, float* exp_avg_sq,
                                             float* grads_mc, float* params32_mc, void* params16_mc, int32_t step, float lr,
                                             float beta1, float beta2, float eps, float weight_decay, int32_t pretrain, int64_t begin,
-                                            int64_t end, int32_t world, void* stream) {
+                                            int64_t end, int32_t world, int32_t max_ctas, void* stream) {
     B2_CHECK(h && params32 && exp_avg && exp_avg_sq && grads_mc && params32_mc && params16_mc && step >= 1 && world >= 1,
              "adamw_multicast: bad arguments");
     B2_CHECK(begin >= 0 && begin < end && end <= h->lay.total, "adamw_multicast: bad range [%ld, %ld)", (long)begin, (long)end);
@@ -1093,7 +1093,7 @@ extern "C" int32_t b200mart_adamw_multicast(b200mart_handle* h, const float* par
     const double bc1d = 1.0 - pow((double)beta1, (double)step), bc2d = 1.0 - pow((double)beta2, (double)step);
     return launch_adamw_mc(params32, exp_avg, exp_avg_sq, grads_mc, params32_mc, reinterpret_cast<bf16*>(params16_mc), h->segs_dev[mode],
                            h->nseg, begin, end, 1.0f / (float)world, lr, beta1, beta2, eps, weight_decay, (float)bc1d, (float)bc2d,
-                           (cudaStream_t)stream);
+                           (cudaStream_t)stream, max_ctas);
 }
 
 // --------------------------------------------------------------------------------------- profiling

@@ -153,7 +153,7 @@ class Engine:
         self.mirror_stale = False
 
     def adamw_multicast(self, step, lr, grads_mc, params32_mc, params16_mc, world, begin, end, betas=(0.9, 0.999), eps=1e-8,
-                        weight_decay=0.01, pretrain=False):
+                        weight_decay=0.01, pretrain=False, max_ctas=0):
         """This rank's shard [begin, end) of the fused reduce-scatter + AdamW + all-gather over NVSwitch multicast
         (b200mart_adamw_multicast); *_mc are the multicast base addresses of the symmetric gradient / parameter buffers."""
         self._need_cuda()
@@ -163,7 +163,7 @@ class Engine:
         _lib.check(self.l.b200mart_adamw_multicast(self.h, self.params32.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                                                    int(grads_mc), int(params32_mc), int(params16_mc), int(step), float(lr),
                                                    float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(pretrain),
-                                                   int(begin), int(end), int(world), _lib.cur_stream()))
+                                                   int(begin), int(end), int(world), int(max_ctas), _lib.cur_stream()))
         self.mirror_stale = False
 
     def cast_range(self, begin, end):

@@ -106,17 +106,17 @@ class MartTrainer:
         # the sharded optimizer that pays.
         self.shard_optimizer = bool(shard_optimizer) and self.world > 1
         self.rank = torch.distributed.get_rank(process_group) if self.world > 1 else 0
-        # NVSwitch multicast exchange (default for N >= 3 when the box supports it; B200MART_MULTICAST=1 / 0 or multicast=True /
-        # False force it on / off): gradients, fp32 masters and the bf16 mirror live in symmetric memory; ONE kernel per layer
-        # extent pulls the mean gradient of the rank's shard with multimem.ld_reduce, applies AdamW and stores the result in every
-        # replica with multimem.st.  Measured (profiles/scaling_r2.txt): 8 GPUs 8.86 ms / step against 9.54 ms with NCCL
-        # all-reduce; 2 GPUs 8.52 against 8.33 ms, hence the N >= 3 default.
+        # NVSwitch multicast exchange (default for N >= 2 when the box supports it; B200MART_MULTICAST=1 / 0 or multicast=True /
+        # False force it on / off): gradients (two buffers, alternating per step), fp32 masters and the bf16 mirror live in
+        # symmetric memory; ONE kernel per layer extent pulls the mean gradient of the rank's shard with multimem.ld_reduce, applies
+        # AdamW and stores the result in every replica with multimem.st.  Measured (profiles/scaling_r2.txt): 8 GPUs 8.17 ms / step
+        # against 9.54 ms with NCCL all-reduce; 2 GPUs 8.17 against 8.33 ms.
         self._mc = None
         self._mc_prev = None
         if multicast is None:
             import os
             env = os.environ.get("B200MART_MULTICAST")
-            multicast = (self.world >= 3) if env is None else (env != "0")
+            multicast = (self.world >= 2) if env is None else (env != "0")
         if multicast and self.world > 1 and overlap_comm:
             self._setup_multicast()
         self._dev_batch = None
@@ -147,6 +147,7 @@ class MartTrainer:
     def _setup_multicast(self):
         """Re-home grads32 / params32 / params16 in torch symmetric memory and fetch their multicast addresses.  Any failure
         (no NVSwitch multicast on this box, old driver) leaves the NCCL path in place."""
+        import os
         import torch.distributed as dist
         try:
             import torch.distributed._symmetric_memory as symm_mem
@@ -160,10 +161,20 @@ class MartTrainer:
                 if not hdl.multicast_ptr:
                     raise RuntimeError("no multicast address (NVSwitch multicast unavailable)")
                 out[name] = (t, hdl)
+            # second gradient buffer: step t accumulates into one while the other (consumed by step t - 1) is cleared off the
+            # critical path
+            g2 = symm_mem.empty(eng.grads32.numel(), dtype=eng.grads32.dtype, device=self.device)
+            g2.zero_()
+            h2 = symm_mem.rendezvous(g2, group=group)
+            if not h2.multicast_ptr:
+                raise RuntimeError("no multicast address (NVSwitch multicast unavailable)")
             for name, (t, _) in out.items():
                 setattr(eng, name, t)
             eng.ws_key = None
             self._mc = {k: h for k, (_, h) in out.items()}
+            self._mc_grads = [(out["grads32"][0], out["grads32"][1]), (g2, h2)]
+            self._mc_cur = 0
+            self._mc_tail_ctas = int(os.environ.get("B200MART_MC_TAIL_CTAS", "128"))
             torch.cuda.synchronize(self.device)
         except Exception as e:      # noqa: BLE001
             import warnings
@@ -210,21 +221,22 @@ class MartTrainer:
         # N > 1: the exchange (NVLink-bound) and the update (HBM-bound) of consecutive layers overlap on two side streams
         upd = self._update_stream if (self.world > 1 and update is not None) else comm
 
-        def finish(b, e):
+        def finish(b, e, tail=False):
             if self._mc is not None and update is not None and (e - b) % (8 * self.world) == 0:
-                # fused exchange + update of the extent [b, e) over NVSwitch multicast; this rank owns [sb, se)
+                # fused exchange + update of the extent [b, e) over NVSwitch multicast; this rank owns [sb, se).
+                # The barrier (every rank's local gradients of this extent are complete) runs on the exchange stream, AHEAD of the
+                # update stream: waiting for the slowest rank's layer never delays the optimizer kernel of the extent before.
                 S = (e - b) // self.world
                 sb, se = b + self.rank * S, b + (self.rank + 1) * S
-                hg = self._mc["grads32"]
-                # ONE barrier per extent: every rank's local gradients of this extent are complete - and, because every rank
-                # queued it behind its fused kernel of the PREVIOUS extent, every shard of that extent has been read and its new
-                # parameters delivered: the previous extent's gradient replica can be cleared locally
+                hg = self._mc_grads[self._mc_cur][1]
                 hg.barrier(channel=0)
-                if self._mc_prev is not None:
-                    g[self._mc_prev[0]:self._mc_prev[1]].zero_()
-                eng.adamw_multicast(update[0], update[1], hg.multicast_ptr, self._mc["params32"].multicast_ptr,
-                                    self._mc["params16"].multicast_ptr, self.world, sb, se, weight_decay=self.weight_decay,
-                                    pretrain=self.pretrain)
+                ev = torch.cuda.Event()
+                ev.record(comm)
+                upd.wait_event(ev)
+                with torch.cuda.stream(upd):
+                    eng.adamw_multicast(update[0], update[1], hg.multicast_ptr, self._mc["params32"].multicast_ptr,
+                                        self._mc["params16"].multicast_ptr, self.world, sb, se, weight_decay=self.weight_decay,
+                                        pretrain=self.pretrain, max_ctas=self._mc_tail_ctas if tail else 0)
                 self._mc_prev = (b, e)
                 return
             if self.shard_optimizer and update is not None and (e - b) % (8 * self.world) == 0:
@@ -276,11 +288,22 @@ class MartTrainer:
             for b0, e0 in ((0, lo), (hi, g.numel())):
                 if e0 > b0:
                     for b, e in bucket_bounds(e0 - b0, self._tail_chunks):
-                        finish(b0 + b, b0 + e)
-            if self._mc is not None and self._mc_prev is not None:      # closing barrier of the step (see finish)
-                self._mc["grads32"].barrier(channel=0)
-                g[self._mc_prev[0]:self._mc_prev[1]].zero_()
-                self._mc_prev = None
+                        finish(b0 + b, b0 + e, tail=True)
+        if self._mc is not None and self._mc_prev is not None:
+            # closing barrier of the step, behind this rank's last optimizer kernel: every rank has read every shard of this step's
+            # gradient buffer and delivered every new parameter.  The next step may start; the consumed buffer is cleared on the
+            # update stream while the next step's forward runs (that step accumulates into the other buffer).
+            with torch.cuda.stream(upd):
+                self._mc_grads[self._mc_cur][1].barrier(channel=1)
+                done = torch.cuda.Event()
+                done.record(upd)
+                g.zero_()
+            main.wait_event(done)
+            main.wait_stream(comm)
+            self._mc_prev = None
+            self._mc_cur ^= 1
+            eng.grads32 = self._mc_grads[self._mc_cur][0]
+            return
         if upd is not comm:
             main.wait_stream(upd)
         main.wait_stream(comm)

@@ -61,17 +61,34 @@ def analyse(events, out):
 
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+    # under torchrun (N > 1): every rank steps, rank 0 is profiled (its kernels + the exchange kernels that run on its GPU)
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
     tr = MartTrainer(BASE, MARS_VOCAB, total_steps=1000)
     init_weights_(tr.engine, 0)
-    batch = {k: v.cuda() for k, v in make_finetune_batch(32, 64, BASE.image_size, MARS_VOCAB, seed=1).items()}
+    batch = {k: v.cuda() for k, v in make_finetune_batch(32, 64, BASE.image_size, MARS_VOCAB, seed=1 + 100 * rank).items()}
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for _ in range(5):
         tr.train_step(batch)
-    torch.cuda.synchronize()
-    marks = []
+    sync()
+    if rank != 0:
+        for i in range(3):
+            tr.train_step(batch)
+            sync()
+        dist.destroy_process_group()
+        return
     with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA, torch.profiler.ProfilerActivity.CPU]) as prof:
         for i in range(3):
             tr.train_step(batch)
-            torch.cuda.synchronize()      # step boundaries: kernels of step i end before step i+1 starts
+            sync()                        # step boundaries: kernels of step i end before step i+1 starts
     os.makedirs("gpurun_out", exist_ok=True)
     path = f"gpurun_out/timeline_{tag}.json"
     prof.export_chrome_trace(path)
@@ -97,6 +114,8 @@ def main():
         print(f"{len(steps)} steps found; analysing the last", file=out)
         analyse(steps[-1], out)
     print(open(f"gpurun_out/timeline_{tag}.txt").read())
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
