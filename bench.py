@@ -519,6 +519,22 @@ def run_family(args):
         dist.all_reduce(s, op=dist.ReduceOp.MAX)
     if sampler:
         sampler.stop()
+    if args.timeline and rank == 0 and world == 1:      # CUPTI kernel timeline of two steps (profiling runs; after the timed regions)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import timeline as TL
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+            for i in range(2):
+                step(devb[i % nb])
+                torch.cuda.synchronize()
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        tp = os.path.join(ROOT, "gpurun_out", f"timeline_{name}.json")
+        prof.export_chrome_trace(tp)
+        with open(tp) as f:
+            ev = [e for e in json.load(f)["traceEvents"] if e.get("cat") == "kernel"]
+        os.remove(tp)
+        with open(os.path.join(ROOT, "gpurun_out", f"timeline_{name}.txt"), "w") as out:
+            print(f"bench.py --config {name} --timeline: kernels of two steps (bs {Bp})", file=out)
+            TL.analyse(ev, out)
     if rank == 0:
         peak_tf, peak_src = measured_peaks()
         step_ms = ms_total / K
@@ -553,6 +569,7 @@ def main():
     ap.add_argument("--config", default="base", choices=list(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="N = 1: launch every kernel from the host each step instead of replaying the "
                                                             "step as one CUDA graph (MartTrainer.enable_graphs)")
+    ap.add_argument("--timeline", action="store_true", help="flava / vilt / visualbert, N = 1: also write a CUPTI kernel summary of two steps to gpurun_out/")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / gpu_eager_baseline legs (profiling runs)")
     ap.add_argument("--no-overlap", action="store_true", help="run the gradient exchange / AdamW after backward instead of pipelined per layer")
     ap.add_argument("--shard", action="store_true", help="N > 1, NCCL route: reduce-scatter + sharded AdamW + all-gather instead of all-reduce + replicated AdamW")

@@ -657,6 +657,269 @@ attn_bwd_keys_mma(const AttnBwd gr, const float* __restrict__ delta) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ backward, tiled two-pass
+// The two passes above for LONG sequences (FLAVA 197 / 458 tokens, ViLT 418, VisualBERT 200, MKGformer-large 513 + prefix), where
+// one CTA of four warps per (head, sample) with every key (or query row) resident in shared memory left 2 CTAs per SM walking
+// 4 - 9 rounds of 16-row blocks through a ~8,000-instruction straight-line body (CUPTI: 40 % of the FLAVA / ViLT / VisualBERT
+// steps).  Here the (head, sample) work is split over gridDim.z CTAs - warp w of CTA z owns 16-row block w * Z + z, so every
+// CTA carries the same number of blocks (+- 1) - the other side is streamed through shared memory in 64-row chunks (18 KB instead of
+// 74 - 166 KB: shared memory no longer bounds residency) and each chunk is consumed in sub-chunks of 8 NT keys by a loop that
+// stays in the instruction caches (as attn_bwd_fused).
+constexpr int TC = 64;      // rows of the streamed side per staged chunk
+
+// rows [kc, kc + TC) of the concatenated [prefix ; own] keys -> Ks / Vs (padded rows); rows >= n are zero-filled
+__device__ __forceinline__ void stage_kv_chunk_async(const AttnFwd& a, int b, int h, int kc, bf16* Ks, bf16* Vs, int tid, int nthreads) {
+    const int n1 = a.n1, n = a.n1 + a.n2;
+    for (int i = tid; i < TC * 8; i += nthreads) {
+        const int r = i >> 3, c = i & 7, j = kc + r;
+        const bool ok = j < n, prefix = j < n1;
+        const long row = ok ? (prefix ? (long)b * n1 + j : (long)b * a.n2 + (j - n1)) : 0;
+        const bf16* kg = (prefix ? a.k1 + row * a.ld1 : a.k2 + row * a.ld2) + h * D + c * 8;
+        const bf16* vg = (prefix ? a.v1 + row * a.ld1 : a.v2 + row * a.ld2) + h * D + c * 8;
+        const int bytes = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(Ks + r * LDS + c * 8)), "l"(kg), "r"(bytes) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(Vs + r * LDS + c * 8)), "l"(vg), "r"(bytes) : "memory");
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(WARPS * 32, 3)
+attn_bwd_rows_tiled(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx, float* __restrict__ delta) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const AttnFwd& a = gr.f;
+    const int h = blockIdx.x, b = blockIdx.y, z = blockIdx.z, Z = gridDim.z;
+    const int n1 = a.n1, n = a.n1 + a.n2, n_pad = (n + 63) & ~63;
+    bf16* Ks = reinterpret_cast<bf16*>(smem);
+    bf16* Vs = Ks + (size_t)TC * LDS;
+    float* madd = reinterpret_cast<float*>(Vs + (size_t)TC * LDS);
+    __shared__ float wred[2][WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    for (int j = tid; j < n_pad; j += WARPS * 32) {
+        float m = 0.f;
+        if (j >= n) m = NEG_BIG;
+        else if (a.key_mask && j >= n1) m = (1.0f - (float)a.key_mask[(long)b * a.n2 + (j - n1)]) * -10000.0f;
+        madd[j] = m;
+    }
+    const Adapt ad = load_adapt(a, b);
+    const int r0 = (warp * Z + z) * 16;          // this warp's 16 query rows
+    const bool active = r0 < a.Lq;
+    uint32_t qa[4][4], doa[4][4];
+    float dl[2] = {0.f, 0.f}, lse[2] = {0.f, 0.f};
+    if (active) {
+        load_a_bf16(a.q + (long)b * a.Lq * a.ldq + h * D, a.ldq, r0, a.Lq, lane, qa);
+        load_a_f32(gr.dout + (long)b * a.Lq * gr.lddo + h * D, gr.lddo, r0, a.Lq, lane, doa, ctx + (long)b * a.Lq * ldctx + h * D, ldctx, dl);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            dl[hh] = quad_sum(dl[hh]);
+            const int row = r0 + g + 8 * hh;
+            lse[hh] = (row < a.Lq) ? a.lse[((long)b * a.nh + h) * a.Lq + row] : 0.f;
+        }
+    }
+    float dw0 = 0.f, dw1 = 0.f;
+    float dq[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+    // pass 0 (adaptive scaling only): delta consistent with this kernel's own dP (see attn_bwd_fused); pass 1: dS, dQ, dW0 / dW1
+    for (int pass = (ad.split >= 0) ? 0 : 1; pass < 2; ++pass) {
+        float acc[2] = {0.f, 0.f};
+        for (int kc = 0; kc < n_pad; kc += TC) {
+            __syncthreads();                     // the previous chunk has been consumed (first trip: madd is complete)
+            stage_kv_chunk_async(a, b, h, kc, Ks, Vs, tid, WARPS * 32);
+            cp_async_wait_all();
+            __syncthreads();
+            if (!active) continue;
+#pragma unroll 1
+            for (int sub = 0; sub < TC; sub += 8 * NT) {
+                float s[NT][4], dp[NT][4];
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+                    s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+                    dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+                }
+                mma_a_bt_t<NT>(s, qa, Ks, sub, lane);
+                mma_a_bt_t<NT>(dp, doa, Vs, sub, lane);
+                if (pass == 0) {
+                    consistent_delta<NT>(a, ad, s, dp, madd, lse, kc + sub, r0, g, t, n1, n, a.Lq, b, h, acc);
+                    continue;
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int col = kc + sub + nt * 8 + 2 * t + (e & 1);
+                        const int row = r0 + g + 8 * (e >> 1);
+                        const int j2 = col - n1;
+                        const float f = afactor(ad, row, j2);
+                        const float sraw = s[nt][e] * a.scale;
+                        const float p = (row < a.Lq) ? __expf(sraw * f + madd[col] - lse[e >> 1]) : 0.f;
+                        float dpe = dp[nt][e];
+                        if (a.drop.thresh) dpe *= drop_mult(a.drop, (uint32_t)((((long)b * a.nh + h) * a.Lq + row) * n + col));
+                        const float ds = p * (dpe - dl[e >> 1]);
+                        if (ad.split >= 0 && j2 >= ad.split && col < n) {
+                            if (row >= ad.split) dw1 = fmaf(ds, sraw, dw1);
+                            else if (row >= ad.row_lo) dw0 = fmaf(ds, sraw, dw0);
+                        }
+                        s[nt][e] = ds * f;
+                    }
+                }
+                uint32_t da[NT / 2][4];
+                acc_to_a_t<NT>(s, da);
+                mma_p_b_t<NT>(dq, da, Ks, sub, lane);
+            }
+        }
+        if (pass == 0 && active) {
+            dl[0] = quad_sum(acc[0]);
+            dl[1] = quad_sum(acc[1]);
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int row = r0 + g + 8 * hh;
+            if (row < a.Lq) {
+                if (t == 0) delta[((long)b * a.nh + h) * a.Lq + row] = dl[hh];      // read by the keys pass
+                const long off = ((long)b * a.Lq + row) * gr.ldd + h * D;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+                    *reinterpret_cast<uint32_t*>(gr.dq + off + nt * 8 + 2 * t) =
+                        pack_bf16x2(dq[nt][2 * hh] * a.scale, dq[nt][2 * hh + 1] * a.scale);
+            }
+        }
+    }
+    if (a.sep_idx) {
+        dw0 = warp_sum(dw0);
+        dw1 = warp_sum(dw1);
+        if (lane == 0) { wred[0][warp] = dw0; wred[1][warp] = dw1; }
+        __syncthreads();
+        if (tid == 0) {
+            float s0 = 0.f, s1 = 0.f;
+            for (int w = 0; w < WARPS; ++w) { s0 += wred[0][w]; s1 += wred[1][w]; }
+            const float w0 = *a.w0, w1 = *a.w1;      // torch.clamp passes the gradient at both (inclusive) bounds
+            if (w0 >= 0.f && w0 <= 0.5f) atomicAdd(gr.dw0, s0);
+            if (w1 >= 0.5f && w1 <= 1.0f) atomicAdd(gr.dw1, s1);
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+attn_bwd_keys_tiled(const AttnBwd gr, const float* __restrict__ delta) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const AttnFwd& a = gr.f;
+    const int h = blockIdx.x, b = blockIdx.y, z = blockIdx.z, Z = gridDim.z;
+    const int n1 = a.n1, n2 = a.n2, n = n1 + n2, Lq = a.Lq, Lq_pad = (Lq + 63) & ~63;
+    bf16* Qs = reinterpret_cast<bf16*>(smem);
+    bf16* Os = Qs + (size_t)TC * LDS;
+    float* lse_s = reinterpret_cast<float*>(Os + (size_t)TC * LDS);
+    float* dl_s = lse_s + Lq_pad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    for (int r = tid; r < Lq_pad; r += WARPS * 32) {
+        lse_s[r] = (r < Lq) ? a.lse[((long)b * a.nh + h) * Lq + r] : 0.f;
+        dl_s[r] = (r < Lq) ? delta[((long)b * a.nh + h) * Lq + r] : 0.f;
+    }
+    const Adapt ad = load_adapt(a, b);
+    const int j0 = (warp * Z + z) * 16;          // this warp's 16 keys
+    const bool active = j0 < n;
+    // the block's 16 keys may straddle the prefix / own boundary: fragments are gathered row by row
+    uint32_t ka[4][4], va[4][4];
+    float madd[2] = {NEG_BIG, NEG_BIG};
+    int j2v[2] = {0, 0};
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int j = j0 + g + 8 * hh;
+        const bool ok = j < n, prefix = j < n1;
+        const long row = ok ? (prefix ? (long)b * n1 + j : (long)b * n2 + (j - n1)) : 0;
+        const bf16* kr = (prefix ? a.k1 + row * a.ld1 : a.k2 + row * a.ld2) + h * D;
+        const bf16* vr = (prefix ? a.v1 + row * a.ld1 : a.v2 + row * a.ld2) + h * D;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            ka[ks][hh] = ok ? *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 2 * t) : 0u;
+            ka[ks][hh + 2] = ok ? *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 2 * t + 8) : 0u;
+            va[ks][hh] = ok ? *reinterpret_cast<const uint32_t*>(vr + ks * 16 + 2 * t) : 0u;
+            va[ks][hh + 2] = ok ? *reinterpret_cast<const uint32_t*>(vr + ks * 16 + 2 * t + 8) : 0u;
+        }
+        j2v[hh] = j - n1;
+        if (ok) madd[hh] = (a.key_mask && !prefix) ? (1.0f - (float)a.key_mask[(long)b * n2 + (j - n1)]) * -10000.0f : 0.f;
+    }
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+        dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+    }
+    const bf16* qbase = a.q + (long)b * Lq * a.ldq + h * D;
+    const float* dobase = gr.dout + (long)b * Lq * gr.lddo + h * D;
+    for (int rc = 0; rc < Lq_pad; rc += TC) {
+        __syncthreads();                         // the previous chunk has been consumed (first trip: lse_s / dl_s are complete)
+        const int rows = min(TC, Lq - rc);
+        stage_bf16_async(Qs, qbase + (long)rc * a.ldq, a.ldq, rows, TC, tid, WARPS * 32);
+        stage_f32_as_bf16(Os, dobase + (long)rc * gr.lddo, gr.lddo, rows, TC, tid, WARPS * 32);
+        cp_async_wait_all();
+        __syncthreads();
+        if (!active) continue;
+#pragma unroll 1
+        for (int sub = 0; sub < TC; sub += 8 * NT) {
+            float st[NT][4], dpt[NT][4];
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+                dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+            }
+            mma_a_bt_t<NT>(st, ka, Qs, sub, lane);
+            mma_a_bt_t<NT>(dpt, va, Os, sub, lane);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int r = rc + sub + nt * 8 + 2 * t + (e & 1);      // query row (column of the transposed tile)
+                    const int hh = e >> 1;                                  // key row g / g + 8
+                    const float f = afactor(ad, r, j2v[hh]);
+                    const float p = (r < Lq) ? __expf(st[nt][e] * a.scale * f + madd[hh] - lse_s[r]) : 0.f;
+                    float mult = 1.f;
+                    if (a.drop.thresh)
+                        mult = drop_mult(a.drop, (uint32_t)((((long)b * a.nh + h) * Lq + r) * n + (j0 + g + 8 * hh)));
+                    const float ds = p * (dpt[nt][e] * mult - dl_s[r]);
+                    dpt[nt][e] = p * mult;    // dropped P^T
+                    st[nt][e] = ds * f;       // dS^T * f
+                }
+            }
+            uint32_t pa[NT / 2][4], da[NT / 2][4];
+            acc_to_a_t<NT>(dpt, pa);
+            acc_to_a_t<NT>(st, da);
+            mma_p_b_t<NT>(dv, pa, Os, sub, lane);
+            mma_p_b_t<NT>(dk, da, Qs, sub, lane);
+        }
+    }
+    if (!active) return;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int j = j0 + g + 8 * hh;
+        if (j >= n) continue;
+        if (j < n1) {
+            const long off = ((long)b * n1 + j) * gr.ldd1 + h * D;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                *reinterpret_cast<float2*>(gr.dk1 + off + nt * 8 + 2 * t) = make_float2(dk[nt][2 * hh] * a.scale, dk[nt][2 * hh + 1] * a.scale);
+                *reinterpret_cast<float2*>(gr.dv1 + off + nt * 8 + 2 * t) = make_float2(dv[nt][2 * hh], dv[nt][2 * hh + 1]);
+            }
+        } else {
+            const long row = (long)b * n2 + (j - n1);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                float k0 = dk[nt][2 * hh] * a.scale, k1 = dk[nt][2 * hh + 1] * a.scale;
+                float v0 = dv[nt][2 * hh], v1 = dv[nt][2 * hh + 1];
+                if (gr.dk2_add) {
+                    const float2 ak = *reinterpret_cast<const float2*>(gr.dk2_add + row * gr.ldadd + h * D + nt * 8 + 2 * t);
+                    const float2 av = *reinterpret_cast<const float2*>(gr.dv2_add + row * gr.ldadd + h * D + nt * 8 + 2 * t);
+                    k0 += ak.x; k1 += ak.y; v0 += av.x; v1 += av.y;
+                }
+                *reinterpret_cast<uint32_t*>(gr.dk2 + row * gr.ldd + h * D + nt * 8 + 2 * t) = pack_bf16x2(k0, k1);
+                *reinterpret_cast<uint32_t*>(gr.dv2 + row * gr.ldd + h * D + nt * 8 + 2 * t) = pack_bf16x2(v0, v1);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ backward, one kernel
 // Both passes in ONE CTA per (head, sample) when P and dS of the whole (head, sample) fit in shared memory (bf16,
 // [Lq][n]): phase A = the rows pass above (warp per 16 query rows: S, dP, P, dS, dQ, dW0/dW1) which also leaves P (with
@@ -937,6 +1200,20 @@ int launch_attention_bwd(const AttnBwd& g, const bf16* ctx, long ldctx, float* d
             B2_LAUNCHED();
             return 0;
         }
+    }
+    static int tiled = -1;     // B200MART_ATTN_TILED=0: the resident two-pass kernels (one CTA per (head, sample)) instead of the tiled ones
+    if (tiled < 0) { const char* e = getenv("B200MART_ATTN_TILED"); tiled = e ? atoi(e) : 1; }
+    if (tiled) {
+        const int lq_pad = (a.Lq + 63) & ~63;
+        const int zr = ((a.Lq + 15) / 16 + WARPS - 1) / WARPS, zk = ((a.n1 + a.n2 + 15) / 16 + WARPS - 1) / WARPS;
+        const size_t sm_r = (size_t)2 * TC * LDS * 2 + (size_t)n_pad * 4, sm_k = (size_t)2 * TC * LDS * 2 + (size_t)2 * lq_pad * 4;
+        B2_TRY(set_smem(attn_bwd_rows_tiled<4>, sm_r));
+        attn_bwd_rows_tiled<4><<<dim3(a.nh, a.B, zr), WARPS * 32, sm_r, s>>>(g, ctx, ldctx, delta);
+        B2_LAUNCHED();
+        B2_TRY(set_smem(attn_bwd_keys_tiled<4>, sm_k));
+        attn_bwd_keys_tiled<4><<<dim3(a.nh, a.B, zk), WARPS * 32, sm_k, s>>>(g, delta);
+        B2_LAUNCHED();
+        return 0;
     }
     const size_t smem1 = (size_t)2 * n_pad * LDS * 2 + (size_t)n_pad * 4;
     B2_TRY(set_smem(attn_bwd_rows_mma, smem1));
