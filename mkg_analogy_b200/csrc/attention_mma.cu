@@ -113,6 +113,9 @@ __device__ __forceinline__ void stage_bf16_async(bf16* dst, const bf16* src, lon
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // dO (fp32, global) -> bf16 rows in shared memory, and delta[r] = sum_d dO[r][d] * O[r][d] (O = forward context, bf16) in
 // fp32.  16 consecutive lanes cover one row (4 columns each); loads are issued four rows ahead of their use.
 __device__ __forceinline__ void stage_do_delta(bf16* dst, float* delta_s, const float* dsrc, long ldd, const bf16* osrc, long ldo, int rows,
@@ -689,9 +692,8 @@ attn_bwd_rows_tiled(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx, 
     const AttnFwd& a = gr.f;
     const int h = blockIdx.x, b = blockIdx.y, z = blockIdx.z, Z = gridDim.z;
     const int n1 = a.n1, n = a.n1 + a.n2, n_pad = (n + 63) & ~63;
-    bf16* Ks = reinterpret_cast<bf16*>(smem);
-    bf16* Vs = Ks + (size_t)TC * LDS;
-    float* madd = reinterpret_cast<float*>(Vs + (size_t)TC * LDS);
+    bf16* KV = reinterpret_cast<bf16*>(smem);                  // two stages of [K chunk ; V chunk]
+    float* madd = reinterpret_cast<float*>(KV + (size_t)4 * TC * LDS);
     __shared__ float wred[2][WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     for (int j = tid; j < n_pad; j += WARPS * 32) {
@@ -722,12 +724,22 @@ attn_bwd_rows_tiled(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx, 
     // pass 0 (adaptive scaling only): delta consistent with this kernel's own dP (see attn_bwd_fused); pass 1: dS, dQ, dW0 / dW1
     for (int pass = (ad.split >= 0) ? 0 : 1; pass < 2; ++pass) {
         float acc[2] = {0.f, 0.f};
-        for (int kc = 0; kc < n_pad; kc += TC) {
-            __syncthreads();                     // the previous chunk has been consumed (first trip: madd is complete)
-            stage_kv_chunk_async(a, b, h, kc, Ks, Vs, tid, WARPS * 32);
-            cp_async_wait_all();
-            __syncthreads();
-            if (!active) continue;
+        __syncthreads();                         // both stages are free (first pass: madd is complete)
+        stage_kv_chunk_async(a, b, h, 0, KV, KV + (size_t)TC * LDS, tid, WARPS * 32);
+        cp_async_commit();
+        for (int kc = 0, it = 0; kc < n_pad; kc += TC, ++it) {
+            const bf16* Ks = KV + (size_t)(it & 1) * 2 * TC * LDS;
+            const bf16* Vs = Ks + (size_t)TC * LDS;
+            if (kc + TC < n_pad) {               // the next chunk streams in under this chunk's products
+                bf16* Kn = KV + (size_t)((it + 1) & 1) * 2 * TC * LDS;
+                stage_kv_chunk_async(a, b, h, kc + TC, Kn, Kn + (size_t)TC * LDS, tid, WARPS * 32);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();                     // chunk `it` has landed for every thread
+            if (active) {
 #pragma unroll 1
             for (int sub = 0; sub < TC; sub += 8 * NT) {
                 float s[NT][4], dp[NT][4];
@@ -766,6 +778,8 @@ attn_bwd_rows_tiled(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx, 
                 acc_to_a_t<NT>(s, da);
                 mma_p_b_t<NT>(dq, da, Ks, sub, lane);
             }
+            }
+            __syncthreads();                     // stage it & 1 may be refilled (by the trip after next)
         }
         if (pass == 0 && active) {
             dl[0] = quad_sum(acc[0]);
@@ -801,16 +815,15 @@ attn_bwd_rows_tiled(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx, 
     }
 }
 
-template <int NT>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 attn_bwd_keys_tiled(const AttnBwd gr, const float* __restrict__ delta) {
     extern __shared__ __align__(16) uint8_t smem[];
     const AttnFwd& a = gr.f;
     const int h = blockIdx.x, b = blockIdx.y, z = blockIdx.z, Z = gridDim.z;
     const int n1 = a.n1, n2 = a.n2, n = n1 + n2, Lq = a.Lq, Lq_pad = (Lq + 63) & ~63;
-    bf16* Qs = reinterpret_cast<bf16*>(smem);
-    bf16* Os = Qs + (size_t)TC * LDS;
-    float* lse_s = reinterpret_cast<float*>(Os + (size_t)TC * LDS);
+    bf16* QO = reinterpret_cast<bf16*>(smem);                  // two stages of [Q chunk ; dO chunk (bf16)]
+    float* lse_s = reinterpret_cast<float*>(QO + (size_t)4 * TC * LDS);
     float* dl_s = lse_s + Lq_pad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     for (int r = tid; r < Lq_pad; r += WARPS * 32) {
@@ -849,14 +862,29 @@ attn_bwd_keys_tiled(const AttnBwd gr, const float* __restrict__ delta) {
     }
     const bf16* qbase = a.q + (long)b * Lq * a.ldq + h * D;
     const float* dobase = gr.dout + (long)b * Lq * gr.lddo + h * D;
-    for (int rc = 0; rc < Lq_pad; rc += TC) {
-        __syncthreads();                         // the previous chunk has been consumed (first trip: lse_s / dl_s are complete)
+    const bf16* do16 = gr.dout16 ? gr.dout16 + (long)b * Lq * gr.lddo16 + h * D : nullptr;
+    // chunk rc -> stage st: Q rows through cp.async; dO through cp.async when the caller supplied a bf16 copy, else converted here
+    auto stage = [&](int rc, int st) {
+        bf16* Qn = QO + (size_t)st * 2 * TC * LDS;
+        bf16* On = Qn + (size_t)TC * LDS;
         const int rows = min(TC, Lq - rc);
-        stage_bf16_async(Qs, qbase + (long)rc * a.ldq, a.ldq, rows, TC, tid, WARPS * 32);
-        stage_f32_as_bf16(Os, dobase + (long)rc * gr.lddo, gr.lddo, rows, TC, tid, WARPS * 32);
-        cp_async_wait_all();
-        __syncthreads();
-        if (!active) continue;
+        stage_bf16_async(Qn, qbase + (long)rc * a.ldq, a.ldq, rows, TC, tid, WARPS * 32);
+        if (do16) stage_bf16_async(On, do16 + (long)rc * gr.lddo16, gr.lddo16, rows, TC, tid, WARPS * 32);
+        else stage_f32_as_bf16(On, dobase + (long)rc * gr.lddo, gr.lddo, rows, TC, tid, WARPS * 32);
+        cp_async_commit();
+    };
+    stage(0, 0);
+    for (int rc = 0, it = 0; rc < Lq_pad; rc += TC, ++it) {
+        const bf16* Qs = QO + (size_t)(it & 1) * 2 * TC * LDS;
+        const bf16* Os = Qs + (size_t)TC * LDS;
+        if (rc + TC < Lq_pad) {                  // the next chunk streams in under this chunk's products
+            stage(rc + TC, (it + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();                         // chunk `it` has landed for every thread (first trip: lse_s / dl_s are complete)
+        if (active) {
 #pragma unroll 1
         for (int sub = 0; sub < TC; sub += 8 * NT) {
             float st[NT][4], dpt[NT][4];
@@ -889,6 +917,8 @@ attn_bwd_keys_tiled(const AttnBwd gr, const float* __restrict__ delta) {
             mma_p_b_t<NT>(dv, pa, Os, sub, lane);
             mma_p_b_t<NT>(dk, da, Qs, sub, lane);
         }
+        }
+        __syncthreads();                         // stage it & 1 may be refilled (by the trip after next)
     }
     if (!active) return;
 #pragma unroll
@@ -915,6 +945,113 @@ attn_bwd_keys_tiled(const AttnBwd gr, const float* __restrict__ delta) {
                 }
                 *reinterpret_cast<uint32_t*>(gr.dk2 + row * gr.ldd + h * D + nt * 8 + 2 * t) = pack_bf16x2(k0, k1);
                 *reinterpret_cast<uint32_t*>(gr.dv2 + row * gr.ldd + h * D + nt * 8 + 2 * t) = pack_bf16x2(v0, v1);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ forward, tiled
+// attn_fwd_mma for long sequences (Lq > 128): warp w of CTA z owns 16-row block w * Z + z and the keys stream through two 64-key
+// stages (as attn_bwd_rows_tiled) instead of being resident (418 keys = 129 KB = one CTA per SM).
+__global__ void __launch_bounds__(WARPS * 32, 3)
+attn_fwd_tiled(const AttnFwd a, float* __restrict__ out32) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    pdl_wait();
+    pdl_launch_dependents();
+    const int h = blockIdx.x, b = blockIdx.y, z = blockIdx.z, Z = gridDim.z;
+    const int n1 = a.n1, n = a.n1 + a.n2, n_pad = (n + 63) & ~63;
+    bf16* KV = reinterpret_cast<bf16*>(smem);
+    float* madd = reinterpret_cast<float*>(KV + (size_t)4 * TC * LDS);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    stage_kv_chunk_async(a, b, h, 0, KV, KV + (size_t)TC * LDS, tid, WARPS * 32);
+    cp_async_commit();
+    for (int j = tid; j < n_pad; j += WARPS * 32) {
+        float m = 0.f;
+        if (j >= n) m = NEG_BIG;
+        else if (a.key_mask && j >= n1) m = (1.0f - (float)a.key_mask[(long)b * a.n2 + (j - n1)]) * -10000.0f;
+        madd[j] = m;
+    }
+    const Adapt ad = load_adapt(a, b);
+    const int r0 = (warp * Z + z) * 16;
+    const bool active = r0 < a.Lq;
+    uint32_t qa[4][4];
+    if (active) load_a_bf16(a.q + (long)b * a.Lq * a.ldq + h * D, a.ldq, r0, a.Lq, lane, qa);
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float mrun[2] = {NEG_BIG, NEG_BIG}, lrun[2] = {0.f, 0.f};
+    for (int kc = 0, it = 0; kc < n_pad; kc += TC, ++it) {
+        const bf16* Ks = KV + (size_t)(it & 1) * 2 * TC * LDS;
+        const bf16* Vs = Ks + (size_t)TC * LDS;
+        if (kc + TC < n_pad) {
+            bf16* Kn = KV + (size_t)((it + 1) & 1) * 2 * TC * LDS;
+            stage_kv_chunk_async(a, b, h, kc + TC, Kn, Kn + (size_t)TC * LDS, tid, WARPS * 32);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();                         // chunk `it` has landed (first trip: madd is complete)
+        if (active) {
+            float s[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+            mma_a_bt(s, qa, Ks, 0, lane);
+            float mx[2] = {NEG_BIG, NEG_BIG};
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = kc + nt * 8 + 2 * t + (e & 1);
+                    const int row = r0 + g + 8 * (e >> 1);
+                    const float v = s[nt][e] * a.scale * afactor(ad, row, col - n1) + madd[col];
+                    s[nt][e] = v;
+                    mx[e >> 1] = fmaxf(mx[e >> 1], v);
+                }
+            }
+            float alpha[2];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const float mnew = fmaxf(mrun[hh], quad_max(mx[hh]));
+                alpha[hh] = __expf(mrun[hh] - mnew);
+                mrun[hh] = mnew;
+                lrun[hh] *= alpha[hh];
+            }
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float p = __expf(s[nt][e] - mrun[e >> 1]);
+                    lrun[e >> 1] += p;
+                    if (a.drop.thresh) {   // dropout on the normalised probabilities: the row sum stays undropped
+                        const int col = kc + nt * 8 + 2 * t + (e & 1);
+                        const int row = r0 + g + 8 * (e >> 1);
+                        p *= drop_mult(a.drop, (uint32_t)((((long)b * a.nh + h) * a.Lq + row) * n + col));
+                    }
+                    s[nt][e] = p;
+                }
+                o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0]; o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
+            }
+            uint32_t pa[4][4];
+            acc_to_a(s, pa);
+            mma_p_b(o, pa, Vs, 0, lane);
+        }
+        __syncthreads();                         // stage it & 1 may be refilled
+    }
+    if (!active) return;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int row = r0 + g + 8 * hh;
+        const float l = quad_sum(lrun[hh]);
+        const float inv = 1.0f / l;
+        if (row < a.Lq) {
+            if (t == 0 && a.lse) a.lse[((long)b * a.nh + h) * a.Lq + row] = mrun[hh] + __logf(l);
+            const long off = ((long)b * a.Lq + row) * a.ldo + h * D;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float x0 = o[nt][2 * hh] * inv, x1 = o[nt][2 * hh + 1] * inv;
+                *reinterpret_cast<uint32_t*>(a.out + off + nt * 8 + 2 * t) = pack_bf16x2(x0, x1);
+                if (out32) *reinterpret_cast<float2*>(out32 + off + nt * 8 + 2 * t) = make_float2(x0, x1);
             }
         }
     }
@@ -1162,6 +1299,16 @@ int launch_attention_fwd(const AttnFwd& a, float* out32, cudaStream_t s) {
     const int n_pad = (a.n1 + a.n2 + 63) & ~63;
     const size_t smem = (size_t)2 * n_pad * LDS * 2 + (size_t)n_pad * 4;
     if (a.Lq > 64) {
+        static int ftiled = -1;    // B200MART_ATTN_FWD_TILED=0: the resident kernel for every shape
+        if (ftiled < 0) { const char* e = getenv("B200MART_ATTN_FWD_TILED"); ftiled = e ? atoi(e) : 1; }
+        if (ftiled && a.Lq > 128) {     // more than one round of 8 x 16 rows: rows split over grid.z, keys streamed in 64-key chunks
+            const int zf = ((a.Lq + 15) / 16 + WARPS - 1) / WARPS;
+            const size_t sm = (size_t)4 * TC * LDS * 2 + (size_t)n_pad * 4;
+            B2_TRY(set_smem(attn_fwd_tiled, sm));
+            CUDA_TRY(launch_pdl(attn_fwd_tiled, dim3(a.nh, a.B, zf), dim3(WARPS * 32), sm, s, a, out32));
+            B2_LAUNCHED();
+            return 0;
+        }
         B2_TRY(set_smem(attn_fwd_mma<8>, smem));
         CUDA_TRY(launch_pdl(attn_fwd_mma<8>, dim3(a.nh, a.B), dim3(8 * 32), smem, s, a, out32));
     } else {
@@ -1206,12 +1353,23 @@ int launch_attention_bwd(const AttnBwd& g, const bf16* ctx, long ldctx, float* d
     if (tiled) {
         const int lq_pad = (a.Lq + 63) & ~63;
         const int zr = ((a.Lq + 15) / 16 + WARPS - 1) / WARPS, zk = ((a.n1 + a.n2 + 15) / 16 + WARPS - 1) / WARPS;
-        const size_t sm_r = (size_t)2 * TC * LDS * 2 + (size_t)n_pad * 4, sm_k = (size_t)2 * TC * LDS * 2 + (size_t)2 * lq_pad * 4;
+        const size_t sm_r = (size_t)4 * TC * LDS * 2 + (size_t)n_pad * 4, sm_k = (size_t)4 * TC * LDS * 2 + (size_t)2 * lq_pad * 4;
+        B2_CHECK(!g.dout16 || g.lddo16 % 8 == 0, "attention bwd: the bf16 copy of dout needs a leading dimension that is a multiple of 8");
         B2_TRY(set_smem(attn_bwd_rows_tiled<4>, sm_r));
         attn_bwd_rows_tiled<4><<<dim3(a.nh, a.B, zr), WARPS * 32, sm_r, s>>>(g, ctx, ldctx, delta);
         B2_LAUNCHED();
-        B2_TRY(set_smem(attn_bwd_keys_tiled<4>, sm_k));
-        attn_bwd_keys_tiled<4><<<dim3(a.nh, a.B, zk), WARPS * 32, sm_k, s>>>(g, delta);
+        static int kv = -1;    // B200MART_ATTN_KEYS_VARIANT: 0 = 32-row inner chunks, 2 CTAs / SM (222 registers); 1 (default) = 16-row chunks, 3 CTAs / SM; 2 = 32-row, 3 CTAs
+        if (kv < 0) { const char* e = getenv("B200MART_ATTN_KEYS_VARIANT"); kv = e ? atoi(e) : 1; }
+        if (kv == 1) {
+            B2_TRY(set_smem(attn_bwd_keys_tiled<2, 3>, sm_k));
+            attn_bwd_keys_tiled<2, 3><<<dim3(a.nh, a.B, zk), WARPS * 32, sm_k, s>>>(g, delta);
+        } else if (kv == 2) {
+            B2_TRY(set_smem(attn_bwd_keys_tiled<4, 3>, sm_k));
+            attn_bwd_keys_tiled<4, 3><<<dim3(a.nh, a.B, zk), WARPS * 32, sm_k, s>>>(g, delta);
+        } else {
+            B2_TRY(set_smem(attn_bwd_keys_tiled<4, 2>, sm_k));
+            attn_bwd_keys_tiled<4, 2><<<dim3(a.nh, a.B, zk), WARPS * 32, sm_k, s>>>(g, delta);
+        }
         B2_LAUNCHED();
         return 0;
     }

@@ -83,6 +83,7 @@ int launch_attention_fwd(const AttnFwd& a, float* out32, cudaStream_t s);
 struct AttnBwd {
     AttnFwd f;                    // same inputs as forward (out unused)
     const float* dout; long lddo; // fp32 gradient wrt context [B*Lq, nh*64]
+    const bf16* dout16 = nullptr; long lddo16 = 0;   // optional bf16 copy of dout (same layout): lets the tiled keys pass stream it with cp.async
     bf16* dq; bf16* dk2; bf16* dv2; long ldd;      // bf16 grads (same column layout as q/k2/v2)
     const float* dk2_add; const float* dv2_add; long ldadd;  // optional fp32 extra gradient added into dk2/dv2
     float* dk1; float* dv1; long ldd1;             // fp32 grads wrt the prefix keys/values (plain store), when n1 > 0

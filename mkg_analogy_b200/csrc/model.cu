@@ -1328,11 +1328,11 @@ extern "C" int32_t b200mart_stack_backward(b200mart_stack* st, const b200mart_bu
             B2_TRY(launch_layernorm_bwd(st->s32b, a.x1, a.mean1, a.rstd1, r.p32(p.ln1_w), nullptr, nullptr, 0, st->s32a, st->s16a,
                                         r.g32(p.ln1_w), r.g32(p.ln1_b), r.g32(p.o_b), M, H, s, nodrop, make_drop(io->p_hidden, io->seed, 2 + 3 * i)));
             B2_TRY(r.grad_weight(M, H, H, st->s16a, H, a.ctx16, H, p.o_w, -1));
-            B2_TRY(r.grad_input(M, H, H, st->s16a, p.o_w, nullptr, 0, nullptr, st->s32b, nullptr));            // d ctx
+            B2_TRY(r.grad_input(M, H, H, st->s16a, p.o_w, nullptr, 0, nullptr, st->s32b, st->dX16));          // d ctx (+ bf16 copy; dX16 is free here)
             AttnBwd ab{};
             stack_attn(st, io, r, i, ab.f);
             if (io->split) { ab.dw0 = r.g32(p.aw0); ab.dw1 = r.g32(p.aw1); }
-            ab.dout = st->s32b; ab.lddo = H;
+            ab.dout = st->s32b; ab.lddo = H; ab.dout16 = st->dX16; ab.lddo16 = H;
             ab.dq = st->sdqkv16; ab.dk2 = st->sdqkv16 + H; ab.dv2 = st->sdqkv16 + 2 * H; ab.ldd = 3 * H;
             B2_TRY(launch_attention_bwd(ab, a.ctx16, H, st->delta, s));
             B2_TRY(r.grad_weight(M, 3 * H, H, st->sdqkv16, 3 * H, a.u16, H, p.qkv_w, p.qkv_b));
@@ -1354,11 +1354,11 @@ extern "C" int32_t b200mart_stack_backward(b200mart_stack* st, const b200mart_bu
         B2_TRY(launch_layernorm_bwd(st->s32a, a.x1, a.mean2, a.rstd2, r.p32(p.ln2_w), st->dX, nullptr, 0, st->s32b, st->s16a,
                                     r.g32(p.ln2_w), r.g32(p.ln2_b), r.g32(p.o_b), M, H, s, nodrop, make_drop(io->p_hidden, io->seed, 2 + 3 * i)));
         B2_TRY(r.grad_weight(M, H, H, st->s16a, H, a.ctx16, H, p.o_w, -1));
-        B2_TRY(r.grad_input(M, H, H, st->s16a, p.o_w, nullptr, 0, nullptr, st->s32a, nullptr));
+        B2_TRY(r.grad_input(M, H, H, st->s16a, p.o_w, nullptr, 0, nullptr, st->s32a, st->dX16));    // d ctx (+ bf16 copy; dX16 is free here)
         AttnBwd ab{};
         stack_attn(st, io, r, i, ab.f);
         if (io->split) { ab.dw0 = r.g32(p.aw0); ab.dw1 = r.g32(p.aw1); }
-        ab.dout = st->s32a; ab.lddo = H;
+        ab.dout = st->s32a; ab.lddo = H; ab.dout16 = st->dX16; ab.lddo16 = H;
         ab.dq = st->sdqkv16; ab.dk2 = st->sdqkv16 + H; ab.dv2 = st->sdqkv16 + 2 * H; ab.ldd = 3 * H;
         B2_TRY(launch_attention_bwd(ab, a.ctx16, H, st->delta, s));
         B2_TRY(r.grad_weight(M, 3 * H, H, st->sdqkv16, 3 * H, a.u16, H, p.qkv_w, p.qkv_b));
