@@ -9,12 +9,12 @@ timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_$tag.txt 2>
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$tag.txt 2>&1; echo "smoke rc $? : $(tail -1 gpurun_out/smoke_$tag.txt)"
 timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_${tag}_base.json 2> gpurun_out/bench_${tag}_base.err; echo "bench base rc $?"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_${tag}_reference.json 2> gpurun_out/bench_${tag}_reference.err; echo "bench reference rc $?"
-for c in large flava vilt; do
+for c in large flava vilt visualbert; do
   timeout 400 python bench.py --config $c --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_${tag}_$c.json 2> gpurun_out/bench_${tag}_$c.err; echo "bench $c rc $?"
 done
 python - <<PY
 import json
-for c in ("base", "reference", "large", "flava", "vilt"):
+for c in ("base", "reference", "large", "flava", "vilt", "visualbert"):
     try:
         d = json.load(open("gpurun_out/bench_${tag}_%s.json" % c))
         r = d.get("roofline") or {}
