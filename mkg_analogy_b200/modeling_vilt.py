@@ -9,7 +9,8 @@ modeling_vilt.py:370-375).  Embeddings and the MLM head are thin PyTorch plumbin
   * image embeddings (:112-196, :214-243): conv patches + cls, position embeddings, the SAME modules for both images;
     sequence = [text, image 1, image 2]; modality embeddings 0 (text) / 1 (image).
     With the all-ones `pixel_mask` the reference builds when none is given (:834-835), its bilinear position-embedding resize
-    is the identity and its `torch.multinomial` "selection" is a random PERMUTATION of the patches of each image; self-attention
+    is the identity for images of `config.image_size` (other sizes: the same `interpolate(..., align_corners=True)` to the
+    actual patch grid) and its `torch.multinomial` "selection" is a random PERMUTATION of the patches of each image; self-attention
     is permutation-equivariant and only the text rows are read (:950), so WITHOUT `sep_idx` (pre-training) the permutation can be
     omitted with equal outputs.  WITH `sep_idx` (fine-tuning) the adaptive scaling indexes rows `img_length+1 : s'` and columns
     `>= s'` of the [text ; image] sequence (:373-375), which reaches image-token columns: the reference then scales a RANDOM
@@ -72,7 +73,16 @@ class _Embeddings(nn.Module):
 
     def image_tokens(self, pixels):
         x = B.patch_embed(pixels, self.patch_embeddings.projection)                      # (B, g*g, H), row-major patches; im2col + tcgen05 GEMM
-        x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1) + self.position_embeddings
+        pos = self.position_embeddings
+        g_cfg = int(round((pos.shape[1] - 1) ** 0.5))
+        gh, gw = pixels.shape[2] // self.patch_embeddings.projection.kernel_size[0], pixels.shape[3] // self.patch_embeddings.projection.kernel_size[1]
+        if (gh, gw) != (g_cfg, g_cfg):
+            # images of another size than config.image_size: the patch position table is resized bilinearly to the actual patch
+            # grid (modeling_vilt.py:121-136; with the all-ones pixel_mask the valid extent is the whole grid)
+            sp = pos[:, 1:].transpose(1, 2).reshape(1, pos.shape[2], g_cfg, g_cfg)
+            sp = F.interpolate(sp, size=(gh, gw), mode="bilinear", align_corners=True)
+            pos = torch.cat([pos[:, :1], sp.flatten(2).transpose(1, 2)], dim=1)
+        x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1) + pos
         return self.dropout(x)
 
 

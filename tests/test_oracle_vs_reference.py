@@ -125,3 +125,80 @@ def test_preln_stack_oracle_matches_live_reference_encoder_other_seed():
         ref = enc(x, attention_mask=(1.0 - mask[:, None, None, :].float()) * -10000.0, sep_idx=sep).last_hidden_state
         mine = O.preln_stack(dict(enc.state_dict()), x, 2, attention_mask=mask, sep_split=sep[:, 2], row_lo=1)
     assert torch.allclose(mine, ref, atol=1e-5, rtol=1e-5)
+
+
+def test_vilt_dropin_resizes_position_table_like_the_reference_for_other_image_sizes():
+    """Images of another size than config.image_size: the reference resizes the patch position table bilinearly to the actual patch
+    grid (modeling_vilt.py:121-136).  ViltKGC's plumbing with the ORACLE encoder injected (test infrastructure) == the live reference
+    on the text rows (which do not depend on the reference's random patch order), for a 3 x 3 grid under a 2 x 2 config."""
+    from transformers import ViltConfig
+    from mkg_analogy_b200.modeling_vilt import ViltKGC
+    Vm = RL.load_vilt()
+    kw = dict(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, vocab_size=300, image_size=64,
+              patch_size=32)
+    torch.manual_seed(7)
+    ref = Vm.ViltForMaskedLM(ViltConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **kw)).eval()
+    with torch.no_grad():
+        for n, prm in ref.named_parameters():
+            prm.normal_(1.0 if ("norm" in n.lower() and n.endswith("weight")) else 0.0, 0.05)
+    ref.mlm_score.decoder.weight = ref.vilt.embeddings.text_embeddings.word_embeddings.weight
+    m = ViltKGC(device="cpu", **kw)
+    missing, unexpected = m.load_state_dict(ref.state_dict(), strict=False)
+    assert not unexpected, unexpected
+    m.tie_weights()
+
+    class OracleEncoder(torch.nn.Module):
+        def __init__(self, st):
+            super().__init__()
+            self.st = st
+
+        def forward(self, x, attention_mask=None, sep_idx=None, row_lo=1):
+            return O.preln_stack(dict(self.st.named_parameters()), x, 2, attention_mask=attention_mask,
+                                 sep_split=None if sep_idx is None else sep_idx[:, 2], row_lo=row_lo)
+    m.vilt.encoder = OracleEncoder(m.vilt.encoder)
+    m.eval()
+    g = torch.Generator().manual_seed(8)
+    Bn, L = 2, 24
+    ids = torch.randint(5, 300, (Bn, L), generator=g)
+    mask = torch.ones(Bn, L, dtype=torch.long)
+    px = torch.randn(Bn, 2, 3, 96, 96, generator=g)             # 3 x 3 patches per image; the table holds 2 x 2
+    sep = torch.full((Bn, 6), L, dtype=torch.long)              # no-op split (the reference cannot run without one)
+    with torch.no_grad():
+        torch.manual_seed(1)
+        ro = ref(input_ids=ids, attention_mask=mask, token_type_ids=torch.zeros_like(ids), pixel_values=px, sep_idx=sep.clone(), return_dict=True)
+        mo = m(input_ids=ids, attention_mask=mask, token_type_ids=torch.zeros_like(ids), pixel_values=px, sep_idx=sep)
+    assert torch.allclose(mo[1], ro[1], atol=2e-5, rtol=1e-4)
+    assert torch.allclose(mo[0].logits, ro[0].logits, atol=2e-5, rtol=1e-4)
+
+
+def test_postln_stack_oracle_matches_live_reference_visual_bert_encoder_other_seed():
+    Vb = RL.load_visual_bert()
+    cfg = RL.visual_bert_config(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                                hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    torch.manual_seed(6)
+    enc = Vb.VisualBertEncoder(cfg).eval()
+    x = torch.randn(2, 27, 128)
+    mask = torch.ones(2, 27, dtype=torch.long)
+    mask[1, 20:] = 0
+    img_length = 6
+    sep = torch.zeros(2, 6, dtype=torch.long)
+    sep[:, 2] = torch.tensor([15, 11])                       # already shifted by img_length, as VisualBertModel passes it
+    with torch.no_grad():
+        ref = enc(x, attention_mask=(1.0 - mask[:, None, None, :].float()) * -10000.0, sep_idx=sep.clone(), img_length=img_length,
+                  return_dict=True).last_hidden_state
+        mine = O.postln_stack(dict(enc.state_dict()), x, 2, attention_mask=mask, sep_split=sep[:, 2], row_lo=img_length + 1)
+    assert torch.allclose(mine, ref, atol=1e-5, rtol=1e-5)
+
+
+def test_visual_bert_dropin_loads_under_the_reference_litmodel_name_check():
+    """TransformerLitModel keys the rel_idx / q_head_idx / a_head_idx shift on the CLASS NAME (lit_models/transformer.py:98): the drop-in
+    must be called VisualBertKGC, as models/model.py:13 names the reference class."""
+    from mkg_analogy_b200.modeling_visual_bert import VisualBertKGC
+    m = VisualBertKGC(device="cpu", vocab_size=120, hidden_size=128, num_hidden_layers=1, num_attention_heads=2, intermediate_size=256,
+                      visual_embedding_dim=32, max_position_embeddings=40)
+    assert "VisualBertKGC" in str(type(m))
+    ref_names = set(RL.load_visual_bert().VisualBertForMaskedLM(RL.visual_bert_config(
+        vocab_size=120, hidden_size=128, num_hidden_layers=1, num_attention_heads=2, intermediate_size=256, visual_embedding_dim=32,
+        max_position_embeddings=40)).state_dict())
+    mine = set(m.state_dict())
+    assert mine == ref_names, (sorted(mine ^ ref_names)[:8])
