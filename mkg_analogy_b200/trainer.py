@@ -24,6 +24,34 @@ def linear_warmup_lr(step, total_steps, base_lr, warmup_ratio):
     return base_lr * max(0.0, (total_steps - step) / max(1.0, total_steps - warm))
 
 
+def step_salt(salt0, t):
+    """32-bit word XORed into every dropout site seed at optimizer step t (b200mart_set_step_block): hash32 of
+    (salt0 + 0x9E3779B9 t), the same finaliser the kernels use for the masks (csrc/common.cuh)."""
+    x = (salt0 + 0x9E3779B9 * t) & 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x7FEB352D) & 0xFFFFFFFF
+    x ^= x >> 15
+    x = (x * 0x846CA68B) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+def pack_step_block(block, salt, lr, t, betas=(0.9, 0.999)):
+    """Fill a 4 x int32 host tensor with {uint32 salt, float lr, float 1 - beta1^t, float 1 - beta2^t} (include/b200mart.h)."""
+    block[0] = salt - (1 << 32) if salt >= (1 << 31) else salt
+    f = block.view(torch.float32)
+    f[1], f[2], f[3] = lr, 1.0 - betas[0] ** t, 1.0 - betas[1] ** t
+    return block
+
+
+def pick_bucket(L, buckets):
+    """Smallest sequence-length bucket that holds L (graph replay pads the text rows up to it)."""
+    for b in buckets:
+        if b >= L:
+            return b
+    raise ValueError(f"sequence length {L} exceeds the largest graph bucket {buckets[-1]}")
+
+
 def bucket_bounds(n, buckets, align=1024):
     """Contiguous [start, end) ranges covering a flat buffer of n elements in about `buckets` aligned pieces."""
     per = (n + buckets - 1) // max(1, buckets)
@@ -347,17 +375,8 @@ class MartTrainer:
             k = t % len(self._step_host)
             if self._step_ev[k] is not None:
                 self._step_ev[k].synchronize()            # the copy that last read this pinned slot has run (never blocks in practice)
-            h = self._step_host[k]
-            x = (self._salt0 + 0x9E3779B9 * t) & 0xFFFFFFFF     # 32-bit mix of (seed, step): the salt of this step's dropout masks
-            x ^= x >> 16
-            x = (x * 0x7FEB352D) & 0xFFFFFFFF
-            x ^= x >> 15
-            x = (x * 0x846CA68B) & 0xFFFFFFFF
-            x ^= x >> 16
-            self.last_salt = x
-            h[0] = x - (1 << 32) if x >= (1 << 31) else x
-            hf = h.view(torch.float32)
-            hf[1], hf[2], hf[3] = lr, 1.0 - 0.9 ** t, 1.0 - 0.999 ** t
+            self.last_salt = step_salt(self._salt0, t)            # this step's dropout masks
+            h = pack_step_block(self._step_host[k], self.last_salt, lr, t)
             self._step_dev.copy_(h, non_blocking=True)
             self._step_ev[k] = torch.cuda.Event()
             self._step_ev[k].record()
@@ -400,9 +419,7 @@ class MartTrainer:
     def _train_step_graphed(self, batch):
         g = self._graphs
         B, L = batch["input_ids"].shape
-        Lb = next((b for b in g["buckets"] if b >= L), None)
-        if Lb is None:
-            raise ValueError(f"sequence length {L} exceeds the largest graph bucket {g['buckets'][-1]}")
+        Lb = pick_bucket(L, g["buckets"])
         keys = tuple(sorted(k for k in batch if k in BATCH_KEYS and k != "pixel_idx"))
         ent = g["entries"].get((B, Lb, keys))
         if ent is None:

@@ -33,7 +33,7 @@ def test_ctypes_structs_match_header_field_order():
         header = fh.read()
     for cname, cls in (("b200mart_gemm_desc", _lib.GemmDesc), ("b200mart_model_desc", _lib.ModelDesc),
                        ("b200mart_buffers", _lib.Buffers), ("b200mart_batch", _lib.Batch), ("b200mart_head", _lib.Head),
-                       ("b200mart_attn_desc", _lib.AttnDesc)):
+                       ("b200mart_attn_desc", _lib.AttnDesc), ("b200mart_stack_desc", _lib.StackDesc), ("b200mart_stack_io", _lib.StackIO)):
         body = re.search(r"typedef struct " + cname + r" \{(.*?)\} " + cname + ";", header, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []
@@ -219,7 +219,7 @@ def test_layer_extents_partition_the_encoder():
             assert inside == [], p.name
 
 
-@pytest.mark.parametrize("family", ["vilt", "flava"])
+@pytest.mark.parametrize("family", ["vilt", "flava", "visual_bert"])
 def test_from_pretrained_local_checkpoint(tmp_path, family):
     """`model_class.from_pretrained(path[, config=config])` (MarT/main.py:119-125) on a local HF-layout directory:
     config.json + safetensors / .bin weights load by name, absent tensors are initialised HF-style, the decoder stays tied."""
@@ -231,6 +231,10 @@ def test_from_pretrained_local_checkpoint(tmp_path, family):
         from transformers import ViltConfig as Cfg
         from mkg_analogy_b200.modeling_vilt import ViltKGC as M
         head = "mlm_score."
+    elif family == "visual_bert":
+        from transformers import VisualBertConfig as Cfg
+        from mkg_analogy_b200.modeling_visual_bert import VisualBertKGC as M
+        head = "cls."
     else:
         from transformers import FlavaConfig as Cfg
         from mkg_analogy_b200.modeling_flava import FlavaKGC as M
@@ -247,7 +251,30 @@ def test_from_pretrained_local_checkpoint(tmp_path, family):
         assert torch.equal(sd[k], v), k
     assert all(k.startswith(head) or "position_ids" in k for k in m.loading_info["missing_keys"]), m.loading_info
     assert m.get_output_embeddings().weight is m.get_input_embeddings().weight
-    dense = sd[head + "transform.dense.weight"]
-    assert 0.01 < dense.std().item() < 0.03 and sd[head + "transform.dense.bias"].abs().max().item() == 0.0
+    tr = head + ("predictions.transform.dense." if family == "visual_bert" else "transform.dense.")
+    dense = sd[tr + "weight"]
+    assert 0.01 < dense.std().item() < 0.03 and sd[tr + "bias"].abs().max().item() == 0.0
     m2 = M.from_pretrained(str(tmp_path), config=Cfg(**c["cfg"]), device="cpu")     # explicit config, as main.py:123 passes it
     assert torch.equal(m2.state_dict()[next(iter(body))], body[next(iter(body))])
+
+
+def test_step_block_packing_and_bucket_choice():
+    """Host side of the graph-replay mode: the 16-byte step block {uint32 salt, float lr, float 1 - beta1^t,
+    float 1 - beta2^t} as include/b200mart.h lays it out, the salt = the kernels' hash32 finaliser (the oracle restates it), buckets."""
+    import struct
+    from mkg_analogy_b200.trainer import pack_step_block, pick_bucket, step_salt
+
+    def h32(x):
+        x ^= x >> 16
+        x = (x * 0x7feb352d) & 0xFFFFFFFF
+        x ^= x >> 15
+        x = (x * 0x846ca68b) & 0xFFFFFFFF
+        return x ^ (x >> 16)
+    salts = [step_salt(1234567, t) for t in range(1, 200)]
+    assert salts[0] == h32((1234567 + 0x9E3779B9) & 0xFFFFFFFF) and len(set(salts)) == len(salts) and all(0 <= x < 2 ** 32 for x in salts)
+    blk = pack_step_block(torch.zeros(4, dtype=torch.int32), 0xDEADBEEF, 3e-5, 7)
+    salt, lr, bc1, bc2 = struct.unpack("<Ifff", blk.numpy().tobytes())
+    assert salt == 0xDEADBEEF and abs(lr - 3e-5) < 1e-12 and abs(bc1 - (1 - 0.9 ** 7)) < 1e-7 and abs(bc2 - (1 - 0.999 ** 7)) < 1e-9
+    assert [pick_bucket(L, (32, 64, 96, 128)) for L in (1, 32, 33, 64, 100, 128)] == [32, 32, 64, 64, 128, 128]
+    with pytest.raises(ValueError):
+        pick_bucket(129, (32, 64, 96, 128))
