@@ -445,6 +445,9 @@ class MartTrainer:
                 with torch.cuda.graph(graph):
                     ent["loss"] = self._step_body(ent["static"], step, lr)
                 ent["graph"] = graph
+                # the captured kernels carry raw pointers into the engine's workspace: keep that allocation alive for as long as
+                # the graph exists (a later, larger bucket makes the engine allocate a new workspace and drop its own reference)
+                ent["ws"] = self.engine.ws
             ent["graph"].replay()
         ent["n"] += 1
         if self.status_every and self.steps_done % self.status_every == 0:
