@@ -339,6 +339,11 @@ class MartTrainer:
     def check_status(self):
         """Raise IndexError (as the reference's indexing would) when a device-side guard fired since the last forward."""
         flags = self.engine.status()
+        if self._graphs is not None:          # graphs of other buckets run on the workspace they were captured on (status word first)
+            for ent in self._graphs["entries"].values():
+                ws = ent.get("ws")
+                if ws is not None and ws is not self.engine.ws:
+                    flags |= int(ws[:4].view(torch.int32).item()) & 15
         if flags:
             names = [n for bit, n in ((1, "token id / score-head column out of range"), (2, "token type out of range"),
                                       (4, "a row without exactly one [MASK]"), (8, "label or relaxation position out of range"))
