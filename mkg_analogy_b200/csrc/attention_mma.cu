@@ -685,8 +685,8 @@ __device__ __forceinline__ void stage_kv_chunk_async(const AttnFwd& a, int b, in
     }
 }
 
-template <int NT>
-__global__ void __launch_bounds__(WARPS * 32, 3)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 attn_bwd_rows_tiled(const AttnBwd gr, const bf16* __restrict__ ctx, long ldctx, float* __restrict__ delta) {
     extern __shared__ __align__(16) uint8_t smem[];
     const AttnFwd& a = gr.f;
@@ -953,7 +953,8 @@ attn_bwd_keys_tiled(const AttnBwd gr, const float* __restrict__ delta) {
 // ------------------------------------------------------------------------------------------ forward, tiled
 // attn_fwd_mma for long sequences (Lq > 128): warp w of CTA z owns 16-row block w * Z + z and the keys stream through two 64-key
 // stages (as attn_bwd_rows_tiled) instead of being resident (418 keys = 129 KB = one CTA per SM).
-__global__ void __launch_bounds__(WARPS * 32, 3)
+template <int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 attn_fwd_tiled(const AttnFwd a, float* __restrict__ out32) {
     extern __shared__ __align__(16) uint8_t smem[];
     pdl_wait();
@@ -1284,6 +1285,13 @@ int check_attn(const AttnFwd& a) {
     return 0;
 }
 
+// B200MART_ATTN_OCC4: the tiled forward / rows kernels compiled for 4 CTAs per SM (128 registers, a few spilled words) instead of 3
+int tiled_occ4() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("B200MART_ATTN_OCC4"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
     B2_CHECK(bytes <= 227 * 1024, "attention: needs %zu bytes of shared memory (> 227 KB)", bytes);
@@ -1304,8 +1312,13 @@ int launch_attention_fwd(const AttnFwd& a, float* out32, cudaStream_t s) {
         if (ftiled && a.Lq > 128) {     // more than one round of 8 x 16 rows: rows split over grid.z, keys streamed in 64-key chunks
             const int zf = ((a.Lq + 15) / 16 + WARPS - 1) / WARPS;
             const size_t sm = (size_t)4 * TC * LDS * 2 + (size_t)n_pad * 4;
-            B2_TRY(set_smem(attn_fwd_tiled, sm));
-            CUDA_TRY(launch_pdl(attn_fwd_tiled, dim3(a.nh, a.B, zf), dim3(WARPS * 32), sm, s, a, out32));
+            if (tiled_occ4()) {
+                B2_TRY(set_smem(attn_fwd_tiled<4>, sm));
+                CUDA_TRY(launch_pdl(attn_fwd_tiled<4>, dim3(a.nh, a.B, zf), dim3(WARPS * 32), sm, s, a, out32));
+            } else {
+                B2_TRY(set_smem(attn_fwd_tiled<3>, sm));
+                CUDA_TRY(launch_pdl(attn_fwd_tiled<3>, dim3(a.nh, a.B, zf), dim3(WARPS * 32), sm, s, a, out32));
+            }
             B2_LAUNCHED();
             return 0;
         }
@@ -1355,8 +1368,13 @@ int launch_attention_bwd(const AttnBwd& g, const bf16* ctx, long ldctx, float* d
         const int zr = ((a.Lq + 15) / 16 + WARPS - 1) / WARPS, zk = ((a.n1 + a.n2 + 15) / 16 + WARPS - 1) / WARPS;
         const size_t sm_r = (size_t)4 * TC * LDS * 2 + (size_t)n_pad * 4, sm_k = (size_t)4 * TC * LDS * 2 + (size_t)2 * lq_pad * 4;
         B2_CHECK(!g.dout16 || g.lddo16 % 8 == 0, "attention bwd: the bf16 copy of dout needs a leading dimension that is a multiple of 8");
-        B2_TRY(set_smem(attn_bwd_rows_tiled<4>, sm_r));
-        attn_bwd_rows_tiled<4><<<dim3(a.nh, a.B, zr), WARPS * 32, sm_r, s>>>(g, ctx, ldctx, delta);
+        if (tiled_occ4()) {
+            B2_TRY(set_smem(attn_bwd_rows_tiled<4, 4>, sm_r));
+            attn_bwd_rows_tiled<4, 4><<<dim3(a.nh, a.B, zr), WARPS * 32, sm_r, s>>>(g, ctx, ldctx, delta);
+        } else {
+            B2_TRY(set_smem(attn_bwd_rows_tiled<4, 3>, sm_r));
+            attn_bwd_rows_tiled<4, 3><<<dim3(a.nh, a.B, zr), WARPS * 32, sm_r, s>>>(g, ctx, ldctx, delta);
+        }
         B2_LAUNCHED();
         static int kv = -1;    // B200MART_ATTN_KEYS_VARIANT: 0 = 32-row inner chunks, 2 CTAs / SM (222 registers); 1 (default) = 16-row chunks, 3 CTAs / SM; 2 = 32-row, 3 CTAs
         if (kv < 0) { const char* e = getenv("B200MART_ATTN_KEYS_VARIANT"); kv = e ? atoi(e) : 1; }
