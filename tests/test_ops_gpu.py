@@ -49,7 +49,7 @@ def _ref_attention(q, k, v, heads, scale, key_mask=None, sep=None, w0=None, w1=N
     return (P @ hs(vv)).permute(0, 2, 1, 3).reshape(B, Lq, HD), torch.logsumexp(S, -1)
 
 
-@pytest.mark.parametrize("B,L,heads", [(3, 24, 2), (4, 64, 12), (2, 128, 4)])
+@pytest.mark.parametrize("B,L,heads", [(3, 24, 2), (4, 64, 12), (2, 128, 4), (2, 200, 2), (1, 418, 3)])   # > 128: the tiled kernels
 def test_text_attention_fwd_bwd(B, L, heads):
     from mkg_analogy_b200 import ops
     HD = heads * 64
