@@ -1,4 +1,4 @@
-"""Plug the B200 encoder stack into the reference's FLAVA / ViLT models.
+"""Plug the B200 encoder stack into the reference's FLAVA / ViLT / VisualBERT models.
 
 The reference's `FlavaKGC` / `ViltKGC` (MarT/models/model.py:27-37) are HF-style modules whose encoders are
 `FlavaEncoder` (modeling_flava.py:668-722; three instances: image, text, multimodal) and `ViltEncoder`
@@ -6,7 +6,8 @@ The reference's `FlavaKGC` / `ViltKGC` (MarT/models/model.py:27-37) are HF-style
 already constructed reference model by `EncoderAdapter`, an `EncoderStack` that keeps the encoder's call signature and
 return type (`encoder(hidden_states, attention_mask=<additive 4-D mask>, ..., sep_idx=..., img_length=...)` ->
 `BaseModelOutput`-like), its `state_dict()` names and its weights.  Embeddings, poolers, projections and the MLM head stay the
-reference's own PyTorch modules (they run on the GPU as they do today); only the encoders change.
+reference's own PyTorch modules (they run on the GPU as they do today); only the encoders change.  `VisualBertEncoder`
+(modeling_visual_bert.py:424-488, post-LayerNorm BERT blocks carrying the reference's `adaptive_weight`s) is swapped the same way.
 
     model = FlavaKGC.from_pretrained(...)          # reference code, unchanged
     model = swap_encoders(model).cuda()
@@ -68,9 +69,28 @@ def _is_preln_encoder(m):
         hasattr(layers[0], "layernorm_after") and hasattr(layers[0], "intermediate")
 
 
+def _is_postln_encoder(m):
+    """A VisualBertEncoder: `.layer` ModuleList of BERT blocks whose self-attention carries the reference's adaptive weights
+    (a plain BertEncoder has none and is left alone)."""
+    layers = getattr(m, "layer", None)
+    if not (isinstance(layers, nn.ModuleList) and len(layers) > 0):
+        return False
+    att = getattr(getattr(layers[0], "attention", None), "self", None)
+    return att is not None and hasattr(att, "adaptive_weight") and hasattr(layers[0].attention, "output") and \
+        hasattr(layers[0].attention.output, "LayerNorm") and hasattr(layers[0], "intermediate") and hasattr(layers[0].output, "LayerNorm")
+
+
 def adapter_from(encoder, device=None):
-    """EncoderAdapter with the shapes and weights of a reference FlavaEncoder / ViltEncoder instance."""
+    """EncoderAdapter with the shapes and weights of a reference FlavaEncoder / ViltEncoder / VisualBertEncoder instance."""
     l0 = encoder.layer[0]
+    if _is_postln_encoder(encoder):
+        att = l0.attention.self
+        ad = EncoderAdapter(att.query.in_features, len(encoder.layer), att.num_attention_heads, l0.intermediate.dense.out_features,
+                            eps=l0.output.LayerNorm.eps, act="gelu", hidden_dropout=l0.output.dropout.p, attn_dropout=att.dropout.p,
+                            device=device if device is not None else att.query.weight.device, post_ln=True)
+        ad.load_state_dict(encoder.state_dict(), strict=True)
+        ad.train(encoder.training)
+        return ad
     att = l0.attention.attention
     hidden = att.query.in_features
     act = l0.intermediate.intermediate_act_fn
@@ -84,10 +104,10 @@ def adapter_from(encoder, device=None):
 
 
 def swap_encoders(model, device=None):
-    """Replace every FlavaEncoder / ViltEncoder inside `model` (in place) by an EncoderAdapter carrying its weights.
+    """Replace every FlavaEncoder / ViltEncoder / VisualBertEncoder inside `model` (in place) by an EncoderAdapter carrying its weights.
     Returns the model; `model.state_dict()` keys are unchanged."""
     for name, child in list(model.named_children()):
-        if _is_preln_encoder(child):
+        if _is_preln_encoder(child) or _is_postln_encoder(child):
             setattr(model, name, adapter_from(child, device))
         else:
             swap_encoders(child, device)

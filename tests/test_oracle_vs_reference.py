@@ -202,3 +202,19 @@ def test_visual_bert_dropin_loads_under_the_reference_litmodel_name_check():
         max_position_embeddings=40)).state_dict())
     mine = set(m.state_dict())
     assert mine == ref_names, (sorted(mine ^ ref_names)[:8])
+
+
+def test_swap_encoders_into_reference_visual_bert_model():
+    """swap_encoders on the REAL reference VisualBertModel: the post-LN encoder (with its adaptive weights) is replaced by an
+    EncoderAdapter(post_ln=True), state_dict keys and values are preserved.  (CPU: structure only; numerics: tests/test_visual_bert_gpu.py.)"""
+    from mkg_analogy_b200.accelerate import EncoderAdapter, swap_encoders
+    Vb = RL.load_visual_bert()
+    cfg = RL.visual_bert_config(vocab_size=200, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                                visual_embedding_dim=32, max_position_embeddings=40)
+    model = Vb.VisualBertModel(cfg, add_pooling_layer=False)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    swap_encoders(model, device="cpu")
+    adapters = [m for m in model.modules() if isinstance(m, EncoderAdapter)]
+    assert len(adapters) == 1 and not any(type(m).__name__ == "VisualBertEncoder" for m in model.modules())
+    after = model.state_dict()
+    assert set(after) == set(before) and all(torch.equal(after[k], before[k]) for k in before)

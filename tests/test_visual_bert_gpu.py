@@ -73,6 +73,21 @@ def test_postln_stack_training_dropout_matches_oracle_masks():
         assert rel(named[n].grad, P[n].grad) <= 6e-2, n
 
 
+def test_encoder_adapter_keeps_the_visual_bert_encoder_call_signature():
+    """EncoderAdapter(post_ln=True) called the way VisualBertModel calls its encoder (additive 4-D mask, sep_idx already shifted,
+    img_length; modeling_visual_bert.py:895-905) reproduces the reference encoder's golden output."""
+    from mkg_analogy_b200.accelerate import EncoderAdapter
+    c = torch.load(os.path.join(GOLD, "postln_stack.pt"), weights_only=False)
+    ad = EncoderAdapter(128, 3, 2, 256, eps=1e-12, act="gelu", device="cuda", post_ln=True)
+    ad.load_state_dict(c["params"], strict=True)
+    ad.eval()
+    ext = (1.0 - c["mask"][:, None, None, :].float()) * -10000.0
+    with torch.no_grad():
+        out = ad(c["x"].cuda(), attention_mask=ext.cuda(), head_mask=[None] * 3, sep_idx=c["sep"].cuda(), img_length=c["row_lo"] - 1,
+                 return_dict=True)
+    assert rel(out.last_hidden_state.cpu(), c["y"]) <= 2e-2 and rel(out[0].cpu(), c["y"]) <= 2e-2
+
+
 def test_visual_bert_dropin_vs_reference_golden():
     from mkg_analogy_b200.modeling_visual_bert import VisualBertKGC
     c = torch.load(os.path.join(GOLD, "visual_bert_tiny.pt"), weights_only=False)
